@@ -1,0 +1,220 @@
+/* b200render.h -- C ABI of the B200-native renderer.
+ *
+ * Drop-in boundary for the two hot paths of fznsakib/Computer-Graphics
+ * (citations are file:line in that repository):
+ *
+ *   RT   raytracer/Source/skeleton.cpp   Draw :104-169 -> ClosestIntersection
+ *        :263-363 -> DirectLight :366-415        (per-pixel primary + shadow rays)
+ *   RAST rasteriser/Source/skeleton.cpp  Draw :203-308 -> DrawPolygon :420-431
+ *        -> VertexShader :510-522 -> ComputePolygonRows :433-498
+ *        -> DrawPolygonRows :500-508 -> PixelShader :559-672
+ *        -> calculateIllumination :674-688, then the post pass :283-307.
+ *
+ * The reference's entry point is `void Draw(screen*)` with every other input a
+ * file-scope global (RT :56-60, RAST :30-86).  This ABI carries what those
+ * globals carry, as plain pointers and sizes.  All structs are byte-compatible
+ * with the reference's own types so a caller can pass `&triangles[0]` directly.
+ *
+ * Conventions
+ *   - every function returns B200_OK (0) or a negative B200_E* code; nothing
+ *     ever calls exit();
+ *   - "host" entry points take HOST pointers and do the H2D/D2H copies
+ *     themselves; "_device" entry points take DEVICE pointers (they may be peer
+ *     mappings of another GPU's memory -- the kernels store bands straight
+ *     through them) and enqueue on the context's stream without synchronising;
+ *   - one context per GPU and per host thread; calls on a context serialise;
+ *   - there is no CPU fallback: without a CUDA device b200_init fails.
+ */
+#ifndef B200RENDER_H
+#define B200RENDER_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_EINVAL (-1) /* bad argument (null pointer, bad size, bad band) */
+#define B200_ECUDA (-2)  /* CUDA runtime error; see b200_last_error()        */
+#define B200_ENOMEM (-3) /* device or pinned-host allocation failed          */
+#define B200_ENODEV (-4) /* no usable CUDA device (no CPU fallback exists)   */
+
+/* index_out value for "no hit" (RT) / "no opaque fragment" (RAST is -1). */
+#define B200_INDEX_MISS INT32_MIN
+
+/* ---- types (byte-compatible with the reference) ---------------------------*/
+
+/* raytracer/Source/TestModelH.h:80-115 `class Triangle`: 76 bytes. */
+typedef struct rt_triangle {
+  float v0[4], v1[4], v2[4];
+  float normal[4]; /* w = 1.0 in the reference (TestModelH.h:104)            */
+  float color[3];
+} rt_triangle;
+
+/* raytracer/Source/TestModelH.h:14-77 `class Sphere`: 44 bytes. */
+typedef struct rt_sphere {
+  float radius, radius_squared;
+  float centre[3], color[3];
+  float normal[3]; /* never initialised nor read by the reference            */
+} rt_sphere;
+
+/* rasteriser/Source/TestModelH.h:13-42 `class Triangle`: 84 bytes. */
+typedef struct rast_triangle {
+  float v0[4], v1[4], v2[4];
+  float normal[4];
+  float color[3];  /* color[0] < 0 marks a shadow-volume triangle (:1705)    */
+  int32_t texture; /* only 0 (untextured) is supported                       */
+  int32_t index;   /* only read by the reference's texture code              */
+} rast_triangle;
+
+/* RT globals cameraPos / focalLength / R (skeleton.cpp:56-60) and RAST globals
+ * cameraPos / focalLength / R (skeleton.cpp:30-35), plus the resolution that
+ * the reference fixes with #define SCREEN_WIDTH / SCREEN_HEIGHT. */
+typedef struct camera_t {
+  float pos[4];
+  float focal;
+  float R[16]; /* column-major, R[4*c + r] == glm R[c][r]                    */
+  int32_t width, height;
+} camera_t;
+
+/* raytracer `struct Light` (skeleton.cpp:47-50). */
+typedef struct light_t {
+  float pos[4];
+  float colour[3];
+} light_t;
+
+/* rasteriser light globals: sceneCoordinatesLightPos (or, for the clipped-list
+ * entry, the camera-space lightPos), lightPower, indirectLightPowerPerArea
+ * (skeleton.cpp:51-54; steady-state indirect is 0.2, see :585). */
+typedef struct rast_light_t {
+  float pos[4];
+  float power[3];
+  float indirect[3];
+} rast_light_t;
+
+typedef struct b200_ctx b200_ctx;
+
+/* ---- context ---------------------------------------------------------------*/
+
+/* Creates a context on CUDA device `device` (one process per GPU: pass
+ * LOCAL_RANK).  Fails with B200_ENODEV when there is no GPU. */
+int b200_init(int device, b200_ctx **out);
+void b200_destroy(b200_ctx *ctx);
+/* Human-readable text of the last error on this context ("" if none). */
+const char *b200_last_error(const b200_ctx *ctx);
+/* The CUDA stream (cudaStream_t) every call on this context is enqueued on. */
+void *b200_stream(b200_ctx *ctx);
+int b200_synchronize(b200_ctx *ctx);
+
+/* Tunables.  B200_OPT_RT_BRUTEFORCE = 1 switches the raytracer to the
+ * unfiltered kernel that runs the reference arithmetic on every ray/triangle
+ * pair (on-device cross-check of the filtered kernel; results are identical). */
+#define B200_OPT_RT_BRUTEFORCE 1
+#define B200_OPT_RAST_TILE_LOG2 2
+int b200_set_option(b200_ctx *ctx, int option, int value);
+
+/* Counters of the last render on this context. */
+typedef struct b200_stats {
+  uint64_t primary_rays;     /* RT: W * rows * 9                              */
+  uint64_t shadow_rays;      /* RT: primary hits * n_lights                   */
+  uint64_t prim_tests;       /* RT: rays * (n_tris + n_spheres)               */
+  uint64_t kernel_launches;  /* kernels of this library launched by the call  */
+  uint64_t fragments;        /* RAST: fragments shaded or depth-tested        */
+  uint64_t bin_entries;      /* RAST: (tile, triangle) pairs                  */
+  float gpu_ms;              /* device time of the call, CUDA events          */
+} b200_stats;
+int b200_get_stats(b200_ctx *ctx, b200_stats *out);
+
+/* ---- RT: replaces raytracer Draw(screen*) (skeleton.cpp:104-169) -----------*/
+
+/* Host-pointer entry.  Renders rows [0, cam->height).
+ *   rgb_out   W*H*3 floats: the colour the reference hands to PutPixelSDL
+ *             (averageLight, or black), before quantisation.   May be NULL.
+ *   depth_out W*H floats: closestIntersection.distance of the centre sample
+ *             (i = j = 0), +inf on miss.                        May be NULL.
+ *   index_out W*H: centre-sample triangleIndex, or -1 - sphereIndex, or
+ *             B200_INDEX_MISS.                                  May be NULL.
+ */
+int render_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris,
+                    const rt_sphere *spheres, int n_spheres, const camera_t *cam,
+                    const light_t *lights, int n_lights, float *rgb_out, float *depth_out,
+                    int32_t *index_out);
+
+/* Same, but only rows [row_begin, row_end) (one GPU's band); the outputs are
+ * band-sized: (row_end - row_begin) * W pixels. */
+int render_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris,
+                         const rt_sphere *spheres, int n_spheres, const camera_t *cam,
+                         const light_t *lights, int n_lights, int row_begin, int row_end,
+                         float *rgb_out, float *depth_out, int32_t *index_out);
+
+/* Exactly what `Draw(screen*)` leaves in screen->buffer: W*H packed 0x80RRGGBB
+ * with the PutPixelSDL truncation rule (SDLauxiliary.h:149-161). */
+int draw_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres,
+                  int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
+                  uint32_t *argb_out);
+
+/* Device-resident path: upload the scene once, render many times. */
+int rt_upload_scene(b200_ctx *ctx, const rt_triangle *tris, int n_tris,
+                    const rt_sphere *spheres, int n_spheres);
+/* All output pointers are DEVICE pointers addressed as full-frame arrays
+ * (pixel (x, y) at y*W + x); only rows [row_begin, row_end) are written.  Any
+ * of them may be NULL.  Asynchronous on b200_stream(ctx). */
+int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, int n_lights,
+                     int row_begin, int row_end, float *d_rgb, float *d_depth,
+                     int32_t *d_index, uint32_t *d_argb);
+
+/* ---- RAST: replaces rasteriser Draw(screen*) (skeleton.cpp:203-308) --------*/
+
+/* Tier 1: the triangle loop + post pass (skeleton.cpp:243-307) on an
+ * already-clipped list (camera space, w = z/f, in draw order).  light->pos is
+ * the camera-space, rotated `lightPos` (skeleton.cpp:211-212,223).
+ *   rgb_out   W*H*3: colour handed to PutPixelSDL (border pixels stay 0)
+ *   depth_out W*H: depthBuffer (1/z, 0 = empty)
+ *   index_out W*H: index of the opaque triangle owning the pixel, -1 if none
+ */
+int render_raster_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris,
+                          const camera_t *cam, const rast_light_t *light, float *rgb_out,
+                          float *depth_out, int32_t *index_out);
+
+/* Tier 2: the whole Draw on a world-space scene: camera transform, shadow
+ * volumes for `boxes`, rotation, clip-space w, six-plane clip, then tier 1.
+ * light->pos is sceneCoordinatesLightPos (world space). */
+int render_raster(b200_ctx *ctx, const rast_triangle *room, int n_room,
+                  const rast_triangle *boxes, int n_boxes, const camera_t *cam,
+                  const rast_light_t *light, float *rgb_out, float *depth_out,
+                  int32_t *index_out);
+
+/* screen->buffer of the whole rasteriser Draw. */
+int draw_raster(b200_ctx *ctx, const rast_triangle *room, int n_room,
+                const rast_triangle *boxes, int n_boxes, const camera_t *cam,
+                const rast_light_t *light, uint32_t *argb_out);
+
+/* Intermediate buffers of the last render_raster* call, for parity checks
+ * against the reference's file-scope buffers (skeleton.cpp:39-46).  HOST
+ * pointers, any may be NULL: screenBuffer before the in-place shadow darkening,
+ * lowLightBuffer, highLightBuffer (W*H*3 each), shadowBuffer (W*H). */
+int raster_read_buffers(b200_ctx *ctx, float *screen_out, float *low_out, float *high_out,
+                        int32_t *shadow_out);
+/* The clipped list the last render_raster built (tier 2); returns its length
+ * in *n_out, copies min(cap, n) triangles. */
+int raster_read_clipped(b200_ctx *ctx, rast_triangle *out, int cap, int *n_out);
+
+/* Device-resident path. */
+int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris);
+int rast_render_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
+                       int row_begin, int row_end, float *d_rgb, float *d_depth,
+                       int32_t *d_index, uint32_t *d_argb);
+
+/* ---- headless framebuffer (replaces SDL_SaveImage, SDLauxiliary.h:24-53) ---*/
+
+/* Quantises float RGB to 0x80RRGGBB with the PutPixelSDL rule (host helper). */
+void b200_quantise(const float *rgb, size_t n_pixels, uint32_t *argb_out);
+/* Writes a 32-bpp top-down-flipped BMP like SDL_SaveBMP of an ARGB8888 surface. */
+int b200_save_bmp(const char *path, const uint32_t *argb, int width, int height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RENDER_H */

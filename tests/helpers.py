@@ -1,0 +1,205 @@
+"""ctypes/numpy plumbing shared by the tests and bench.py.
+
+Three libraries are wrapped here:
+
+* ``oracle/liboracle.so``      -- the plain-C restatement of the reference (checker)
+* ``oracle/_ref/libref_*.so``  -- the unmodified reference compiled as a library
+                                  (checker; built in the dev container, travels
+                                  to the GPU box as a prebuilt file)
+* the product C ABI (``include/b200render.h``) lives in the package, see
+  ``computer-graphics_b200/__init__.py``.
+
+Nothing here is product code.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+
+INDEX_MISS = -2147483648
+
+RT_TRI = np.dtype([("v0", "<f4", 4), ("v1", "<f4", 4), ("v2", "<f4", 4),
+                   ("normal", "<f4", 4), ("color", "<f4", 3)])
+RT_SPHERE = np.dtype([("radius", "<f4"), ("radius2", "<f4"), ("centre", "<f4", 3),
+                      ("color", "<f4", 3), ("normal", "<f4", 3)])
+RAST_TRI = np.dtype([("v0", "<f4", 4), ("v1", "<f4", 4), ("v2", "<f4", 4),
+                     ("normal", "<f4", 4), ("color", "<f4", 3),
+                     ("texture", "<i4"), ("index", "<i4")])
+assert RT_TRI.itemsize == 76 and RT_SPHERE.itemsize == 44 and RAST_TRI.itemsize == 84
+
+c_f = ctypes.c_float
+c_i = ctypes.c_int
+VP = ctypes.c_void_p
+
+
+def ptr(a):
+    """void* of a numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(VP)
+
+
+def f32(*vals):
+    return np.array(vals, dtype=np.float32)
+
+
+def identity_R():
+    return np.eye(4, dtype=np.float32).reshape(-1).copy()
+
+
+def yaw_R(yaw):
+    """The reference's yaw update (raytracer skeleton.cpp:236-238), column-major."""
+    R = np.eye(4, dtype=np.float32)
+    c, s = np.float32(np.cos(yaw)), np.float32(np.sin(yaw))
+    # R[c][r] in glm = column c, row r ; flat index 4*c + r
+    R[0, 0] = c; R[0, 2] = -s
+    R[2, 0] = s; R[2, 2] = c
+    return R.reshape(-1).copy()
+
+
+# ----------------------------------------------------------------------------
+# oracle (plain C restatement)
+# ----------------------------------------------------------------------------
+_oracle = None
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liboracle.so"])
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".c")]
+        if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+            build_oracle()
+        _oracle = ctypes.CDLL(path)
+    return _oracle
+
+
+def lights_array(lights):
+    """[(pos4, colour3), ...] -> flat float32[7*n]."""
+    out = np.zeros((len(lights), 7), np.float32)
+    for i, (p, c) in enumerate(lights):
+        out[i, :4] = p
+        out[i, 4:] = c
+    return out.reshape(-1)
+
+
+DEFAULT_RT_LIGHTS = [((0, -0.5, -0.7, 1.0), (14, 14, 14))]
+
+
+def oracle_rt_render(W, H, focal, cam, R, lights7, tris, spheres, row0=0, row1=None,
+                     want=("rgb", "dist", "index", "argb")):
+    lib = oracle()
+    row1 = H if row1 is None else row1
+    rgb = np.zeros((H, W, 3), np.float32) if "rgb" in want else None
+    dist = np.zeros((H, W), np.float32) if "dist" in want else None
+    index = np.zeros((H, W), np.int32) if "index" in want else None
+    argb = np.zeros((H, W), np.uint32) if "argb" in want else None
+    counts = np.zeros(2, np.uint64)
+    n_l = len(lights7) // 7
+    rc = lib.oracle_rt_render(c_i(W), c_i(H), c_f(focal), ptr(np.asarray(cam, np.float32)),
+                              ptr(np.asarray(R, np.float32)), ptr(np.asarray(lights7, np.float32)),
+                              c_i(n_l), ptr(tris), c_i(len(tris)), ptr(spheres),
+                              c_i(0 if spheres is None else len(spheres)), c_i(row0), c_i(row1),
+                              ptr(rgb), ptr(dist), ptr(index), ptr(argb), ptr(counts))
+    assert rc == 0
+    return dict(rgb=rgb, dist=dist, index=index, argb=argb, primary=int(counts[0]), shadow=int(counts[1]))
+
+
+# ----------------------------------------------------------------------------
+# compiled reference (oracle/_ref)
+# ----------------------------------------------------------------------------
+def have_ref(name):
+    return os.path.exists(os.path.join(REF_DIR, name))
+
+
+_ref_cache = {}
+
+
+def ref_lib(name):
+    if name not in _ref_cache:
+        _ref_cache[name] = ctypes.CDLL(os.path.join(REF_DIR, name))
+    return _ref_cache[name]
+
+
+def ref_rt_testmodel():
+    lib = ref_lib("libref_rt.so")
+    tris = np.zeros(64, RT_TRI)
+    sph = np.zeros(8, RT_SPHERE)
+    nt, ns = c_i(0), c_i(0)
+    assert lib.ref_rt_load_testmodel(ptr(tris), 64, ptr(sph), 8, ctypes.byref(nt), ctypes.byref(ns)) == 0
+    return tris[:nt.value].copy(), sph[:ns.value].copy()
+
+
+def ref_rt_draw(W, H, focal, cam, R, lights7, tris=None, spheres=None):
+    lib = ref_lib("libref_rt.so")
+    argb = np.zeros((H, W), np.uint32)
+    rgb = np.zeros((H, W, 3), np.float32)
+    rc = lib.ref_rt_draw(c_i(W), c_i(H), c_f(focal), ptr(np.asarray(cam, np.float32)),
+                         ptr(np.asarray(R, np.float32)), ptr(np.asarray(lights7, np.float32)),
+                         c_i(len(lights7) // 7), ptr(tris), c_i(0 if tris is None else len(tris)),
+                         ptr(spheres), c_i(0 if spheres is None else len(spheres)), ptr(argb), ptr(rgb))
+    assert rc == 0
+    return dict(argb=argb, rgb=rgb)
+
+
+def ref_rt_trace(W, H, focal, cam, R, tris=None, spheres=None):
+    lib = ref_lib("libref_rt.so")
+    dist = np.zeros((H, W), np.float32)
+    index = np.zeros((H, W), np.int32)
+    rc = lib.ref_rt_trace(c_i(W), c_i(H), c_f(focal), ptr(np.asarray(cam, np.float32)),
+                          ptr(np.asarray(R, np.float32)), ptr(tris), c_i(0 if tris is None else len(tris)),
+                          ptr(spheres), c_i(0 if spheres is None else len(spheres)), ptr(dist), ptr(index))
+    assert rc == 0
+    return dict(dist=dist, index=index)
+
+
+# ----------------------------------------------------------------------------
+# scene helpers (numpy; independent of both the reference and the product)
+# ----------------------------------------------------------------------------
+def compute_normals(tris):
+    """Triangle::ComputeNormal (raytracer TestModelH.h:96-105) in float32 steps."""
+    v0 = tris["v0"][:, :3]; v1 = tris["v1"][:, :3]; v2 = tris["v2"][:, :3]
+    e1 = (v1 - v0).astype(np.float32)
+    e2 = (v2 - v0).astype(np.float32)
+    # glm::cross(e2, e1)
+    cx = (e2[:, 1] * e1[:, 2]).astype(np.float32) - (e1[:, 1] * e2[:, 2]).astype(np.float32)
+    cy = (e2[:, 2] * e1[:, 0]).astype(np.float32) - (e1[:, 2] * e2[:, 0]).astype(np.float32)
+    cz = (e2[:, 0] * e1[:, 1]).astype(np.float32) - (e1[:, 0] * e2[:, 1]).astype(np.float32)
+    d = ((cx * cx).astype(np.float32) + (cy * cy).astype(np.float32)).astype(np.float32)
+    d = (d + (cz * cz).astype(np.float32)).astype(np.float32)
+    inv = (np.float32(1.0) / np.sqrt(d, dtype=np.float32)).astype(np.float32)
+    tris["normal"][:, 0] = cx * inv
+    tris["normal"][:, 1] = cy * inv
+    tris["normal"][:, 2] = cz * inv
+    tris["normal"][:, 3] = 1.0
+    return tris
+
+
+def random_rt_scene(n_tris, seed, extent=1.0, size=0.6, n_spheres=1):
+    rng = np.random.default_rng(seed)
+    tris = np.zeros(n_tris, RT_TRI)
+    c = rng.uniform(-extent, extent, (n_tris, 3)).astype(np.float32)
+    tris["v0"][:, :3] = c
+    tris["v1"][:, :3] = c + rng.uniform(-size, size, (n_tris, 3)).astype(np.float32)
+    tris["v2"][:, :3] = c + rng.uniform(-size, size, (n_tris, 3)).astype(np.float32)
+    tris["v0"][:, 3] = tris["v1"][:, 3] = tris["v2"][:, 3] = 1.0
+    tris["color"] = rng.uniform(0.15, 0.75, (n_tris, 3)).astype(np.float32)
+    compute_normals(tris)
+    sph = np.zeros(n_spheres, RT_SPHERE)
+    for i in range(n_spheres):
+        r = np.float32(rng.uniform(0.1, 0.4))
+        sph[i]["radius"] = r
+        sph[i]["radius2"] = r * r
+        sph[i]["centre"] = rng.uniform(-0.7, 0.7, 3).astype(np.float32)
+        sph[i]["color"] = rng.uniform(0.15, 0.75, 3).astype(np.float32)
+    return tris, sph
