@@ -1,0 +1,293 @@
+// C ABI of include/b200render.h: context, uploads, host-pointer entry points.
+#include "common.cuh"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+int ctx_fail(b200_ctx *ctx, int code, const char *what, cudaError_t e) {
+  if (ctx) {
+    ctx->err = what ? what : "";
+    if (e != cudaSuccess) {
+      ctx->err += ": ";
+      ctx->err += cudaGetErrorString(e);
+    }
+  }
+  return code;
+}
+
+int ensure(b200_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return B200_OK;
+  if (b.p) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+  }
+  size_t cap = bytes < 256 ? 256 : bytes;
+  cudaError_t e = cudaMalloc(&b.p, cap);
+  if (e != cudaSuccess) { b.p = nullptr; return ctx_fail(ctx, B200_ENOMEM, "cudaMalloc", e); }
+  b.cap = cap;
+  return B200_OK;
+}
+
+static int ensure_pinned(b200_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_cap) return B200_OK;
+  if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_cap = 0; }
+  cudaError_t e = cudaMallocHost(&ctx->pinned, bytes);
+  if (e != cudaSuccess) { ctx->pinned = nullptr; return ctx_fail(ctx, B200_ENOMEM, "cudaMallocHost", e); }
+  ctx->pinned_cap = bytes;
+  return B200_OK;
+}
+
+extern "C" {
+
+int b200_init(int device, b200_ctx **out) {
+  if (!out) return B200_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return B200_ENODEV;
+  if (device < 0 || device >= n) return B200_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return B200_ECUDA;
+  b200_ctx *ctx = new b200_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    delete ctx;
+    return B200_ECUDA;
+  }
+  if (ensure(ctx, ctx->counters, 8 * sizeof(unsigned long long)) != B200_OK) { delete ctx; return B200_ENOMEM; }
+  *out = ctx;
+  return B200_OK;
+}
+
+void b200_destroy(b200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rast_src,
+                    &ctx->rast_setup, &ctx->rast_bins, &ctx->rast_tile_count, &ctx->rast_tile_off,
+                    &ctx->rast_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
+                    &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
+                    &ctx->out_argb, &ctx->counters};
+  for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void *b200_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int b200_synchronize(b200_ctx *ctx) {
+  if (!ctx) return B200_EINVAL;
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_set_option(b200_ctx *ctx, int option, int value) {
+  if (!ctx) return B200_EINVAL;
+  switch (option) {
+    case B200_OPT_RT_BRUTEFORCE: ctx->opt_rt_bruteforce = value != 0; return B200_OK;
+    case B200_OPT_RAST_TILE_LOG2:
+      if (value < 3 || value > 6) return ctx_fail(ctx, B200_EINVAL, "tile log2 must be 3..6");
+      ctx->opt_rast_tile_log2 = value;
+      return B200_OK;
+  }
+  return ctx_fail(ctx, B200_EINVAL, "unknown option");
+}
+
+static int finish_stats(b200_ctx *ctx);
+
+int b200_get_stats(b200_ctx *ctx, b200_stats *out) {
+  if (!ctx || !out) return B200_EINVAL;
+  if (int rc = finish_stats(ctx)) return rc;
+  *out = ctx->stats;
+  return B200_OK;
+}
+
+// ---- RT ---------------------------------------------------------------------------
+
+static int check_camera(b200_ctx *ctx, const camera_t *cam) {
+  if (!cam) return ctx_fail(ctx, B200_EINVAL, "null camera");
+  if (cam->width <= 0 || cam->height <= 0 || cam->width > 32768 || cam->height > 32768)
+    return ctx_fail(ctx, B200_EINVAL, "bad resolution");
+  return B200_OK;
+}
+
+int rt_upload_scene(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres,
+                    int n_spheres) {
+  if (!ctx) return B200_EINVAL;
+  if (n_tris < 0 || n_spheres < 0 || (n_tris > 0 && !tris) || (n_spheres > 0 && !spheres))
+    return ctx_fail(ctx, B200_EINVAL, "bad scene arguments");
+  cudaSetDevice(ctx->device);
+  if (int rc = ensure(ctx, ctx->rt_src, sizeof(rt_triangle) * (size_t)(n_tris ? n_tris : 1))) return rc;
+  if (int rc = ensure(ctx, ctx->rt_spheres, sizeof(rt_sphere) * (size_t)(n_spheres ? n_spheres : 1))) return rc;
+  if (n_tris) CU_CHECK(ctx, cudaMemcpyAsync(ctx->rt_src.p, tris, sizeof(rt_triangle) * (size_t)n_tris,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+  if (n_spheres) CU_CHECK(ctx, cudaMemcpyAsync(ctx->rt_spheres.p, spheres, sizeof(rt_sphere) * (size_t)n_spheres,
+                                               cudaMemcpyHostToDevice, ctx->stream));
+  ctx->rt_n_tris = n_tris;
+  ctx->rt_n_spheres = n_spheres;
+  // bound of |coordinate| over the scene, for the shadow filter's error budget
+  float m = 0.f;
+  for (int i = 0; i < n_tris; ++i)
+    for (int k = 0; k < 3; ++k) {
+      m = fmaxf(m, fabsf(tris[i].v0[k]));
+      m = fmaxf(m, fabsf(tris[i].v1[k]));
+      m = fmaxf(m, fabsf(tris[i].v2[k]));
+    }
+  for (int i = 0; i < n_spheres; ++i)
+    for (int k = 0; k < 3; ++k) m = fmaxf(m, fabsf(spheres[i].centre[k]) + fabsf(spheres[i].radius));
+  ctx->rt_world_abs = m;
+  return rt_prepare_scene(ctx);
+}
+
+static int fill_frame(b200_ctx *ctx, const camera_t *cam, const light_t *lights, int n_lights, int row0,
+                      int row1, RtFrame &f) {
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (n_lights < 0 || n_lights > B200_MAX_LIGHTS || (n_lights > 0 && !lights))
+    return ctx_fail(ctx, B200_EINVAL, "bad lights (at most 8)");
+  if (row0 < 0 || row1 > cam->height || row0 > row1) return ctx_fail(ctx, B200_EINVAL, "bad row band");
+  memcpy(f.cam, cam->pos, sizeof f.cam);
+  f.focal = cam->focal;
+  memcpy(f.R, cam->R, sizeof f.R);
+  f.W = cam->width; f.H = cam->height; f.row0 = row0; f.row1 = row1;
+  f.n_lights = n_lights;
+  memset(f.lights, 0, sizeof f.lights);
+  for (int l = 0; l < n_lights; ++l) {
+    memcpy(&f.lights[l][0], lights[l].pos, 4 * sizeof(float));
+    memcpy(&f.lights[l][4], lights[l].colour, 3 * sizeof(float));
+  }
+  return B200_OK;
+}
+
+int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, int n_lights,
+                     int row_begin, int row_end, float *d_rgb, float *d_depth, int32_t *d_index,
+                     uint32_t *d_argb) {
+  if (!ctx) return B200_EINVAL;
+  RtFrame f;
+  if (int rc = fill_frame(ctx, cam, lights, n_lights, row_begin, row_end, f)) return rc;
+  cudaSetDevice(ctx->device);
+  ctx->stats.kernel_launches = 0;
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (int rc = rt_launch(ctx, f, d_rgb, d_depth, d_index, d_argb)) return rc;
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->stats.primary_rays = (uint64_t)f.W * (uint64_t)(row_end - row_begin) * 9u;
+  ctx->pending = 1;
+  return B200_OK;
+}
+
+// Waits for the last render and reads its device counters back.
+static int finish_stats(b200_ctx *ctx) {
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!ctx->pending) return B200_OK;
+  unsigned long long c[8];
+  CU_CHECK(ctx, cudaMemcpy(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats.gpu_ms = ms;
+  if (ctx->pending == 1) {
+    ctx->stats.shadow_rays = c[0];
+    ctx->stats.exact_evals = c[1];
+    ctx->stats.prim_tests = (ctx->stats.primary_rays + ctx->stats.shadow_rays) *
+                            (uint64_t)(ctx->rt_n_tris + ctx->rt_n_spheres);
+  } else {
+    ctx->stats.fragments = c[2];
+    ctx->stats.bin_entries = c[3];
+  }
+  ctx->pending = 0;
+  return B200_OK;
+}
+
+static int copy_out(b200_ctx *ctx, void *host, const void *dev, size_t bytes) {
+  if (!host) return B200_OK;
+  CU_CHECK(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return B200_OK;
+}
+
+int render_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres,
+                         int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
+                         int row_begin, int row_end, float *rgb_out, float *depth_out,
+                         int32_t *index_out) {
+  if (!ctx) return B200_EINVAL;
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (int rc = rt_upload_scene(ctx, tris, n_tris, spheres, n_spheres)) return rc;
+  const size_t npix = (size_t)cam->width * cam->height;
+  if (rgb_out) if (int rc = ensure(ctx, ctx->out_rgb, npix * 3 * sizeof(float))) return rc;
+  if (depth_out) if (int rc = ensure(ctx, ctx->out_depth, npix * sizeof(float))) return rc;
+  if (index_out) if (int rc = ensure(ctx, ctx->out_index, npix * sizeof(int32_t))) return rc;
+  if (int rc = rt_render_device(ctx, cam, lights, n_lights, row_begin, row_end,
+                                rgb_out ? (float *)ctx->out_rgb.p : nullptr,
+                                depth_out ? (float *)ctx->out_depth.p : nullptr,
+                                index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr))
+    return rc;
+  const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
+  if (int rc = copy_out(ctx, rgb_out, (float *)ctx->out_rgb.p + 3 * off, cnt * 3 * sizeof(float))) return rc;
+  if (int rc = copy_out(ctx, depth_out, (float *)ctx->out_depth.p + off, cnt * sizeof(float))) return rc;
+  if (int rc = copy_out(ctx, index_out, (int32_t *)ctx->out_index.p + off, cnt * sizeof(int32_t))) return rc;
+  return finish_stats(ctx);
+}
+
+int render_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres,
+                    int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
+                    float *rgb_out, float *depth_out, int32_t *index_out) {
+  if (!ctx) return B200_EINVAL;
+  if (int rc = check_camera(ctx, cam)) return rc;
+  return render_raytrace_band(ctx, tris, n_tris, spheres, n_spheres, cam, lights, n_lights, 0, cam->height,
+                              rgb_out, depth_out, index_out);
+}
+
+int draw_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres,
+                  int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
+                  uint32_t *argb_out) {
+  if (!ctx) return B200_EINVAL;
+  if (!argb_out) return ctx_fail(ctx, B200_EINVAL, "null framebuffer");
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (int rc = rt_upload_scene(ctx, tris, n_tris, spheres, n_spheres)) return rc;
+  const size_t npix = (size_t)cam->width * cam->height;
+  if (int rc = ensure(ctx, ctx->out_argb, npix * sizeof(uint32_t))) return rc;
+  if (int rc = rt_render_device(ctx, cam, lights, n_lights, 0, cam->height, nullptr, nullptr, nullptr,
+                                (uint32_t *)ctx->out_argb.p))
+    return rc;
+  if (int rc = copy_out(ctx, argb_out, ctx->out_argb.p, npix * sizeof(uint32_t))) return rc;
+  return finish_stats(ctx);
+}
+
+// ---- headless framebuffer -------------------------------------------------------------
+
+void b200_quantise(const float *rgb, size_t n_pixels, uint32_t *argb_out) {
+  for (size_t i = 0; i < n_pixels; ++i) argb_out[i] = put_pixel_argb(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+}
+
+// 32-bpp BMP with a BITMAPV4-style header and ARGB masks, rows bottom-up: the
+// layout SDL_SaveBMP writes for the ARGB8888 surface the reference builds in
+// SDL_SaveImage (SDLauxiliary.h:24-53); pixel bytes are identical.
+int b200_save_bmp(const char *path, const uint32_t *argb, int width, int height) {
+  if (!path || !argb || width <= 0 || height <= 0) return B200_EINVAL;
+  FILE *f = fopen(path, "wb");
+  if (!f) return B200_EINVAL;
+  const uint32_t hdr = 14, info = 108, off = hdr + info;
+  const uint32_t img = (uint32_t)width * (uint32_t)height * 4u;
+  unsigned char h[122];
+  memset(h, 0, sizeof h);
+  auto put32 = [&](int at, uint32_t v) { h[at] = v & 255; h[at + 1] = (v >> 8) & 255; h[at + 2] = (v >> 16) & 255; h[at + 3] = (v >> 24) & 255; };
+  auto put16 = [&](int at, uint32_t v) { h[at] = v & 255; h[at + 1] = (v >> 8) & 255; };
+  h[0] = 'B'; h[1] = 'M';
+  put32(2, off + img); put32(10, off);
+  put32(14, info); put32(18, (uint32_t)width); put32(22, (uint32_t)height);
+  put16(26, 1); put16(28, 32); put32(30, 3 /* BI_BITFIELDS */); put32(34, img);
+  put32(38, 2835); put32(42, 2835);
+  put32(54, 0x00FF0000u); put32(58, 0x0000FF00u); put32(62, 0x000000FFu); put32(66, 0xFF000000u);
+  put32(70, 0x57696E20u);  // 'Win ' colour space
+  bool ok = fwrite(h, 1, off, f) == off;
+  for (int y = height - 1; y >= 0 && ok; --y)
+    ok = fwrite(argb + (size_t)y * width, 4, (size_t)width, f) == (size_t)width;
+  fclose(f);
+  return ok ? B200_OK : B200_EINVAL;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// Shared device helpers and the context object behind include/b200render.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b200render.h"
+
+// ---- strictly-rounded arithmetic ---------------------------------------------
+// The reference is built without FMA contraction (raytracer/Makefile:15: g++ -O3,
+// no -march), so every product and sum below is rounded on its own.  These
+// wrappers stop nvcc from fusing them; they compile to plain FMUL/FADD/FFMA-free
+// SASS.  Division and square root are the IEEE-exact variants.
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+
+// glm::determinant(mat3) with columns a, b, c
+// (glm/glm/detail/func_matrix.inl:235-238), one rounding per operation.
+__device__ __forceinline__ float xdet3(float ax, float ay, float az, float bx, float by, float bz,
+                                       float cx, float cy, float cz) {
+  float c0 = xsub(xmul(by, cz), xmul(cy, bz));
+  float c1 = xsub(xmul(ay, cz), xmul(cy, az));
+  float c2 = xsub(xmul(ay, bz), xmul(by, az));
+  return xadd(xsub(xmul(ax, c0), xmul(bx, c1)), xmul(cx, c2));
+}
+
+// glm::dot(vec3) (glm/glm/detail/func_geometric.inl:65-73)
+__device__ __forceinline__ float xdot3(float ax, float ay, float az, float bx, float by, float bz) {
+  return xadd(xadd(xmul(ax, bx), xmul(ay, by)), xmul(az, bz));
+}
+
+// PutPixelSDL (raytracer/Source/SDLauxiliary.h:149-161): clamp(255*c, 0, 255),
+// truncate, pack 0x80RRGGBB.
+__host__ __device__ __forceinline__ uint32_t put_pixel_argb(float r, float g, float b) {
+  float c[3] = {r, g, b};
+  uint32_t ch[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = 255.0f * c[k];
+    v = v < 0.f ? 0.f : v;
+    v = v > 255.f ? 255.f : v;
+    ch[k] = (uint32_t)v;
+  }
+  return (128u << 24) + (ch[0] << 16) + (ch[1] << 8) + ch[2];
+}
+
+// ---- context -------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  b200_stats stats{};
+  int opt_rt_bruteforce = 0;
+  int opt_rast_tile_log2 = 5;
+  int sm_count = 148;
+
+  // RT scene (device)
+  DevBuf rt_src;      // rt_triangle[n] as uploaded (normal/colour gathered from here)
+  DevBuf rt_geom;     // float4[3n]: v0, e1, e2 for the exact test
+  DevBuf rt_spheres;  // rt_sphere[n]
+  DevBuf rt_planes;   // float4[..]: per-origin edge-function planes for the filter
+  int rt_n_tris = 0, rt_n_spheres = 0;
+  float rt_world_abs = 0.f;   // max |coordinate| over the uploaded scene
+  int pending = 0;            // 1 = RT, 2 = RAST render whose counters are not read back yet
+
+  // RAST scene (device)
+  DevBuf rast_src;    // rast_triangle[n] clipped list
+  int rast_n_tris = 0;
+  DevBuf rast_setup, rast_bins, rast_tile_count, rast_tile_off, rast_tmp;
+  DevBuf rast_screen, rast_low, rast_high, rast_shadow, rast_depth, rast_index;
+  int rast_w = 0, rast_h = 0;
+
+  // outputs / staging (device) used by the host-pointer entry points
+  DevBuf out_rgb, out_depth, out_index, out_argb;
+  DevBuf counters;    // unsigned long long[8]
+  void *pinned = nullptr;
+  size_t pinned_cap = 0;
+};
+
+int ctx_fail(b200_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
+int ensure(b200_ctx *ctx, DevBuf &b, size_t bytes);
+
+#define CU_CHECK(ctx, call)                                          \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) return ctx_fail(ctx, B200_ECUDA, #call, e__); \
+  } while (0)
+
+// ---- kernels' host launchers (defined in rt_kernels.cu / rast_kernels.cu) ------
+struct RtFrame {
+  float cam[4];
+  float focal;
+  float R[16];
+  int W, H, row0, row1;
+  int n_lights;
+  float lights[8][7];  // pos[4], colour[3]
+};
+#define B200_MAX_LIGHTS 8
+
+int rt_prepare_scene(b200_ctx *ctx);
+int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int32_t *d_index,
+              uint32_t *d_argb);

@@ -1,0 +1,201 @@
+// Raytracer hot path on sm_100a: replaces Draw -> ClosestIntersection ->
+// DirectLight of raytracer/Source/skeleton.cpp:104-169, 263-363, 366-415.
+//
+// Two kernels produce bit-identical frames:
+//   rt_bruteforce_kernel  the reference arithmetic on every (ray, primitive)
+//                         pair; the on-device cross-check.
+//   rt_filtered_kernel    (rt_filtered.cuh) the production kernel: conservative
+//                         edge-function filters decide almost every pair, the
+//                         reference arithmetic runs only where it can matter.
+#include "rt_exact.cuh"
+#include "rt_filtered.cuh"
+
+// ------------------------------------------------------------------------------
+// scene preparation: v0 / e1 / e2 per triangle (skeleton.cpp:283-284)
+// ------------------------------------------------------------------------------
+__global__ void rt_prep_geom_kernel(const rt_triangle *__restrict__ src, int n, float4 *__restrict__ geom) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const rt_triangle t = src[i];
+  float4 g0, g1, g2;
+  g0.x = t.v0[0]; g0.y = t.v0[1]; g0.z = t.v0[2];
+  g0.w = xsub(t.v1[0], t.v0[0]);
+  g1.x = xsub(t.v1[1], t.v0[1]);
+  g1.y = xsub(t.v1[2], t.v0[2]);
+  g1.z = xsub(t.v2[0], t.v0[0]);
+  g1.w = xsub(t.v2[1], t.v0[1]);
+  g2.x = xsub(t.v2[2], t.v0[2]);
+  g2.y = g2.z = g2.w = 0.f;
+  geom[3 * i + 0] = g0;
+  geom[3 * i + 1] = g1;
+  geom[3 * i + 2] = g2;
+}
+
+// ------------------------------------------------------------------------------
+// brute force, reference arithmetic everywhere
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ RtHit rt_closest_bruteforce(const RtKParams &p, float sx, float sy, float sz,
+                                                       float dx, float dy, float dz) {
+  RtHit best;
+  best.t = 0.f; best.dist = FLT_MAX; best.idx = 0;
+  const float len = xsqrt(xdot3(dx, dy, dz, dx, dy, dz));  // glm::length(dir3), :307
+  for (int i = 0; i < p.n_tris; ++i) {
+    const float4 g0 = __ldg(p.geom + 3 * i), g1 = __ldg(p.geom + 3 * i + 1), g2 = __ldg(p.geom + 3 * i + 2);
+    rt_exact_triangle(sx, sy, sz, dx, dy, dz, len, g0, g1, g2, i, best);
+  }
+  rt_exact_spheres(p.sph, p.n_sph, sx, sy, sz, dx, dy, dz, best);
+  return best;
+}
+
+__global__ void __launch_bounds__(128) rt_bruteforce_kernel(const __grid_constant__ RtKParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // each warp owns an 8x4 pixel patch; a 128-thread block covers 16x8 pixels
+  const int u = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+  const int v = p.row0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+  unsigned long long n_shadow = 0;
+  if (u < p.W && v < p.row1) {
+    // dir = R * vec4(u - W/2, v - H/2, f, 1)   (skeleton.cpp:126-128)
+    const float x = (float)(u - p.W / 2), y = (float)(v - p.H / 2);
+    const float dir0 = xadd(xadd(xmul(p.R[0], x), xmul(p.R[4], y)), xadd(xmul(p.R[8], p.focal), xmul(p.R[12], 1.0f)));
+    const float dir1 = xadd(xadd(xmul(p.R[1], x), xmul(p.R[5], y)), xadd(xmul(p.R[9], p.focal), xmul(p.R[13], 1.0f)));
+    float pix[3] = {0.f, 0.f, 0.f};
+    bool valid = false;
+    const size_t pid = (size_t)v * p.W + u;
+    for (int i = -1; i <= 1; ++i) {
+      for (int j = -1; j <= 1; ++j) {
+        const float dx = xadd(dir0, xmul(0.5f, (float)i));   // :137
+        const float dy = xadd(dir1, xmul(0.5f, (float)j));
+        const float dz = p.focal;
+        const RtHit h = rt_closest_bruteforce(p, p.cam[0], p.cam[1], p.cam[2], dx, dy, dz);
+        const bool hit = h.dist < FLT_MAX;
+        if (i == 0 && j == 0) {
+          if (p.depth) p.depth[pid] = hit ? h.dist : INFINITY;
+          if (p.index) p.index[pid] = hit ? h.idx : INT32_MIN;
+        }
+        if (!hit) continue;
+        valid = true;
+        // position = start + vec4(t * dir3, 0)   (:326 / :345)
+        const float px = xadd(p.cam[0], xmul(h.t, dx));
+        const float py = xadd(p.cam[1], xmul(h.t, dy));
+        const float pz = xadd(p.cam[2], xmul(h.t, dz));
+        float col[3], nx, ny, nz;
+        rt_surface(p, h.idx, px, py, pz, col, nx, ny, nz);
+        for (int l = 0; l < p.n_lights; ++l) {
+          // DirectLight (:366-415)
+          const float rx = xsub(p.lights[l][0], px), ry = xsub(p.lights[l][1], py), rz = xsub(p.lights[l][2], pz);
+          const float r_mag = rt_exact_rmag(rx, ry, rz);
+          const float ox = xadd(px, xmul(nx, 0.00001f)), oy = xadd(py, xmul(ny, 0.00001f)),
+                      oz = xadd(pz, xmul(nz, 0.00001f));     // :394
+          ++n_shadow;
+          const RtHit sh = rt_closest_bruteforce(p, ox, oy, oz, rx, ry, rz);
+          if (sh.dist < FLT_MAX && sh.dist < r_mag) continue;  // :395-397, adds (0,0,0)
+          float pw[3];
+          rt_exact_lambert(rx, ry, rz, r_mag, nx, ny, nz, col, &p.lights[l][4], pw);
+          pix[0] = xadd(pix[0], pw[0]); pix[1] = xadd(pix[1], pw[1]); pix[2] = xadd(pix[2], pw[2]);
+        }
+        // pixelColour + objectColor * indirectLight   (:156, indirectLight = 0.5)
+        pix[0] = xadd(pix[0], xmul(col[0], 0.5f));
+        pix[1] = xadd(pix[1], xmul(col[1], 0.5f));
+        pix[2] = xadd(pix[2], xmul(col[2], 0.5f));
+      }
+    }
+    rt_store_pixel(p, pid, valid, pix);
+  }
+  rt_count_shadow(p, n_shadow);
+}
+
+// ------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------
+int rt_prepare_scene(b200_ctx *ctx) {
+  const int n = ctx->rt_n_tris;
+  if (int rc = ensure(ctx, ctx->rt_geom, sizeof(float4) * 3 * (size_t)(n > 0 ? n : 1))) return rc;
+  if (n > 0) {
+    rt_prep_geom_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const rt_triangle *)ctx->rt_src.p, n,
+                                                                  (float4 *)ctx->rt_geom.p);
+    ctx->stats.kernel_launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+  }
+  return B200_OK;
+}
+
+int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int32_t *d_index,
+              uint32_t *d_argb) {
+  RtKParams p;
+  memcpy(p.cam, f.cam, sizeof p.cam);
+  p.focal = f.focal;
+  memcpy(p.R, f.R, sizeof p.R);
+  p.W = f.W; p.H = f.H; p.row0 = f.row0; p.row1 = f.row1;
+  p.n_lights = f.n_lights;
+  memcpy(p.lights, f.lights, sizeof p.lights);
+  p.geom = (const float4 *)ctx->rt_geom.p;
+  p.src = (const rt_triangle *)ctx->rt_src.p;
+  p.sph = (const rt_sphere *)ctx->rt_spheres.p;
+  p.n_tris = ctx->rt_n_tris; p.n_sph = ctx->rt_n_spheres;
+  p.rgb = d_rgb; p.depth = d_depth; p.index = d_index; p.argb = d_argb;
+  p.counters = (unsigned long long *)ctx->counters.p;
+  const int rows = f.row1 - f.row0;
+  if (rows <= 0 || f.W <= 0) return B200_OK;
+  if (ctx->opt_rt_bruteforce) {
+    dim3 grid((f.W + 15) / 16, (rows + 7) / 8);
+    rt_bruteforce_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    ctx->stats.kernel_launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return B200_OK;
+  }
+  return rt_launch_filtered(ctx, f, p);
+}
+
+int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
+  const int n = ctx->rt_n_tris;
+  const int n_tiles = (n + RT_TILE - 1) / RT_TILE;
+  const size_t origin_stride = (size_t)n_tiles * RT_TILE * RT_REC_F4;
+  if (int rc = ensure(ctx, ctx->rt_planes, sizeof(float4) * (origin_stride * (1 + f.n_lights) + 1))) return rc;
+  p.planes = (const float4 *)ctx->rt_planes.p;
+
+  if (n > 0) {
+    RtPrepParams q;
+    q.geom = (const float4 *)ctx->rt_geom.p;
+    q.n_tris = n;
+    q.cam[0] = f.cam[0]; q.cam[1] = f.cam[1]; q.cam[2] = f.cam[2];
+    q.focal = f.focal;
+    // |d|inf over the band: dir.x / dir.y are affine in (u, v), extremes at the corners
+    float dmax = fabsf(f.focal);
+    const int us[2] = {0, f.W - 1}, vs[2] = {f.row0, f.row1 - 1};
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const float x = (float)(us[a] - f.W / 2), y = (float)(vs[b] - f.H / 2);
+        for (int r = 0; r < 2; ++r) {
+          const float d = f.R[0 + r] * x + f.R[4 + r] * y + f.R[8 + r] * f.focal + f.R[12 + r];
+          dmax = fmaxf(dmax, fabsf(d) + 0.5f);
+        }
+      }
+    q.dmax = dmax * 1.001f + 1.0f;
+    float m = ctx->rt_world_abs;
+    for (int k = 0; k < 3; ++k) m = fmaxf(m, fabsf(f.cam[k]));
+    q.n_lights = f.n_lights;
+    for (int l = 0; l < f.n_lights; ++l)
+      for (int k = 0; k < 3; ++k) {
+        q.lights[l][k] = f.lights[l][k];
+        m = fmaxf(m, fabsf(f.lights[l][k]));
+      }
+    q.world_S = 2.0f * m * 1.001f + 1e-4f;
+    q.planes = (float4 *)ctx->rt_planes.p;
+    q.origin_stride_f4 = origin_stride;
+    dim3 grid((n + 127) / 128, 1 + f.n_lights);
+    rt_prep_planes_kernel<<<grid, 128, 0, ctx->stream>>>(q);
+    ctx->stats.kernel_launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+  }
+
+  const int rows = f.row1 - f.row0;
+  dim3 grid((f.W + 15) / 16, (rows + 15) / 16);
+  const size_t smem = 2 * (size_t)RT_TILE * RT_REC_F4 * sizeof(float4);
+  if (f.n_lights > 1)
+    rt_filtered_kernel<true><<<grid, RT_THREADS, smem, ctx->stream>>>(p);
+  else
+    rt_filtered_kernel<false><<<grid, RT_THREADS, smem, ctx->stream>>>(p);
+  ctx->stats.kernel_launches++;
+  CU_CHECK(ctx, cudaGetLastError());
+  return B200_OK;
+}

@@ -115,11 +115,12 @@ int b200_synchronize(b200_ctx *ctx);
 #define B200_OPT_RAST_TILE_LOG2 2
 int b200_set_option(b200_ctx *ctx, int option, int value);
 
-/* Counters of the last render on this context. */
+/* Counters of the last render on this context (b200_get_stats synchronises). */
 typedef struct b200_stats {
   uint64_t primary_rays;     /* RT: W * rows * 9                              */
   uint64_t shadow_rays;      /* RT: primary hits * n_lights                   */
   uint64_t prim_tests;       /* RT: rays * (n_tris + n_spheres)               */
+  uint64_t exact_evals;      /* RT: pairs that ran the reference arithmetic   */
   uint64_t kernel_launches;  /* kernels of this library launched by the call  */
   uint64_t fragments;        /* RAST: fragments shaded or depth-tested        */
   uint64_t bin_entries;      /* RAST: (tile, triangle) pairs                  */

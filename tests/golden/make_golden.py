@@ -1,0 +1,66 @@
+"""Generates the committed golden fixtures under tests/golden/.
+
+Run in the development container, where /root/reference exists and the
+unmodified reference has been compiled into oracle/_ref/ (oracle/refbuild/
+build_ref.sh).  The GPU box has neither, so everything the `-m gpu` tests and
+the oracle tests need from the reference is frozen here as small .npz files:
+
+  rt_screenshot_320x256.npz  the reference's own golden image
+                             raytracer/screenshot.bmp (KAT #2), as the uint32
+                             ARGB pixel array top-down
+  rt_cornell.npz             bytes of the reference's LoadTestModel scene
+                             (28 triangles + 1 sphere)
+  rt_ref_*.npz               outputs of the compiled reference (Draw float colour,
+                             centre-sample distance / index) on seeded inputs
+  rast_*.npz                 the same for the rasteriser (see make_rast below)
+"""
+import os
+import struct
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import helpers as h  # noqa: E402
+
+REF = os.environ.get("REF", "/root/reference")
+
+
+def read_bmp32(path):
+    b = open(path, "rb").read()
+    off = struct.unpack_from("<I", b, 10)[0]
+    w, hgt = struct.unpack_from("<ii", b, 18)
+    bpp = struct.unpack_from("<H", b, 28)[0]
+    assert bpp == 32
+    px = np.frombuffer(b, np.uint32, count=w * abs(hgt), offset=off).reshape(abs(hgt), w)
+    return px[::-1].copy() if hgt > 0 else px.copy()
+
+
+def make_rt():
+    px = read_bmp32(os.path.join(REF, "raytracer", "screenshot.bmp"))
+    np.savez_compressed(os.path.join(HERE, "rt_screenshot_320x256.npz"), argb=px)
+    tris, sph = h.ref_rt_testmodel()
+    np.savez_compressed(os.path.join(HERE, "rt_cornell.npz"), tris=tris.view(np.uint8), spheres=sph.view(np.uint8))
+    L = h.lights_array(h.DEFAULT_RT_LIGHTS)
+    cases = {
+        # name: (W, H, focal, cam, R, scene)
+        "cornell_default_160x128": (160, 128, 128.0, h.f32(0, 0, -3, 1), h.identity_R(), None),
+        "cornell_yaw_96x64": (96, 64, 64.0, h.f32(0.1, 0, -2.9, 1), h.yaw_R(-0.174533), None),
+        "random40_96x64": (96, 64, 80.0, h.f32(0.1, -0.2, -2.5, 1), h.yaw_R(0.3), h.random_rt_scene(40, 7, n_spheres=2)),
+    }
+    for name, (W, H, f, cam, R, scene) in cases.items():
+        t, s = scene if scene is not None else (None, None)
+        d = h.ref_rt_draw(W, H, f, cam, R, L, t, s)
+        tr = h.ref_rt_trace(W, H, f, cam, R, t, s)
+        np.savez_compressed(os.path.join(HERE, f"rt_ref_{name}.npz"), W=W, H=H, focal=f, cam=cam, R=R,
+                            lights=L, rgb=d["rgb"], argb=d["argb"], dist=tr["dist"], index=tr["index"],
+                            tris=(t if t is not None else tris).view(np.uint8),
+                            spheres=(s if s is not None else sph).view(np.uint8))
+    print("rt goldens written")
+
+
+if __name__ == "__main__":
+    make_rt()
+    if hasattr(sys.modules[__name__], "make_rast"):
+        make_rast()

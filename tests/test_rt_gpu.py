@@ -1,0 +1,147 @@
+"""GPU parity tests for the raytracer path: the CUDA kernels (through the C ABI)
+against the plain-C oracle on the same inputs, and against the committed golden
+fixtures.  Bar: bit-exact float colour, distance and index."""
+import numpy as np
+import pytest
+
+import helpers as h
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def check_equal(got, want, what):
+    assert np.array_equal(got["index"], want["index"]), f"{what}: index differs at {np.count_nonzero(got['index'] != want['index'])} px"
+    assert np.array_equal(bits(got["depth"]), bits(want["dist"])), f"{what}: distance differs at {np.count_nonzero(bits(got['depth']) != bits(want['dist']))} px"
+    nb = np.count_nonzero((bits(got["rgb"]) != bits(want["rgb"])).any(axis=-1))
+    assert nb == 0, f"{what}: colour differs at {nb} px"
+
+
+def run_both(b200, renderer, tris, sph, W, H, focal, cam, R, lights, what, brute=True):
+    c = b200.make_camera(cam, focal, R, W, H)
+    want = h.oracle_rt_render(W, H, focal, cam, R, h.lights_array(lights), tris, sph if sph is not None and len(sph) else None)
+    renderer.set_option(b200.OPT_RT_BRUTEFORCE, 0)
+    got = renderer.render_raytrace(tris, sph, c, lights)
+    st = renderer.stats()
+    check_equal(got, want, what + " [filtered]")
+    assert st["primary_rays"] == want["primary"] and st["shadow_rays"] == want["shadow"]
+    if brute:
+        renderer.set_option(b200.OPT_RT_BRUTEFORCE, 1)
+        got2 = renderer.render_raytrace(tris, sph, c, lights)
+        st2 = renderer.stats()
+        renderer.set_option(b200.OPT_RT_BRUTEFORCE, 0)
+        check_equal(got2, want, what + " [bruteforce]")
+        assert st2["shadow_rays"] == want["shadow"]
+    return got, want, st
+
+
+def test_kat2_golden_screenshot(b200, renderer, cornell_rt):
+    """The reference's own golden image, bit-exact through draw_raytrace."""
+    tris, sph = cornell_rt
+    gold = load_golden("rt_screenshot_320x256.npz")["argb"]
+    cam = h.f32(0, 0, np.float32(-3.0) + np.float32(0.1), 1)
+    c = b200.make_camera(cam, 256.0, h.identity_R(), 320, 256)
+    argb = renderer.draw_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
+    assert np.array_equal(argb, gold)
+
+
+def test_cornell_default_config(b200, renderer, cornell_rt):
+    """BASELINE config 1: 320x256, f=256, cam (0,0,-3,1)."""
+    tris, sph = cornell_rt
+    _, want, st = run_both(b200, renderer, tris, sph, 320, 256, 256.0, h.f32(0, 0, -3, 1), h.identity_R(),
+                           h.DEFAULT_RT_LIGHTS, "cornell 320x256")
+    assert st["primary_rays"] == 737280 and st["shadow_rays"] == 589823
+    # most pairs are decided by the filter, not by the reference arithmetic
+    assert st["exact_evals"] < 0.2 * st["prim_tests"]
+
+
+@pytest.mark.parametrize("name", ["cornell_default_160x128", "cornell_yaw_96x64", "random40_96x64"])
+def test_committed_reference_outputs(b200, renderer, name):
+    g = load_golden(f"rt_ref_{name}.npz")
+    tris = g["tris"].view(h.RT_TRI).copy()
+    sph = g["spheres"].view(h.RT_SPHERE).copy()
+    W, H = int(g["W"]), int(g["H"])
+    c = b200.make_camera(g["cam"], float(g["focal"]), g["R"], W, H)
+    L = [(g["lights"][:4], g["lights"][4:7])]
+    got = renderer.render_raytrace(tris, sph, c, L)
+    check_equal(got, dict(rgb=g["rgb"], dist=g["dist"], index=g["index"]), name)
+    assert np.array_equal(renderer.draw_raytrace(tris, sph, c, L), g["argb"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_scenes(b200, renderer, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 700))
+    tris, sph = h.random_rt_scene(n, seed, size=float(rng.uniform(0.05, 0.8)), n_spheres=int(rng.integers(0, 3)))
+    W, H = int(rng.integers(17, 90)), int(rng.integers(9, 70))
+    cam = h.f32(*rng.uniform(-0.3, 0.3, 2), -2.5, 1)
+    R = h.yaw_R(float(rng.uniform(-0.5, 0.5)))
+    lights = [((0.2, -0.4, -0.9, 1), (10, 12, 14)), ((-0.5, 0.3, -1.2, 1), (3, 2, 1)),
+              ((0.0, 0.9, -0.2, 1), (5, 5, 5))][: 1 + seed % 3]
+    run_both(b200, renderer, tris, sph, W, H, 70.0, cam, R, lights, f"random seed {seed}")
+
+
+def test_camera_inside_scene_and_yaw(b200, renderer, cornell_rt):
+    tris, sph = cornell_rt
+    run_both(b200, renderer, tris, sph, 128, 96, 90.0, h.f32(0.3, 0.2, -0.5, 1), h.yaw_R(0.7),
+             h.DEFAULT_RT_LIGHTS, "inside+yaw")
+
+
+def test_light_in_a_triangle_plane(b200, renderer, cornell_rt):
+    """Degenerate origin: the light lies exactly in the ceiling's plane (y = -1)."""
+    tris, sph = cornell_rt
+    run_both(b200, renderer, tris, sph, 96, 80, 80.0, h.f32(0, 0, -3, 1), h.identity_R(),
+             [((0.0, -1.0, -0.3, 1), (14, 14, 14))], "light in plane")
+
+
+def test_edge_cases(b200, renderer, cornell_rt):
+    tris, sph = cornell_rt
+    L = h.DEFAULT_RT_LIGHTS
+    # no triangles, only the sphere; no spheres; nothing at all; no lights
+    run_both(b200, renderer, np.zeros(0, h.RT_TRI), sph, 40, 30, 30.0, h.f32(0, 0, -3, 1), h.identity_R(), L, "sphere only")
+    run_both(b200, renderer, tris, np.zeros(0, h.RT_SPHERE), 40, 30, 30.0, h.f32(0, 0, -3, 1), h.identity_R(), L, "no spheres")
+    got, _, _ = run_both(b200, renderer, np.zeros(0, h.RT_TRI), np.zeros(0, h.RT_SPHERE), 19, 7, 30.0,
+                         h.f32(0, 0, -3, 1), h.identity_R(), L, "empty scene")
+    assert not got["rgb"].any() and (got["index"] == h.INDEX_MISS).all() and np.isinf(got["depth"]).all()
+    run_both(b200, renderer, tris, sph, 33, 17, 30.0, h.f32(0, 0, -3, 1), h.identity_R(), [], "no lights")
+    # a single pixel, and a 1-row frame
+    run_both(b200, renderer, tris, sph, 1, 1, 1.0, h.f32(0, 0, -3, 1), h.identity_R(), L, "1x1")
+    run_both(b200, renderer, tris, sph, 257, 1, 128.0, h.f32(0, 0, -3, 1), h.identity_R(), L, "257x1")
+
+
+def test_bands_tile_the_frame(b200, renderer, cornell_rt):
+    tris, sph = cornell_rt
+    cam = h.f32(0, 0, -3, 1)
+    c = b200.make_camera(cam, 100.0, h.identity_R(), 120, 100)
+    full = renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
+    n_shadow = renderer.stats()["shadow_rays"]
+    parts, acc = [], 0
+    for r0, r1 in [(0, 13), (13, 50), (50, 51), (51, 100)]:
+        parts.append(renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS, r0, r1))
+        acc += renderer.stats()["shadow_rays"]
+    for key in ("rgb", "depth", "index"):
+        assert np.array_equal(np.concatenate([p[key] for p in parts]), full[key])
+    assert acc == n_shadow
+
+
+def test_many_triangles_multi_tile(b200, renderer):
+    """More triangles than one shared-memory tile (256): exercises the TMA ring."""
+    tris, sph = h.random_rt_scene(1500, 42, size=0.15, n_spheres=1)
+    run_both(b200, renderer, tris, sph, 64, 48, 60.0, h.f32(0, 0, -2.6, 1), h.identity_R(),
+             h.DEFAULT_RT_LIGHTS, "1500 tris")
+
+
+def test_invalid_arguments(b200, renderer, cornell_rt):
+    tris, sph = cornell_rt
+    c = b200.make_camera(h.f32(0, 0, -3, 1), 10.0, h.identity_R(), 0, 10)
+    with pytest.raises(b200.B200Error):
+        renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
+    c = b200.make_camera(h.f32(0, 0, -3, 1), 10.0, h.identity_R(), 16, 16)
+    with pytest.raises(b200.B200Error):
+        renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS, 5, 40)
+    with pytest.raises(b200.B200Error):
+        renderer.render_raytrace(tris, sph, c, [((0, 0, 0, 1), (1, 1, 1))] * 9)
