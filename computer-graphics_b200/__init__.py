@@ -60,7 +60,9 @@ class Stats(ctypes.Structure):
 # Every symbol include/b200render.h declares; tests check they are all exported.
 ABI_SYMBOLS = [
     "b200_init", "b200_destroy", "b200_last_error", "b200_stream", "b200_synchronize",
-    "b200_set_option", "b200_get_stats",
+    "b200_set_stream", "b200_set_option", "b200_get_stats",
+    "b200_scene_cornell_rt", "b200_scene_cornell_rt_tessellated", "b200_scene_cornell_rast",
+    "b200_scene_soup_rast",
     "render_raytrace", "render_raytrace_band", "draw_raytrace", "rt_upload_scene", "rt_render_device",
     "render_raster_clipped", "render_raster", "draw_raster", "raster_read_buffers",
     "raster_read_clipped", "rast_upload_clipped", "rast_render_device",
@@ -161,6 +163,9 @@ class Renderer:
     def stream(self):
         return self.lib.b200_stream(self.ctx)
 
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.b200_set_stream(self.ctx, ctypes.c_void_p(cuda_stream or 0)), "b200_set_stream")
+
     def synchronize(self):
         self._check(self.lib.b200_synchronize(self.ctx), "b200_synchronize")
 
@@ -259,6 +264,38 @@ class Renderer:
                                          int(row_begin), int(row_end), _ptr(d_rgb), _ptr(d_depth),
                                          _ptr(d_index), _ptr(d_argb))
         self._check(rc, "rast_render_device")
+
+
+def scene_cornell_rt():
+    lib = load_library()
+    tris, sph = np.zeros(28, RT_TRI), np.zeros(1, RT_SPHERE)
+    nt, ns = ctypes.c_int(), ctypes.c_int()
+    assert lib.b200_scene_cornell_rt(_ptr(tris), 28, _ptr(sph), 1, ctypes.byref(nt), ctypes.byref(ns)) == 0
+    return tris, sph
+
+
+def scene_cornell_rt_tessellated(n):
+    lib = load_library()
+    nt = ctypes.c_int()
+    assert lib.b200_scene_cornell_rt_tessellated(int(n), None, 0, ctypes.byref(nt)) == 0
+    tris = np.zeros(nt.value, RT_TRI)
+    assert lib.b200_scene_cornell_rt_tessellated(int(n), _ptr(tris), len(tris), ctypes.byref(nt)) == 0
+    return tris, scene_cornell_rt()[1]
+
+
+def scene_cornell_rast():
+    lib = load_library()
+    room, boxes = np.zeros(10, RAST_TRI), np.zeros(20, RAST_TRI)
+    a, b = ctypes.c_int(), ctypes.c_int()
+    assert lib.b200_scene_cornell_rast(_ptr(room), 10, _ptr(boxes), 20, ctypes.byref(a), ctypes.byref(b)) == 0
+    return room, boxes
+
+
+def scene_soup_rast(n, seed=0x5EED, edge=0.01):
+    lib = load_library()
+    tris = np.zeros(int(n), RAST_TRI)
+    assert lib.b200_scene_soup_rast(int(n), ctypes.c_uint32(seed), ctypes.c_float(edge), _ptr(tris)) == 0
+    return tris
 
 
 def quantise(rgb):

@@ -51,11 +51,12 @@ int b200_init(int device, b200_ctx **out) {
   ctx->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     delete ctx;
     return B200_ECUDA;
   }
+  ctx->stream = ctx->own_stream;
   if (ensure(ctx, ctx->counters, 8 * sizeof(unsigned long long)) != B200_OK) { delete ctx; return B200_ENOMEM; }
   *out = ctx;
   return B200_OK;
@@ -74,7 +75,7 @@ void b200_destroy(b200_ctx *ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
@@ -84,6 +85,13 @@ void *b200_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int b200_synchronize(b200_ctx *ctx) {
   if (!ctx) return B200_EINVAL;
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_set_stream(b200_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return B200_EINVAL;
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return B200_OK;
 }
 

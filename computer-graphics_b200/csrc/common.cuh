@@ -56,7 +56,8 @@ struct DevBuf {
 
 struct b200_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // where work is enqueued (own_stream unless overridden)
+  cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   b200_stats stats{};

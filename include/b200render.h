@@ -107,6 +107,9 @@ const char *b200_last_error(const b200_ctx *ctx);
 /* The CUDA stream (cudaStream_t) every call on this context is enqueued on. */
 void *b200_stream(b200_ctx *ctx);
 int b200_synchronize(b200_ctx *ctx);
+/* Makes the context enqueue on a caller-owned stream (e.g. the one the caller's
+ * collectives run on); NULL restores the context's own stream. */
+int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
 
 /* Tunables.  B200_OPT_RT_BRUTEFORCE = 1 switches the raytracer to the
  * unfiltered kernel that runs the reference arithmetic on every ray/triangle
@@ -207,6 +210,21 @@ int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris)
 int rast_render_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
                        int row_begin, int row_end, float *d_rgb, float *d_depth,
                        int32_t *d_index, uint32_t *d_argb);
+
+/* ---- scenes (host-side data builders) ---------------------------------------*/
+
+/* The raytracer's LoadTestModel (raytracer/Source/TestModelH.h:121-279): 28
+ * triangles + 1 sphere, byte-identical to the reference's vectors. */
+int b200_scene_cornell_rt(rt_triangle *tris, int tri_cap, rt_sphere *spheres, int sph_cap,
+                          int *n_tris, int *n_spheres);
+/* BASELINE config 5: each Cornell triangle split into n*n (n = 60: 100 800). */
+int b200_scene_cornell_rt_tessellated(int n, rt_triangle *tris, int tri_cap, int *n_tris);
+/* The rasteriser's LoadTestModel with setting = settingBoxes = 0
+ * (rasteriser/Source/TestModelH.h:48-312): 10 room + 20 box triangles. */
+int b200_scene_cornell_rast(rast_triangle *room, int room_cap, rast_triangle *boxes, int boxes_cap,
+                            int *n_room, int *n_boxes);
+/* BASELINE config 4: n-triangle random soup (mt19937(seed), edges in +-edge). */
+int b200_scene_soup_rast(int n, uint32_t seed, float edge, rast_triangle *tris);
 
 /* ---- headless framebuffer (replaces SDL_SaveImage, SDLauxiliary.h:24-53) ---*/
 

@@ -1,0 +1,284 @@
+/* oracle_rast.c -- CPU restatement of the reference rasteriser's hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline leg as the checker; never linked into or loaded by
+ * the product library.
+ *
+ * Parity status: PINNED.  tests/test_oracle_rast.py checks this file against
+ * (a) KAT #1, the ComputePolygonRows table of the lab sheet
+ * (rasteriser/Source/skeleton.cpp:183-199), and (b) bit-for-bit against the
+ * unmodified reference compiled into oracle/_ref/libref_rast_<W>x<H>.so
+ * (depth / screen / low / high / shadow buffers, final colour, clipped list),
+ * plus the committed outputs of that library under tests/golden/.
+ *
+ * Citations are file:line in rasteriser/Source/skeleton.cpp unless noted.  IEEE
+ * binary32, one rounding per operation (reference build: g++ -O3, no -march =>
+ * no FMA; compile this file with -ffp-contract=off); pow()/M_PI double islands
+ * kept as double.
+ */
+#include <limits.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+  float v0[4], v1[4], v2[4], normal[4], color[3];
+  int32_t texture, index;
+} o_rtri; /* 84 B, rasteriser/Source/TestModelH.h:13-42 */
+
+typedef struct {
+  int x, y;
+  float zinv;
+  float pos[4];
+} o_pixel; /* :88-94 */
+
+static int imax(int a, int b) { return a > b ? a : b; }
+
+/* VertexShader :510-522 */
+static void vertex_shader(const float *v, float focal, int W, int H, o_pixel *p) {
+  float x = (focal * (v[0] / v[2])) + (float)(W / 2);
+  float y = (focal * (v[1] / v[2])) + (float)(H / 2);
+  p->x = (int)x;
+  p->y = (int)y;
+  p->zinv = 1 / v[2];
+  memcpy(p->pos, v, sizeof p->pos);
+}
+
+/* Interpolate :524-551 */
+static void interpolate(o_pixel a, o_pixel b, o_pixel *result, int N) {
+  a.pos[0] = a.pos[0] * a.zinv;
+  a.pos[1] = a.pos[1] * a.zinv;
+  b.pos[0] = b.pos[0] * b.zinv;
+  b.pos[1] = b.pos[1] * b.zinv;
+  float den = (float)imax(N - 1, 1);
+  float step_x = (float)(b.x - a.x) / den;
+  float step_y = (float)(b.y - a.y) / den;
+  float step_z = (b.zinv - a.zinv) / den;
+  float step_px = (b.pos[0] - a.pos[0]) / den;
+  float step_py = (b.pos[1] - a.pos[1]) / den;
+  for (int i = 0; i < N; ++i) {
+    result[i].x = (int)floorf((float)a.x + (step_x * (float)i));
+    result[i].y = (int)floorf((float)a.y + (step_y * (float)i));
+    result[i].zinv = (a.zinv + (step_z * (float)i));
+    result[i].pos[2] = 1 / result[i].zinv;
+    result[i].pos[0] = (a.pos[0] + (step_px * (float)i)) / result[i].zinv;
+    result[i].pos[1] = (a.pos[1] + (step_py * (float)i)) / result[i].zinv;
+    result[i].pos[3] = 1.0f;
+  }
+}
+
+/* ComputePolygonRows :433-498.  Returns the number of rows; *left / *right are
+ * malloc'ed arrays the caller frees. */
+static int compute_polygon_rows(const o_pixel *vp, o_pixel **left_out, o_pixel **right_out) {
+  int max = -INT_MAX, min = +INT_MAX;
+  for (int i = 0; i < 3; ++i) {
+    if (vp[i].y > max) max = vp[i].y;
+    if (vp[i].y < min) min = vp[i].y;
+  }
+  int rows = (max - min) + 1;
+  o_pixel *left = (o_pixel *)calloc((size_t)rows, sizeof(o_pixel));
+  o_pixel *right = (o_pixel *)calloc((size_t)rows, sizeof(o_pixel));
+  for (int j = 0; j < rows; ++j) {
+    left[j].x = +INT_MAX; left[j].y = min + j;
+    right[j].x = -INT_MAX; right[j].y = min + j;
+  }
+  for (int i = 0; i < 3; ++i) {
+    o_pixel a = vp[i], b = vp[(i + 1) % 3];
+    int dx = abs(a.x - b.x), dy = abs(a.y - b.y);
+    int pixels = imax(dx, dy) + 1;
+    o_pixel *line = (o_pixel *)malloc((size_t)pixels * sizeof(o_pixel));
+    interpolate(a, b, line, pixels);
+    for (int j = 0; j < pixels; ++j) {
+      int r = line[j].y - min;
+      if (r < 0) continue; /* the ":485 SEG FAULT FIXED HERE" guard */
+      if (line[j].x <= left[r].x) { left[r].x = line[j].x; left[r].zinv = line[j].zinv; memcpy(left[r].pos, line[j].pos, 16); }
+      if (line[j].x >= right[r].x) { right[r].x = line[j].x; right[r].zinv = line[j].zinv; memcpy(right[r].pos, line[j].pos, 16); }
+    }
+    free(line);
+  }
+  *left_out = left; *right_out = right;
+  return rows;
+}
+
+typedef struct {
+  int W, H;
+  float focal;
+  float light[4];
+  float power[3];
+  float indirect[3];
+  float *depth, *screen, *low, *high;
+  int32_t *shadow, *index;
+  uint64_t fragments;
+} o_frame;
+
+/* calculateIllumination :674-688, without the final "+ indirect": returns D. */
+static void illumination_D(const o_frame *f, const float *pos, const float *normal, float *D) {
+  float r[3] = {f->light[0] - pos[0], f->light[1] - pos[1], f->light[2] - pos[2]};
+  float r_mag = (float)((double)r[0] * (double)r[0] + (double)r[1] * (double)r[1] + (double)r[2] * (double)r[2]);
+  float vp = (r[0] * normal[0] + r[1] * normal[1]) + r[2] * normal[2];
+  float m = vp < 0.0f ? 0.0f : vp; /* glm::max(x, 0) = (x < 0) ? 0 : x */
+  float den = (float)((double)4.0f * M_PI * (double)r_mag);
+  for (int k = 0; k < 3; ++k) D[k] = (f->power[k] * m) / den;
+}
+
+/* PixelShader :559-672, untextured colour-mode-0 branch. */
+static void pixel_shader(o_frame *f, const o_pixel *p, const o_rtri *t, int tri_index) {
+  int x = p->x, y = p->y;
+  if (x >= 0 && x < f->W && y >= 0 && y < f->H) {
+    size_t q = (size_t)y * f->W + x;
+    f->fragments++;
+    if (p->zinv >= f->depth[q] && t->color[0] >= 0) {
+      float D[3];
+      illumination_D(f, p->pos, t->normal, D);
+      for (int k = 0; k < 3; ++k) {
+        f->screen[3 * q + k] = t->color[k] * (D[k] + f->indirect[k]);
+        f->low[3 * q + k] = t->color[k] * (D[k] + 0.0f);
+        f->high[3 * q + k] = t->color[k] * (D[k] + 0.4f);
+      }
+      f->depth[q] = p->zinv;
+      if (f->index) f->index[q] = tri_index;
+    } else if (p->zinv > f->depth[q] && t->color[0] < 0) {
+      f->shadow[q] = 1;
+    }
+  }
+}
+
+/* DrawPolygon :420-431 = VertexShader x3, ComputePolygonRows, DrawPolygonRows :500-508 */
+static void draw_polygon(o_frame *f, const o_rtri *t, int tri_index) {
+  o_pixel vp[3];
+  vertex_shader(t->v0, f->focal, f->W, f->H, &vp[0]);
+  vertex_shader(t->v1, f->focal, f->W, f->H, &vp[1]);
+  vertex_shader(t->v2, f->focal, f->W, f->H, &vp[2]);
+  o_pixel *left, *right;
+  int rows = compute_polygon_rows(vp, &left, &right);
+  for (int r = 0; r < rows; ++r) {
+    int n = right[r].x - left[r].x + 1;
+    if (n <= 0) continue;
+    o_pixel *line = (o_pixel *)malloc((size_t)n * sizeof(o_pixel));
+    interpolate(left[r], right[r], line, n);
+    for (int x = 0; x < (right[r].x - left[r].x); ++x) pixel_shader(f, &line[x], t, tri_index);
+    free(line);
+  }
+  free(left); free(right);
+}
+
+/* surroundingShadowSum :1725-1733 (note [y+1][x-1] twice, [y+1][x+1] never) */
+static float shadow_sum(const int32_t *s, int W, int y, int x) {
+#define S(yy, xx) s[(size_t)(yy) * W + (xx)]
+  float val = (float)(S(y, x) + S(y - 1, x) + S(y - 1, x - 1) + S(y - 1, x + 1) + S(y + 1, x - 1) +
+                      S(y + 1, x) + S(y + 1, x - 1) + S(y, x - 1) + S(y, x + 1));
+#undef S
+  val /= 9.0f;
+  return val;
+}
+
+/* antiAliasing :1736-1753 for one buffer: 5-tap cross / 5 */
+static void cross5(const float *b, int W, int y, int x, float *out) {
+  for (int k = 0; k < 3; ++k) {
+#define B(yy, xx) b[3 * ((size_t)(yy) * W + (xx)) + k]
+    float v = B(y, x) + B(y - 1, x);
+    v = v + B(y + 1, x);
+    v = v + B(y, x - 1);
+    v = v + B(y, x + 1);
+#undef B
+    out[k] = v / 5.0f;
+  }
+}
+
+static uint32_t put_pixel(const float *c) {
+  uint32_t ch[3];
+  for (int k = 0; k < 3; ++k) {
+    float v = 255 * c[k];
+    v = v < 0.f ? 0.f : v;
+    v = v > 255.f ? 255.f : v;
+    ch[k] = (uint32_t)v;
+  }
+  return (128u << 24) + (ch[0] << 16) + (ch[1] << 8) + ch[2];
+}
+
+/* The triangle loop and the post pass of Draw (:243-307) on an already-clipped
+ * list.  All buffers are W*H (x3 for colours), caller-allocated; index_out,
+ * screen_pre_out (screenBuffer before the in-place darkening), rgb_out and
+ * argb_out may be NULL.  `screen` ends up darkened, like the reference's. */
+int oracle_rast_draw_clipped(int W, int H, float focal, const float *light_cam4, const float *power3,
+                             const float *indirect3, const void *tris_, int n, float *depth,
+                             float *screen, float *low, float *high, int32_t *shadow,
+                             int32_t *index_out, float *screen_pre_out, float *rgb_out,
+                             uint32_t *argb_out, uint64_t *fragments_out) {
+  const o_rtri *tris = (const o_rtri *)tris_;
+  o_frame f;
+  f.W = W; f.H = H; f.focal = focal;
+  memcpy(f.light, light_cam4, sizeof f.light);
+  memcpy(f.power, power3, sizeof f.power);
+  memcpy(f.indirect, indirect3, sizeof f.indirect);
+  f.depth = depth; f.screen = screen; f.low = low; f.high = high; f.shadow = shadow; f.index = index_out;
+  f.fragments = 0;
+  size_t np = (size_t)W * H;
+  memset(depth, 0, np * sizeof(float));
+  memset(screen, 0, np * 3 * sizeof(float));
+  memset(low, 0, np * 3 * sizeof(float));
+  memset(high, 0, np * 3 * sizeof(float));
+  memset(shadow, 0, np * sizeof(int32_t));
+  if (index_out) for (size_t i = 0; i < np; ++i) index_out[i] = -1;
+  for (int i = 0; i < n; ++i) draw_polygon(&f, &tris[i], i);   /* :262-281 */
+  if (screen_pre_out) memcpy(screen_pre_out, screen, np * 3 * sizeof(float));
+  if (rgb_out) memset(rgb_out, 0, np * 3 * sizeof(float));
+  if (argb_out) memset(argb_out, 0, np * sizeof(uint32_t));
+  for (int y = 1; y < H - 1; ++y) {                            /* :283-307 */
+    for (int x = 1; x < W - 1; ++x) {
+      size_t q = (size_t)y * W + x;
+      if (shadow[q] == 1) {
+        float s = shadow_sum(shadow, W, y, x);
+        float sub = s < 0.6 ? 0.05f : s < 0.7 ? 0.08f : s < 0.8 ? 0.1f : s < 0.9 ? 0.12f : 0.3f;
+        for (int k = 0; k < 3; ++k) screen[3 * q + k] -= sub;
+      }
+      float a[3], b[3], c[3], out[3];
+      cross5(screen, W, y, x, a);
+      cross5(low, W, y, x, b);
+      cross5(high, W, y, x, c);
+      for (int k = 0; k < 3; ++k) out[k] = ((a[k] + b[k]) + c[k]) / 3.0f;
+      if (rgb_out) memcpy(rgb_out + 3 * q, out, sizeof out);
+      if (argb_out) argb_out[q] = put_pixel(out);
+    }
+  }
+  if (fragments_out) *fragments_out = f.fragments;
+  return 0;
+}
+
+/* Row table of one triangle (VertexShader + ComputePolygonRows), 8 words per
+ * row like ref_rast_rows in oracle/refbuild/ref_rast_harness.cpp. */
+int oracle_rast_rows(int W, int H, float focal, const float *verts12, int *y_min, int *n_rows,
+                     float *rows_out, int rows_cap) {
+  o_pixel vp[3];
+  for (int i = 0; i < 3; ++i) vertex_shader(verts12 + 4 * i, focal, W, H, &vp[i]);
+  o_pixel *L, *R;
+  int rows = compute_polygon_rows(vp, &L, &R);
+  *n_rows = rows;
+  *y_min = rows ? L[0].y : 0;
+  int rc = rows > rows_cap ? -1 : 0;
+  for (int r = 0; r < rows && rc == 0; ++r) {
+    float *o = rows_out + 8 * r;
+    memcpy(o + 0, &L[r].x, 4); memcpy(o + 1, &R[r].x, 4);
+    o[2] = L[r].zinv; o[3] = R[r].zinv;
+    o[4] = L[r].pos[0]; o[5] = L[r].pos[1];
+    o[6] = R[r].pos[0]; o[7] = R[r].pos[1];
+  }
+  free(L); free(R);
+  return rc;
+}
+
+/* KAT #1 helper: ComputePolygonRows on bare pixel vertices. */
+int oracle_rast_polygon_rows_kat(const int *xy6, int *y_min, int *n_rows, int *left_x, int *right_x, int cap) {
+  o_pixel vp[3];
+  memset(vp, 0, sizeof vp);
+  for (int i = 0; i < 3; ++i) { vp[i].x = xy6[2 * i]; vp[i].y = xy6[2 * i + 1]; }
+  o_pixel *L, *R;
+  int rows = compute_polygon_rows(vp, &L, &R);
+  *n_rows = rows;
+  *y_min = rows ? L[0].y : 0;
+  int rc = rows > cap ? -1 : 0;
+  for (int r = 0; r < rows && rc == 0; ++r) { left_x[r] = L[r].x; right_x[r] = R[r].x; }
+  free(L); free(R);
+  return rc;
+}

@@ -203,3 +203,109 @@ def random_rt_scene(n_tris, seed, extent=1.0, size=0.6, n_spheres=1):
         sph[i]["centre"] = rng.uniform(-0.7, 0.7, 3).astype(np.float32)
         sph[i]["color"] = rng.uniform(0.15, 0.75, 3).astype(np.float32)
     return tris, sph
+
+
+# ----------------------------------------------------------------------------
+# rasteriser: oracle + compiled reference wrappers
+# ----------------------------------------------------------------------------
+DEFAULT_RAST_LIGHT = dict(pos=(0.0, -0.5, 0.0, 1.0), power=(20.0, 20.0, 20.0), indirect=(0.2, 0.2, 0.2))
+DEFAULT_RAST_CAM = (0.0, 0.0, -3.001, 1.0)
+
+
+def ref_rast_name(W, H):
+    return f"libref_rast_{W}x{H}.so"
+
+
+def ref_rast_testmodel(W=64, H=48):
+    lib = ref_lib(ref_rast_name(W, H))
+    room, boxes = np.zeros(16, RAST_TRI), np.zeros(32, RAST_TRI)
+    a, b = c_i(0), c_i(0)
+    assert lib.ref_rast_load_testmodel(ptr(room), 16, ptr(boxes), 32, ctypes.byref(a), ctypes.byref(b)) == 0
+    return room[:a.value].copy(), boxes[:b.value].copy()
+
+
+def ref_rast_draw(W, H, focal, cam, R, light, room, boxes, clipped_cap=1 << 16):
+    """Whole reference Draw on a world-space scene."""
+    lib = ref_lib(ref_rast_name(W, H))
+    out = dict(argb=np.zeros((H, W), np.uint32), rgb=np.zeros((H, W, 3), np.float32),
+               depth=np.zeros((H, W), np.float32), screen_post=np.zeros((H, W, 3), np.float32),
+               low=np.zeros((H, W, 3), np.float32), high=np.zeros((H, W, 3), np.float32),
+               shadow=np.zeros((H, W), np.int32))
+    clipped = np.zeros(clipped_cap, RAST_TRI)
+    n = c_i(0)
+    lc = np.zeros(4, np.float32)
+    rc = lib.ref_rast_draw(c_f(focal), ptr(np.asarray(cam, np.float32)), ptr(np.asarray(R, np.float32)),
+                           ptr(f32(*light["pos"])), ptr(f32(*light["power"])), ptr(f32(*light["indirect"])),
+                           ptr(room), c_i(len(room)), ptr(boxes), c_i(len(boxes)),
+                           ptr(out["argb"]), ptr(out["rgb"]), ptr(out["depth"]), ptr(out["screen_post"]),
+                           ptr(out["low"]), ptr(out["high"]), ptr(out["shadow"]),
+                           ptr(clipped), c_i(clipped_cap), ctypes.byref(n), ptr(lc))
+    assert rc == 0, rc
+    out["clipped"] = clipped[:n.value].copy()
+    out["light_cam"] = lc
+    return out
+
+
+def ref_rast_draw_clipped(W, H, focal, light_cam, light, clipped, want_index=True):
+    lib = ref_lib(ref_rast_name(W, H))
+    out = dict(argb=np.zeros((H, W), np.uint32), rgb=np.zeros((H, W, 3), np.float32),
+               depth=np.zeros((H, W), np.float32), screen=np.zeros((H, W, 3), np.float32),
+               low=np.zeros((H, W, 3), np.float32), high=np.zeros((H, W, 3), np.float32),
+               shadow=np.zeros((H, W), np.int32),
+               index=np.zeros((H, W), np.int32) if want_index else None)
+    rc = lib.ref_rast_draw_clipped(c_f(focal), ptr(np.asarray(light_cam, np.float32)), ptr(f32(*light["power"])),
+                                   ptr(f32(*light["indirect"])), ptr(clipped), c_i(len(clipped)),
+                                   ptr(out["argb"]), ptr(out["rgb"]), ptr(out["depth"]), ptr(out["screen"]),
+                                   ptr(out["low"]), ptr(out["high"]), ptr(out["shadow"]), ptr(out["index"]))
+    assert rc == 0
+    return out
+
+
+def oracle_rast_draw_clipped(W, H, focal, light_cam, light, clipped):
+    lib = oracle()
+    out = dict(argb=np.zeros((H, W), np.uint32), rgb=np.zeros((H, W, 3), np.float32),
+               depth=np.zeros((H, W), np.float32), screen_post=np.zeros((H, W, 3), np.float32),
+               low=np.zeros((H, W, 3), np.float32), high=np.zeros((H, W, 3), np.float32),
+               shadow=np.zeros((H, W), np.int32), index=np.zeros((H, W), np.int32),
+               screen=np.zeros((H, W, 3), np.float32))
+    frags = np.zeros(1, np.uint64)
+    rc = lib.oracle_rast_draw_clipped(c_i(W), c_i(H), c_f(focal), ptr(np.asarray(light_cam, np.float32)),
+                                      ptr(f32(*light["power"])), ptr(f32(*light["indirect"])),
+                                      ptr(clipped), c_i(len(clipped)), ptr(out["depth"]), ptr(out["screen_post"]),
+                                      ptr(out["low"]), ptr(out["high"]), ptr(out["shadow"]), ptr(out["index"]),
+                                      ptr(out["screen"]), ptr(out["rgb"]), ptr(out["argb"]), ptr(frags))
+    assert rc == 0
+    out["fragments"] = int(frags[0])
+    return out
+
+
+def rows_call(fn, focal, verts, cap=1 << 14, dims=None):
+    y0, n = c_i(0), c_i(0)
+    rows = np.zeros((cap, 8), np.float32)
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1)
+    if dims is None:
+        rc = fn(c_f(focal), ptr(v), ctypes.byref(y0), ctypes.byref(n), ptr(rows), c_i(cap))
+    else:
+        rc = fn(c_i(dims[0]), c_i(dims[1]), c_f(focal), ptr(v), ctypes.byref(y0), ctypes.byref(n), ptr(rows), c_i(cap))
+    assert rc == 0
+    return y0.value, rows[:n.value].copy()
+
+
+def random_clipped_list(n, seed, W, H, focal, shadow_frac=0.3, size=0.5):
+    """Camera-space triangles in front of the camera that project near the screen
+    (what the reference's clip stage would hand to the triangle loop)."""
+    rng = np.random.default_rng(seed)
+    t = np.zeros(n, RAST_TRI)
+    z = rng.uniform(0.5, 4.0, n).astype(np.float32)
+    cx = (rng.uniform(-0.5, 0.5, n) * W / focal * z).astype(np.float32)
+    cy = (rng.uniform(-0.5, 0.5, n) * H / focal * z).astype(np.float32)
+    for name in ("v0", "v1", "v2"):
+        t[name][:, 0] = cx + rng.uniform(-size, size, n).astype(np.float32)
+        t[name][:, 1] = cy + rng.uniform(-size, size, n).astype(np.float32)
+        t[name][:, 2] = np.maximum(z + rng.uniform(-size, size, n).astype(np.float32), np.float32(0.05))
+        t[name][:, 3] = t[name][:, 2] / np.float32(focal)
+    t["color"] = rng.uniform(0.15, 0.75, (n, 3)).astype(np.float32)
+    sh = rng.uniform(0, 1, n) < shadow_frac
+    t["color"][sh] = -1.0
+    compute_normals(t)
+    return t
