@@ -67,8 +67,8 @@ void b200_destroy(b200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rast_src,
-                    &ctx->rast_setup, &ctx->rast_bins, &ctx->rast_tile_count, &ctx->rast_tile_off,
-                    &ctx->rast_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
+                    &ctx->rast_setup, &ctx->rast_rowsA, &ctx->rast_rowsB, &ctx->rast_bins, &ctx->rast_tile_count,
+                    &ctx->rast_tmp, &ctx->rast_clipped, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
                     &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
                     &ctx->out_argb, &ctx->counters};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -263,6 +263,76 @@ int draw_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_s
     return rc;
   if (int rc = copy_out(ctx, argb_out, ctx->out_argb.p, npix * sizeof(uint32_t))) return rc;
   return finish_stats(ctx);
+}
+
+// ---- RAST -------------------------------------------------------------------------------
+
+int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris) {
+  if (!ctx) return B200_EINVAL;
+  if (n_tris < 0 || (n_tris > 0 && !clipped)) return ctx_fail(ctx, B200_EINVAL, "bad triangle list");
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < n_tris; ++i)
+    if (clipped[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+  if (int rc = ensure(ctx, ctx->rast_src, sizeof(rast_triangle) * (size_t)(n_tris ? n_tris : 1))) return rc;
+  if (n_tris) CU_CHECK(ctx, cudaMemcpyAsync(ctx->rast_src.p, clipped, sizeof(rast_triangle) * (size_t)n_tris,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+  ctx->rast_n_tris = n_tris;
+  return B200_OK;
+}
+
+int rast_render_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin,
+                       int row_end, float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
+  if (!ctx) return B200_EINVAL;
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (!light) return ctx_fail(ctx, B200_EINVAL, "null light");
+  if (row_begin < 0 || row_end > cam->height || row_begin > row_end) return ctx_fail(ctx, B200_EINVAL, "bad row band");
+  cudaSetDevice(ctx->device);
+  ctx->stats.kernel_launches = 0;
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (int rc = rast_launch(ctx, cam, light, row_begin, row_end, d_rgb, d_depth, d_index, d_argb)) return rc;
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->pending = 2;
+  return B200_OK;
+}
+
+static int raster_host_outputs(b200_ctx *ctx, const camera_t *cam, float *rgb_out, float *depth_out,
+                               int32_t *index_out, uint32_t *argb_out) {
+  const size_t npix = (size_t)cam->width * cam->height;
+  if (rgb_out) if (int rc = ensure(ctx, ctx->out_rgb, npix * 3 * sizeof(float))) return rc;
+  if (depth_out) if (int rc = ensure(ctx, ctx->out_depth, npix * sizeof(float))) return rc;
+  if (index_out) if (int rc = ensure(ctx, ctx->out_index, npix * sizeof(int32_t))) return rc;
+  if (argb_out) if (int rc = ensure(ctx, ctx->out_argb, npix * sizeof(uint32_t))) return rc;
+  return B200_OK;
+}
+
+int render_raster_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris, const camera_t *cam,
+                          const rast_light_t *light, float *rgb_out, float *depth_out, int32_t *index_out) {
+  if (!ctx) return B200_EINVAL;
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (int rc = rast_upload_clipped(ctx, clipped, n_tris)) return rc;
+  if (int rc = raster_host_outputs(ctx, cam, rgb_out, depth_out, index_out, nullptr)) return rc;
+  if (int rc = rast_render_device(ctx, cam, light, 0, cam->height, rgb_out ? (float *)ctx->out_rgb.p : nullptr,
+                                  depth_out ? (float *)ctx->out_depth.p : nullptr,
+                                  index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr))
+    return rc;
+  const size_t npix = (size_t)cam->width * cam->height;
+  if (int rc = copy_out(ctx, rgb_out, ctx->out_rgb.p, npix * 3 * sizeof(float))) return rc;
+  if (int rc = copy_out(ctx, depth_out, ctx->out_depth.p, npix * sizeof(float))) return rc;
+  if (int rc = copy_out(ctx, index_out, ctx->out_index.p, npix * sizeof(int32_t))) return rc;
+  return finish_stats(ctx);
+}
+
+int raster_read_buffers(b200_ctx *ctx, float *screen_out, float *low_out, float *high_out, int32_t *shadow_out) {
+  if (!ctx) return B200_EINVAL;
+  if (ctx->rast_w <= 0) return ctx_fail(ctx, B200_EINVAL, "no raster frame rendered yet");
+  const size_t npix = (size_t)ctx->rast_w * ctx->rast_h;
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (screen_out) CU_CHECK(ctx, cudaMemcpy(screen_out, ctx->rast_screen.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (low_out) CU_CHECK(ctx, cudaMemcpy(low_out, ctx->rast_low.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (high_out) CU_CHECK(ctx, cudaMemcpy(high_out, ctx->rast_high.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (shadow_out) CU_CHECK(ctx, cudaMemcpy(shadow_out, ctx->rast_shadow.p, npix * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return B200_OK;
 }
 
 // ---- headless framebuffer -------------------------------------------------------------

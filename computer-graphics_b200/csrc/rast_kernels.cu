@@ -1,0 +1,667 @@
+// Rasteriser hot path on sm_100a: replaces the triangle loop and post pass of
+// rasteriser/Source/skeleton.cpp Draw :243-307 (DrawPolygon :420-431,
+// VertexShader :510-522, ComputePolygonRows :433-498, Interpolate :524-551,
+// DrawPolygonRows :500-508, PixelShader :559-672, calculateIllumination
+// :674-688, surroundingShadowSum :1725-1733, antiAliasing :1736-1753).
+//
+// The reference draws triangles strictly in list order into global buffers; the
+// result at a pixel is a fold over that pixel's fragments in triangle order:
+//   opaque  : accepted when zinv >= depth  => winner = max zinv, LATEST on ties
+//   shadow  : sets the pixel's flag when zinv > depth *as it stands then*
+// Pixels are independent, so the fold is done per pixel by one thread, over the
+// pixel's screen tile's triangle list in ascending index order.  Only the
+// depth test runs per fragment; shading is deferred to the single winning
+// fragment (the reference overwrites the colours of every earlier one).
+//
+// Coverage is the reference's float edge walk, reproduced exactly but in closed
+// form: along an edge one of x / y moves by exactly +-1 per sample, so per
+// (edge, row) the samples that land in the row form one run whose two ends are
+// found directly (rast_row_record); the reference's min-x / max-x "last equal
+// sample wins" rule is then replayed on at most six samples.
+//
+// Kernels per frame:
+//   rast_setup_kernel  per triangle: VertexShader, row range, row-table space,
+//                      tile counts
+//   rast_rows_kernel   per (triangle,row): left/right span ends + steps
+//   rast_scan_kernel   exclusive scan of tile counts
+//   rast_bin_kernel    per triangle: append to the tiles' lists (atomics)
+//   rast_fill_kernel   per tile: sort list, depth/shadow fold, deferred shading
+//   rast_post_kernel   shadow softening + 5-tap AA + "HDR" mean (:283-307)
+#include "common.cuh"
+#include <limits.h>
+
+constexpr int RAST_LIST_CAP = 2048;   // tile list entries sorted in shared memory
+constexpr int RAST_BATCH = 32;        // triangles per shared-memory row batch
+
+struct RastVtx {
+  int x, y;
+  float zinv, px, py;
+};
+
+struct RastSetup {   // 80 bytes
+  RastVtx v[3];
+  int ymin;          // smallest vertex y (row 0 of the reference's row table)
+  int row0;          // first stored row (clamped to the band being rendered)
+  int nrows;         // stored rows (0: nothing to draw)
+  unsigned row_off;  // index of the first stored row in the row arrays
+  int flags;         // bit0: shadow-volume triangle (colour.x < 0)
+};
+
+struct RastParams {
+  int W, H;
+  int fb0, fb1;      // rows the fill pass must produce (band + post-pass halo)
+  int row0, row1;    // rows the post pass writes
+  int ts_log2;       // screen-tile size (log2)
+  int tiles_x, tiles_y, ty0;  // tile grid; ty0 = first tile row of the band
+  float focal;
+  float light[4];
+  float power[3];
+  float indirect[3];
+  const rast_triangle *src;
+  int n_tris;
+  RastSetup *setup;
+  float4 *rowsA;     // lx, rx (bit-cast ints), left zinv, zinv step
+  float4 *rowsB;     // left px*zinv, its step, left py*zinv, its step
+  unsigned row_cap;
+  unsigned *tile_count, *tile_off, *tile_cursor;
+  int *bins, *bins_tmp;
+  unsigned bin_cap;
+  float *depth, *screen, *low, *high;
+  int *shadow, *index;
+  float *out_rgb;
+  float *out_depth;
+  int *out_index;
+  uint32_t *out_argb;
+  unsigned long long *counters;  // [2] fragments, [3] bin entries, [4] rows, [5] overflow flag
+};
+
+// ---- VertexShader (:510-522) ---------------------------------------------------------
+__device__ __forceinline__ bool rast_vertex(const float *v, float focal, int W, int H, RastVtx &o) {
+  const float x = xadd(xmul(focal, xdiv(v[0], v[2])), (float)(W / 2));
+  const float y = xadd(xmul(focal, xdiv(v[1], v[2])), (float)(H / 2));
+  // static_cast<int> of a value outside int range is undefined in the reference;
+  // such triangles (never produced by its clip stage) are dropped
+  if (!(fabsf(x) < 8.0e6f) || !(fabsf(y) < 8.0e6f)) return false;
+  o.x = (int)x;
+  o.y = (int)y;
+  o.zinv = xdiv(1.0f, v[2]);
+  o.px = v[0];
+  o.py = v[1];
+  return true;
+}
+
+__global__ void rast_setup_kernel(const __grid_constant__ RastParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int nrows = 0;
+  RastSetup s;
+  s.flags = 0; s.ymin = 0; s.row0 = 0; s.nrows = 0; s.row_off = 0;
+  int xmin = 0, xmax = -1;
+  if (t < p.n_tris) {
+    const rast_triangle *tr = p.src + t;
+    float v[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { v[0][k] = tr->v0[k]; v[1][k] = tr->v1[k]; v[2][k] = tr->v2[k]; }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ok = rast_vertex(v[k], p.focal, p.W, p.H, s.v[k]) && ok;
+    s.flags = tr->color[0] < 0 ? 1 : 0;
+    if (ok) {
+      const int ymin = min(s.v[0].y, min(s.v[1].y, s.v[2].y));
+      const int ymax = max(s.v[0].y, max(s.v[1].y, s.v[2].y));
+      xmin = min(s.v[0].x, min(s.v[1].x, s.v[2].x)) - 1;   // a minor-axis sample can undershoot by one
+      xmax = max(s.v[0].x, max(s.v[1].x, s.v[2].x));
+      s.ymin = ymin;
+      s.row0 = max(ymin, p.fb0);
+      const int rlast = min(ymax, p.fb1 - 1);
+      nrows = max(0, rlast - s.row0 + 1);
+      if (xmax <= 0 || xmin >= p.W || xmax <= xmin) nrows = 0;   // no pixel of [xmin, xmax) on screen
+    }
+    s.nrows = nrows;
+  }
+  // row-table space: one atomic per warp
+  unsigned incl = (unsigned)nrows;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned base = 0;
+  if (lane == 31 && total) base = (unsigned)atomicAdd(p.counters + 4, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (t >= p.n_tris) return;
+  s.row_off = base + incl - (unsigned)nrows;
+  if (s.row_off + (unsigned)nrows > p.row_cap) { s.nrows = 0; nrows = 0; atomicExch(p.counters + 5, 1ull); }
+  p.setup[t] = s;
+  if (nrows > 0) {
+    const int ts = p.ts_log2;
+    const int tx0 = max(0, xmin) >> ts, tx1 = min(p.W - 1, xmax - 1) >> ts;
+    const int tya = s.row0 >> ts, tyb = (s.row0 + nrows - 1) >> ts;
+    for (int ty = tya; ty <= tyb; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(p.tile_count + (size_t)(ty - p.ty0) * p.tiles_x + tx, 1u);
+  }
+}
+
+// ---- closed-form edge walk -------------------------------------------------------------
+struct RastEdge {
+  int ax, ay, n;       // start pixel, sample count
+  float sx, sy, den;
+};
+
+__device__ __forceinline__ int edge_px(const RastEdge &e, int i) {
+  return (int)floorf(xadd((float)e.ax, xmul(e.sx, (float)i)));   // :541
+}
+__device__ __forceinline__ int edge_py(const RastEdge &e, int i) {
+  return (int)floorf(xadd((float)e.ay, xmul(e.sy, (float)i)));   // :542
+}
+
+// Smallest i in [0, n] with (up ? y(i) >= Y : y(i) <= Y); y(i) is monotone in i.
+__device__ __forceinline__ int edge_first(const RastEdge &e, int Y, bool up) {
+  float est = ceilf(((float)(Y - e.ay)) / e.sy);
+  int i = est >= 0.f ? (est <= (float)e.n ? (int)est : e.n) : 0;   // NaN -> 0
+  if (up) {
+    while (i > 0 && edge_py(e, i - 1) >= Y) --i;
+    while (i < e.n && edge_py(e, i) < Y) ++i;
+  } else {
+    while (i > 0 && edge_py(e, i - 1) <= Y) --i;
+    while (i < e.n && edge_py(e, i) > Y) ++i;
+  }
+  return i;
+}
+
+// The samples of edge a->b (Interpolate with N = max(|dx|,|dy|)+1, :472-479) whose
+// floor(y) equals Y form one run [i0, i1]; returns false when the run is empty.
+__device__ __forceinline__ bool edge_run(const RastVtx &a, const RastVtx &b, int Y, RastEdge &e, int &i0, int &i1) {
+  const int dx = abs(a.x - b.x), dy = abs(a.y - b.y);
+  e.ax = a.x; e.ay = a.y;
+  e.n = max(dx, dy) + 1;
+  e.den = (float)max(e.n - 1, 1);
+  e.sx = xdiv((float)(b.x - a.x), e.den);   // :533
+  e.sy = xdiv((float)(b.y - a.y), e.den);   // :534
+  if (dy == 0) {                     // step_y = 0: every sample is in row a.y
+    if (Y != a.y) return false;
+    i0 = 0; i1 = e.n - 1;
+    return true;
+  }
+  if (dy >= dx) {                    // step_y = +-1 exactly: one sample per row
+    const int i = b.y > a.y ? Y - a.y : a.y - Y;
+    if (i < 0 || i > e.n - 1) return false;
+    i0 = i1 = i;
+    return true;
+  }
+  const bool up = b.y > a.y;         // |step_y| < 1: a run of samples per row
+  i0 = edge_first(e, Y, up);
+  i1 = edge_first(e, up ? Y + 1 : Y - 1, up) - 1;
+  return i0 <= i1 && i0 < e.n;
+}
+
+struct RastEnd { int x, e, i; };
+
+// Row Y of ComputePolygonRows' table (:481-495) and the span steps that
+// DrawPolygonRows' Interpolate derives from it (:502-503, :524-538).
+__device__ __forceinline__ void rast_row_record(const RastSetup &s, int Y, float4 &A, float4 &B) {
+  RastEnd L, R;
+  L.x = INT_MAX; L.e = -1; L.i = 0;
+  R.x = -INT_MAX; R.e = -1; R.i = 0;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    RastEdge ed;
+    int i0, i1;
+    if (!edge_run(s.v[e], s.v[(e + 1) % 3], Y, ed, i0, i1)) continue;
+    const int x0 = edge_px(ed, i0);
+    if (x0 <= L.x) { L.x = x0; L.e = e; L.i = i0; }
+    if (x0 >= R.x) { R.x = x0; R.e = e; R.i = i0; }
+    if (i1 > i0) {
+      const int x1 = edge_px(ed, i1);
+      if (x1 <= L.x) { L.x = x1; L.e = e; L.i = i1; }
+      if (x1 >= R.x) { R.x = x1; R.e = e; R.i = i1; }
+    }
+  }
+  if (L.e < 0) {   // unreachable for a valid triangle: every row receives a sample
+    A = make_float4(__int_as_float(0), __int_as_float(0), 0.f, 0.f);
+    B = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float zinv[2], px[2], py[2];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const RastEnd &E = side ? R : L;
+    const RastVtx &a = s.v[E.e], &b = s.v[(E.e + 1) % 3];
+    const int n = max(abs(a.x - b.x), abs(a.y - b.y)) + 1;
+    const float den = (float)max(n - 1, 1);
+    const float apx = xmul(a.px, a.zinv), apy = xmul(a.py, a.zinv);   // :526-530
+    const float bpx = xmul(b.px, b.zinv), bpy = xmul(b.py, b.zinv);
+    const float sz = xdiv(xsub(b.zinv, a.zinv), den);                 // :535
+    const float spx = xdiv(xsub(bpx, apx), den), spy = xdiv(xsub(bpy, apy), den);   // :537-538
+    const float fi = (float)E.i;
+    zinv[side] = xadd(a.zinv, xmul(sz, fi));                          // :543
+    px[side] = xdiv(xadd(apx, xmul(spx, fi)), zinv[side]);            // :547
+    py[side] = xdiv(xadd(apy, xmul(spy, fi)), zinv[side]);            // :548
+  }
+  const int n = R.x - L.x + 1;
+  const float den = (float)max(n - 1, 1);
+  const float lpx = xmul(px[0], zinv[0]), lpy = xmul(py[0], zinv[0]);
+  const float rpx = xmul(px[1], zinv[1]), rpy = xmul(py[1], zinv[1]);
+  A = make_float4(__int_as_float(L.x), __int_as_float(R.x), zinv[0], xdiv(xsub(zinv[1], zinv[0]), den));
+  B = make_float4(lpx, xdiv(xsub(rpx, lpx), den), lpy, xdiv(xsub(rpy, lpy), den));
+}
+
+// 8 lanes per triangle, lanes stride the triangle's stored rows.
+__global__ void rast_rows_kernel(const __grid_constant__ RastParams p) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = gid >> 3, sub = gid & 7;
+  if (t >= p.n_tris) return;
+  const RastSetup s = p.setup[t];
+  for (int r = sub; r < s.nrows; r += 8) {
+    float4 A, B;
+    rast_row_record(s, s.row0 + r, A, B);
+    p.rowsA[s.row_off + r] = A;
+    p.rowsB[s.row_off + r] = B;
+  }
+}
+
+// ---- tile lists ---------------------------------------------------------------------------
+__global__ void rast_scan_kernel(const __grid_constant__ RastParams p, int n_tiles) {
+  __shared__ unsigned warp_excl[32];
+  __shared__ unsigned chunk_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned carry = 0;   // identical in every thread
+  for (int base = 0; base < n_tiles; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const unsigned v = i < n_tiles ? p.tile_count[i] : 0u;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_excl[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned w = lane < nw ? warp_excl[lane] : 0u;
+      unsigned wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += n;
+      }
+      warp_excl[lane] = wi - w;
+      if (lane == 31) chunk_total = wi;
+    }
+    __syncthreads();
+    if (i < n_tiles) { p.tile_off[i] = carry + warp_excl[warp] + incl - v; p.tile_cursor[i] = 0; }
+    carry += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { p.tile_off[n_tiles] = carry; p.counters[3] = carry; }
+}
+
+// 8 lanes per triangle, lanes stride the overlapped tiles.
+__global__ void rast_bin_kernel(const __grid_constant__ RastParams p) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = gid >> 3, sub = gid & 7;
+  if (t >= p.n_tris) return;
+  const RastSetup s = p.setup[t];
+  if (s.nrows <= 0) return;
+  const int ts = p.ts_log2;
+  const int xmin = min(s.v[0].x, min(s.v[1].x, s.v[2].x)) - 1;
+  const int xmax = max(s.v[0].x, max(s.v[1].x, s.v[2].x));
+  const int tx0 = max(0, xmin) >> ts, tx1 = min(p.W - 1, xmax - 1) >> ts;
+  const int tya = s.row0 >> ts, tyb = (s.row0 + s.nrows - 1) >> ts;
+  const int nx = tx1 - tx0 + 1, n = nx * (tyb - tya + 1);
+  for (int k = sub; k < n; k += 8) {
+    const int ty = tya + k / nx, tx = tx0 + k % nx;
+    const size_t tile = (size_t)(ty - p.ty0) * p.tiles_x + tx;
+    const unsigned pos = atomicAdd(p.tile_cursor + tile, 1u);
+    const unsigned at = p.tile_off[tile] + pos;
+    if (at < p.bin_cap) p.bins[at] = t;
+  }
+}
+
+// ---- calculateIllumination (:674-688) without the final "+ indirect" -----------------------
+__device__ __forceinline__ void rast_illum_D(const RastParams &p, float x, float y, float z, float nx, float ny,
+                                             float nz, float *D) {
+  const float rx = xsub(p.light[0], x), ry = xsub(p.light[1], y), rz = xsub(p.light[2], z);
+  const double r2d = __dadd_rn(__dadd_rn(__dmul_rn((double)rx, (double)rx), __dmul_rn((double)ry, (double)ry)),
+                               __dmul_rn((double)rz, (double)rz));
+  const float r_mag = __double2float_rn(r2d);                                       // :677
+  const float vp = xadd(xadd(xmul(rx, nx), xmul(ry, ny)), xmul(rz, nz));           // :681
+  const float m = vp < 0.0f ? 0.0f : vp;                                            // glm::max
+  const float den = __double2float_rn(__dmul_rn((double)4.0f * 3.14159265358979323846, (double)r_mag));  // :682
+#pragma unroll
+  for (int k = 0; k < 3; ++k) D[k] = xdiv(xmul(p.power[k], m), den);
+}
+
+// In-place ascending sort of a tile's list in global memory when it does not fit
+// in shared memory: LSD radix sort, one bit per pass (a stable split), by the
+// whole block.  Only pathological scenes (> RAST_LIST_CAP triangles over one
+// tile) come here.
+__device__ void rast_sort_global(int *a, int *tmp, int n, int max_key, unsigned *scratch) {
+  const int T = blockDim.x;
+  int bits = 1;
+  while ((1 << bits) <= max_key && bits < 31) ++bits;
+  int *src = a, *dst = tmp;
+  for (int b = 0; b < bits; ++b) {
+    // count zeros
+    unsigned z = 0;
+    for (int i = threadIdx.x; i < n; i += T) z += ((src[i] >> b) & 1) ? 0u : 1u;
+    if (threadIdx.x == 0) scratch[0] = 0;
+    __syncthreads();
+    atomicAdd(&scratch[0], z);
+    __syncthreads();
+    const unsigned n_zero = scratch[0];
+    __syncthreads();
+    unsigned run0 = 0, run1 = 0;   // elements placed so far in each half
+    for (int base = 0; base < n; base += T) {
+      const int i = base + threadIdx.x;
+      const int key = i < n ? src[i] : 0;
+      const unsigned one = i < n ? (unsigned)((key >> b) & 1) : 0u;
+      const unsigned zero = i < n ? 1u - one : 0u;
+      // block-wide exclusive scan of `zero` through shared scratch[1..T]
+      scratch[1 + threadIdx.x] = zero;
+      __syncthreads();
+      for (int o = 1; o < T; o <<= 1) {
+        const unsigned add = threadIdx.x >= o ? scratch[1 + threadIdx.x - o] : 0u;
+        __syncthreads();
+        scratch[1 + threadIdx.x] += add;
+        __syncthreads();
+      }
+      const unsigned incl = scratch[1 + threadIdx.x];
+      const unsigned chunk_zero = scratch[T];
+      const int in_chunk = min(T, n - base);
+      if (i < n) {
+        if (zero) dst[run0 + incl - 1] = key;
+        else dst[n_zero + run1 + (threadIdx.x - (incl))] = key;
+      }
+      run0 += chunk_zero;
+      run1 += (unsigned)in_chunk - chunk_zero;
+      __syncthreads();
+    }
+    int *sw = src; src = dst; dst = sw;
+    __threadfence_block();
+    __syncthreads();
+  }
+  if (src != a) {
+    for (int i = threadIdx.x; i < n; i += T) a[i] = src[i];
+    __syncthreads();
+  }
+}
+
+// ---- per-tile fold + deferred shading -------------------------------------------------------
+template <int TS_LOG2>
+__global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __grid_constant__ RastParams p) {
+  constexpr int TS = 1 << TS_LOG2, NT = TS * TS, NW = NT / 32;
+  __shared__ int list[RAST_LIST_CAP];
+  __shared__ float4 recA[RAST_BATCH][TS];
+  __shared__ int recFlags[RAST_BATCH];
+  __shared__ unsigned scratch[NT + 2];
+
+  const int tile_x = blockIdx.x, tile_y = p.ty0 + blockIdx.y;
+  const size_t tile = (size_t)blockIdx.y * p.tiles_x + tile_x;
+  const unsigned off = p.tile_off[tile];
+  const int cnt = (int)min(p.tile_off[tile + 1] - off, p.bin_cap > off ? p.bin_cap - off : 0u);
+  const int lx_ = threadIdx.x & (TS - 1), ly_ = threadIdx.x >> TS_LOG2;
+  const int x = (tile_x << TS_LOG2) + lx_, y = (tile_y << TS_LOG2) + ly_;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- the tile's triangle list in ascending order ----
+  const int *sorted;
+  if (cnt <= RAST_LIST_CAP) {
+    int m = 1;
+    while (m < cnt) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += NT) list[i] = i < cnt ? p.bins[off + i] : INT_MAX;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1)            // bitonic sort
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < m; i += NT) {
+          const int q = i ^ j;
+          if (q > i) {
+            const int a = list[i], b = list[q];
+            const bool asc = (i & k) == 0;
+            if ((a > b) == asc) { list[i] = b; list[q] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    sorted = list;
+  } else {
+    rast_sort_global(p.bins + off, p.bins_tmp + off, cnt, p.n_tris, scratch);
+    sorted = p.bins + off;
+  }
+
+  // ---- fold the fragments of this pixel in triangle order ----
+  float depth = 0.f;       // depthBuffer cleared to 0 (:247)
+  int win = -1;
+  int shadow = 0;
+  unsigned n_frag = 0;
+  const bool on_screen = x < p.W && y < p.H;
+  for (int b0 = 0; b0 < cnt; b0 += RAST_BATCH) {
+    const int nb = min(RAST_BATCH, cnt - b0);
+    __syncthreads();
+    // stage row records: warp w takes triangles w, w+NW, ...; lane = tile row
+    for (int b = warp; b < nb; b += NW) {
+      const int t = sorted[b0 + b];
+      const RastSetup *s = p.setup + t;
+      const int row0 = s->row0, nrows = s->nrows;
+      if (lane == 0) recFlags[b] = s->flags;
+      if (lane < TS) {
+        const int yy = (tile_y << TS_LOG2) + lane;
+        const int r = yy - row0;
+        float4 A = make_float4(__int_as_float(0), __int_as_float(0), 0.f, 0.f);
+        if (r >= 0 && r < nrows) A = p.rowsA[s->row_off + r];
+        recA[b][lane] = A;
+      }
+    }
+    __syncthreads();
+    if (on_screen) {
+      for (int b = 0; b < nb; ++b) {
+        const float4 A = recA[b][ly_];
+        const int lx = __float_as_int(A.x), rx = __float_as_int(A.y);
+        // fragments x = lx .. rx-1 (right end excluded, :504); (:573) bounds hold by construction
+        if (x >= lx && x < rx) {
+          ++n_frag;
+          const float zinv = xadd(A.z, xmul(A.w, (float)(x - lx)));   // :543
+          if (recFlags[b] & 1) {
+            if (zinv > depth) shadow = 1;                            // :668-670
+          } else if (zinv >= depth) {                                // :574
+            depth = zinv;                                            // :665
+            win = sorted[b0 + b];
+          }
+        }
+      }
+    }
+  }
+
+  // ---- deferred PixelShader of the winning fragment (:575-586) ----
+  if (on_screen && y >= p.fb0 && y < p.fb1) {
+    const size_t q = (size_t)y * p.W + x;
+    float sc[3] = {0.f, 0.f, 0.f}, lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+    if (win >= 0) {
+      const RastSetup *s = p.setup + win;
+      const unsigned r = s->row_off + (unsigned)(y - s->row0);
+      const float4 A = p.rowsA[r], B = p.rowsB[r];
+      const float fi = (float)(x - __float_as_int(A.x));
+      const float zinv = xadd(A.z, xmul(A.w, fi));
+      const float pz = xdiv(1.0f, zinv);                              // :546
+      const float px = xdiv(xadd(B.x, xmul(B.y, fi)), zinv);          // :547
+      const float py = xdiv(xadd(B.z, xmul(B.w, fi)), zinv);          // :548
+      const rast_triangle *tr = p.src + win;
+      float D[3];
+      rast_illum_D(p, px, py, pz, tr->normal[0], tr->normal[1], tr->normal[2], D);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float c = tr->color[k];
+        sc[k] = xmul(c, xadd(D[k], p.indirect[k]));   // :580
+        lo[k] = xmul(c, xadd(D[k], 0.0f));            // :581-582
+        hi[k] = xmul(c, xadd(D[k], 0.4f));            // :583-584
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { p.screen[3 * q + k] = sc[k]; p.low[3 * q + k] = lo[k]; p.high[3 * q + k] = hi[k]; }
+    p.depth[q] = depth;
+    p.shadow[q] = shadow;
+    p.index[q] = win;
+  }
+  unsigned long long nf = (on_screen && y >= p.fb0 && y < p.fb1) ? n_frag : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  if (lane == 0 && nf) atomicAdd(p.counters + 2, nf);
+}
+
+// ---- post pass (:283-307) --------------------------------------------------------------------
+// The reference darkens screenBuffer in place while scanning row-major, so the
+// 5-tap cross at (y,x) sees darkened (y,x), (y-1,x), (y,x-1) and original
+// (y+1,x), (y,x+1).  The amount depends only on the final shadow mask, so every
+// pixel can be evaluated independently.
+__device__ __forceinline__ float rast_sub(const RastParams &p, int y, int x) {
+  if (y < 1 || y > p.H - 2 || x < 1 || x > p.W - 2) return 0.f;   // never visited by the loop
+  const int *s = p.shadow;
+  const size_t W = p.W;
+  if (s[y * W + x] != 1) return 0.f;
+  // surroundingShadowSum (:1725-1733): [y+1][x-1] counted twice, [y+1][x+1] never
+  const int sum = s[y * W + x] + s[(y - 1) * W + x] + s[(y - 1) * W + x - 1] + s[(y - 1) * W + x + 1] +
+                  s[(y + 1) * W + x - 1] + s[(y + 1) * W + x] + s[(y + 1) * W + x - 1] + s[y * W + x - 1] +
+                  s[y * W + x + 1];
+  const float f = xdiv((float)sum, 9.0f);
+  const double d = (double)f;
+  return d < 0.6 ? 0.05f : d < 0.7 ? 0.08f : d < 0.8 ? 0.1f : d < 0.9 ? 0.12f : 0.3f;
+}
+
+__global__ void rast_post_kernel(const __grid_constant__ RastParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = p.row0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= p.W || y >= p.row1) return;
+  const size_t W = p.W, q = (size_t)y * W + x;
+  float out[3] = {0.f, 0.f, 0.f};
+  const bool interior = y >= 1 && y <= p.H - 2 && x >= 1 && x <= p.W - 2;
+  if (interior) {
+    const float s0 = rast_sub(p, y, x), s1 = rast_sub(p, y - 1, x), s2 = rast_sub(p, y, x - 1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float *S = p.screen + k, *L = p.low + k, *Hh = p.high + k;
+      // the reference only subtracts when the flag is set; x - 0 == x keeps that exact
+      const float c0 = s0 != 0.f ? xsub(S[3 * q], s0) : S[3 * q];
+      const float c1 = s1 != 0.f ? xsub(S[3 * (q - W)], s1) : S[3 * (q - W)];
+      const float c2 = s2 != 0.f ? xsub(S[3 * (q - 1)], s2) : S[3 * (q - 1)];
+      float a = xadd(c0, c1);
+      a = xadd(a, S[3 * (q + W)]);
+      a = xadd(a, c2);
+      a = xadd(a, S[3 * (q + 1)]);
+      a = xdiv(a, 5.0f);
+      float b = xadd(L[3 * q], L[3 * (q - W)]);
+      b = xadd(b, L[3 * (q + W)]);
+      b = xadd(b, L[3 * (q - 1)]);
+      b = xadd(b, L[3 * (q + 1)]);
+      b = xdiv(b, 5.0f);
+      float c = xadd(Hh[3 * q], Hh[3 * (q - W)]);
+      c = xadd(c, Hh[3 * (q + W)]);
+      c = xadd(c, Hh[3 * (q - 1)]);
+      c = xadd(c, Hh[3 * (q + 1)]);
+      c = xdiv(c, 5.0f);
+      out[k] = xdiv(xadd(xadd(a, b), c), 3.0f);   // :1750
+    }
+  }
+  if (p.out_rgb) { p.out_rgb[3 * q] = out[0]; p.out_rgb[3 * q + 1] = out[1]; p.out_rgb[3 * q + 2] = out[2]; }
+  if (p.out_argb) p.out_argb[q] = interior ? put_pixel_argb(out[0], out[1], out[2]) : 0u;   // border: memset 0 (:244)
+  if (p.out_depth) p.out_depth[q] = p.depth[q];
+  if (p.out_index) p.out_index[q] = p.index[q];
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row0, int row1,
+                float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
+  const int W = cam->width, H = cam->height, n = ctx->rast_n_tris;
+  RastParams p;
+  memset(&p, 0, sizeof p);
+  p.W = W; p.H = H;
+  p.row0 = row0; p.row1 = row1;
+  p.fb0 = row0 - 2 > 0 ? row0 - 2 : 0;
+  p.fb1 = row1 + 2 < H ? row1 + 2 : H;
+  p.ts_log2 = ctx->opt_rast_tile_log2;
+  const int ts = p.ts_log2, TS = 1 << ts;
+  p.tiles_x = (W + TS - 1) >> ts;
+  p.ty0 = p.fb0 >> ts;
+  p.tiles_y = ((p.fb1 - 1) >> ts) - p.ty0 + 1;
+  const int n_tiles = p.tiles_x * p.tiles_y;
+  p.focal = cam->focal;
+  memcpy(p.light, light->pos, sizeof p.light);
+  memcpy(p.power, light->power, sizeof p.power);
+  memcpy(p.indirect, light->indirect, sizeof p.indirect);
+  p.src = (const rast_triangle *)ctx->rast_src.p;
+  p.n_tris = n;
+
+  const size_t npix = (size_t)W * H;
+  // worst case rows: every triangle spans the whole band
+  size_t row_cap = (size_t)n * (size_t)(p.fb1 - p.fb0);
+  const size_t row_budget = (size_t)64 << 20;   // 64 Mi rows = 2 GiB of row records
+  if (row_cap > row_budget) row_cap = row_budget;
+  if (row_cap < 1) row_cap = 1;
+  if (int rc = ensure(ctx, ctx->rast_setup, sizeof(RastSetup) * (size_t)(n ? n : 1))) return rc;
+  if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(float4) * row_cap)) return rc;
+  if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * row_cap)) return rc;
+  if (int rc = ensure(ctx, ctx->rast_tile_count, sizeof(unsigned) * (size_t)(n_tiles + 1) * 3)) return rc;
+  if (int rc = ensure(ctx, ctx->rast_screen, npix * 3 * sizeof(float))) return rc;
+  if (int rc = ensure(ctx, ctx->rast_low, npix * 3 * sizeof(float))) return rc;
+  if (int rc = ensure(ctx, ctx->rast_high, npix * 3 * sizeof(float))) return rc;
+  if (int rc = ensure(ctx, ctx->rast_shadow, npix * sizeof(int))) return rc;
+  if (int rc = ensure(ctx, ctx->rast_depth, npix * sizeof(float))) return rc;
+  if (int rc = ensure(ctx, ctx->rast_index, npix * sizeof(int))) return rc;
+  ctx->rast_w = W; ctx->rast_h = H;
+  p.setup = (RastSetup *)ctx->rast_setup.p;
+  p.rowsA = (float4 *)ctx->rast_rowsA.p;
+  p.rowsB = (float4 *)ctx->rast_rowsB.p;
+  p.row_cap = (unsigned)(row_cap > 0xffffffffull ? 0xffffffffull : row_cap);
+  p.tile_count = (unsigned *)ctx->rast_tile_count.p;
+  p.tile_off = p.tile_count + (n_tiles + 1);
+  p.tile_cursor = p.tile_off + (n_tiles + 1);
+  p.depth = (float *)ctx->rast_depth.p;
+  p.screen = (float *)ctx->rast_screen.p;
+  p.low = (float *)ctx->rast_low.p;
+  p.high = (float *)ctx->rast_high.p;
+  p.shadow = (int *)ctx->rast_shadow.p;
+  p.index = (int *)ctx->rast_index.p;
+  p.out_rgb = d_rgb; p.out_depth = d_depth; p.out_index = d_index; p.out_argb = d_argb;
+  p.counters = (unsigned long long *)ctx->counters.p;
+
+  CU_CHECK(ctx, cudaMemsetAsync(p.tile_count, 0, sizeof(unsigned) * (size_t)(n_tiles + 1), ctx->stream));
+  if (n > 0) {
+    rast_setup_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(p);
+    ctx->stats.kernel_launches++;
+    rast_rows_kernel<<<(int)(((size_t)n * 8 + 255) / 256), 256, 0, ctx->stream>>>(p);
+    ctx->stats.kernel_launches++;
+  }
+  rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
+  ctx->stats.kernel_launches++;
+  CU_CHECK(ctx, cudaGetLastError());
+  // the bin array is sized from the scanned total: read it back (tiny, one sync)
+  unsigned long long c[8];
+  CU_CHECK(ctx, cudaMemcpyAsync(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (c[5]) return ctx_fail(ctx, B200_ENOMEM, "row table budget exceeded (triangles too tall for this band)");
+  const size_t bin_total = (size_t)c[3];
+  if (int rc = ensure(ctx, ctx->rast_bins, sizeof(int) * (bin_total ? bin_total : 1))) return rc;
+  if (int rc = ensure(ctx, ctx->rast_tmp, sizeof(int) * (bin_total ? bin_total : 1))) return rc;
+  p.bins = (int *)ctx->rast_bins.p;
+  p.bins_tmp = (int *)ctx->rast_tmp.p;
+  p.bin_cap = (unsigned)bin_total;
+  if (n > 0 && bin_total > 0) {
+    rast_bin_kernel<<<(int)(((size_t)n * 8 + 255) / 256), 256, 0, ctx->stream>>>(p);
+    ctx->stats.kernel_launches++;
+  }
+  dim3 grid(p.tiles_x, p.tiles_y);
+  switch (ts) {
+    case 3: rast_fill_kernel<3><<<grid, 64, 0, ctx->stream>>>(p); break;
+    case 4: rast_fill_kernel<4><<<grid, 256, 0, ctx->stream>>>(p); break;
+    default: rast_fill_kernel<5><<<grid, 1024, 0, ctx->stream>>>(p); break;
+  }
+  ctx->stats.kernel_launches++;
+  CU_CHECK(ctx, cudaGetLastError());
+  if (row1 > row0) {
+    dim3 pb(32, 8), pg((W + 31) / 32, (row1 - row0 + 7) / 8);
+    rast_post_kernel<<<pg, pb, 0, ctx->stream>>>(p);
+    ctx->stats.kernel_launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+  }
+  return B200_OK;
+}

@@ -60,7 +60,36 @@ def make_rt():
     print("rt goldens written")
 
 
+
+
+def make_rast():
+    """Rasteriser goldens: the compiled reference's whole Draw on its own Cornell
+    box (untextured), with the clipped list it built and its buffers."""
+    for (W, H, f, yaw, keys) in [(64, 48, 36.0, 0.0, ("rgb", "argb", "depth", "low", "high", "shadow", "screen_post")),
+                                 (320, 240, 170.0, 0.0, ("rgb", "depth", "shadow")),
+                                 (320, 240, 170.0, -0.174533, ("rgb", "depth", "shadow"))]:
+        room, boxes = h.ref_rast_testmodel(W, H)
+        R = h.yaw_R(yaw) if yaw else h.identity_R()
+        r = h.ref_rast_draw(W, H, f, h.DEFAULT_RAST_CAM, R, h.DEFAULT_RAST_LIGHT, room, boxes)
+        r2 = h.ref_rast_draw_clipped(W, H, f, r["light_cam"], h.DEFAULT_RAST_LIGHT, r["clipped"])
+        assert np.array_equal(r2["rgb"].view(np.uint32), r["rgb"].view(np.uint32))
+        out = {k: r[k] for k in keys}
+        name = f"rast_ref_cornell_{W}x{H}" + ("_yaw" if yaw else "")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), W=W, H=H, focal=f, cam=h.f32(*h.DEFAULT_RAST_CAM),
+                            R=R, light_cam=r["light_cam"], clipped=r["clipped"].view(np.uint8),
+                            room=room.view(np.uint8), boxes=boxes.view(np.uint8), index=r2["index"],
+                            screen=r2["screen"] if W == 64 else np.zeros(0, np.float32), **out)
+    # a random clipped list with shadow triangles, equal depths and off-screen parts
+    W, H, f = 64, 48, 40.0
+    tl = h.random_clipped_list(60, 5, W, H, f)
+    lc = h.f32(0.1, -0.3, 1.2, 1.0)
+    r = h.ref_rast_draw_clipped(W, H, f, lc, h.DEFAULT_RAST_LIGHT, tl)
+    np.savez_compressed(os.path.join(HERE, "rast_ref_random60_64x48.npz"), W=W, H=H, focal=f, light_cam=lc,
+                        clipped=tl.view(np.uint8), rgb=r["rgb"], argb=r["argb"], depth=r["depth"],
+                        screen=r["screen"], low=r["low"], high=r["high"], shadow=r["shadow"], index=r["index"])
+    print("rast goldens written")
+
+
 if __name__ == "__main__":
     make_rt()
-    if hasattr(sys.modules[__name__], "make_rast"):
-        make_rast()
+    make_rast()

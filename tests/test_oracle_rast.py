@@ -1,0 +1,93 @@
+"""CPU tests: pin the plain-C rasteriser oracle against KAT #1, the committed
+outputs of the compiled reference, and (when present) the compiled reference."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import helpers as h
+from conftest import load_golden
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+# rasteriser/Instructions/instructions.pdf, "ComputePolygonRows ... should give
+# the output" (the commented-out test at rasteriser/Source/skeleton.cpp:183-199)
+KAT1 = [(10, 5, 10, 5), (9, 6, 10, 6), (8, 7, 11, 7), (7, 8, 11, 8), (6, 9, 12, 9), (5, 10, 12, 10),
+        (7, 11, 13, 11), (9, 12, 13, 12), (11, 13, 14, 13), (13, 14, 14, 14), (15, 15, 15, 15)]
+
+
+def test_kat1_compute_polygon_rows():
+    lib = h.oracle()
+    xy = np.array([10, 5, 5, 10, 15, 15], np.int32)
+    y0, n = h.c_i(), h.c_i()
+    lx, rx = np.zeros(64, np.int32), np.zeros(64, np.int32)
+    assert lib.oracle_rast_polygon_rows_kat(h.ptr(xy), ctypes.byref(y0), ctypes.byref(n), h.ptr(lx), h.ptr(rx), 64) == 0
+    got = [(int(lx[r]), y0.value + r, int(rx[r]), y0.value + r) for r in range(n.value)]
+    assert got == KAT1
+
+
+@pytest.mark.parametrize("name", ["rast_ref_cornell_64x48", "rast_ref_cornell_320x240", "rast_ref_cornell_320x240_yaw",
+                                  "rast_ref_random60_64x48"])
+def test_oracle_matches_committed_reference_outputs(name):
+    g = load_golden(name + ".npz")
+    W, H = int(g["W"]), int(g["H"])
+    clipped = g["clipped"].view(h.RAST_TRI)
+    o = h.oracle_rast_draw_clipped(W, H, float(g["focal"]), g["light_cam"], h.DEFAULT_RAST_LIGHT, clipped)
+    for key in ("rgb", "depth", "low", "high", "screen_post"):
+        if key in g.files:
+            assert np.array_equal(bits(o[key]), bits(g[key])), key
+    if "screen" in g.files and g["screen"].size:
+        assert np.array_equal(bits(o["screen"]), bits(g["screen"]))
+    assert np.array_equal(o["shadow"], g["shadow"])
+    assert np.array_equal(o["index"], g["index"])
+    if "argb" in g.files:
+        assert np.array_equal(o["argb"], g["argb"])
+
+
+def test_rows_vs_compiled_reference():
+    if not h.have_ref(h.ref_rast_name(64, 48)):
+        pytest.skip("oracle/_ref not built")
+    ref = h.ref_lib(h.ref_rast_name(64, 48))
+    lib = h.oracle()
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        v = np.zeros((3, 4), np.float32)
+        v[:, :2] = rng.uniform(-1.5, 1.5, (3, 2))
+        v[:, 2] = rng.uniform(0.3, 3, 3)
+        v[:, 3] = 1
+        a = h.rows_call(ref.ref_rast_rows, 40.0, v)
+        b = h.rows_call(lib.oracle_rast_rows, 40.0, v, dims=(64, 48))
+        assert a[0] == b[0] and a[1].shape == b[1].shape
+        assert np.array_equal(bits(a[1]), bits(b[1]))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_vs_compiled_reference_random_lists(seed):
+    if not h.have_ref(h.ref_rast_name(64, 48)):
+        pytest.skip("oracle/_ref not built")
+    W, H, f = 64, 48, 40.0
+    tl = h.random_clipped_list(80 + 40 * seed, 50 + seed, W, H, f, size=0.3 + 0.3 * seed)
+    lc = h.f32(0.1, -0.3, 1.2, 1.0)
+    r = h.ref_rast_draw_clipped(W, H, f, lc, h.DEFAULT_RAST_LIGHT, tl)
+    o = h.oracle_rast_draw_clipped(W, H, f, lc, h.DEFAULT_RAST_LIGHT, tl)
+    for key in ("rgb", "depth", "low", "high", "screen"):
+        assert np.array_equal(bits(o[key]), bits(r[key])), key
+    assert np.array_equal(o["shadow"], r["shadow"]) and np.array_equal(o["index"], r["index"])
+    assert np.array_equal(o["argb"], r["argb"])
+
+
+def test_whole_draw_default_config():
+    """BASELINE config 2: 900x720, f = 512: 303 clipped triangles, the fragment count
+    SURVEY.md quotes, and the oracle equal to the reference's whole Draw."""
+    if not h.have_ref(h.ref_rast_name(900, 720)):
+        pytest.skip("oracle/_ref not built")
+    room, boxes = h.ref_rast_testmodel(900, 720)
+    r = h.ref_rast_draw(900, 720, 512.0, h.DEFAULT_RAST_CAM, h.identity_R(), h.DEFAULT_RAST_LIGHT, room, boxes)
+    assert len(r["clipped"]) == 303
+    o = h.oracle_rast_draw_clipped(900, 720, 512.0, r["light_cam"], h.DEFAULT_RAST_LIGHT, r["clipped"])
+    assert np.array_equal(bits(o["rgb"]), bits(r["rgb"])) and np.array_equal(o["argb"], r["argb"])
+    assert np.array_equal(bits(o["depth"]), bits(r["depth"])) and np.array_equal(o["shadow"], r["shadow"])
+    assert not o["rgb"][0].any() and not o["rgb"][:, 0].any()   # border never written

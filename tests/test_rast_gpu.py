@@ -1,0 +1,160 @@
+"""GPU parity tests for the rasteriser path: CUDA kernels (through the C ABI)
+against the plain-C oracle and the committed reference outputs.  Bar: bit-exact
+depth, colour buffers, shadow mask, owner index and final colour."""
+import numpy as np
+import pytest
+
+import helpers as h
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def compare(b200, renderer, W, H, focal, light_cam, light, clipped, what, tiles=(4, 5, 3)):
+    want = h.oracle_rast_draw_clipped(W, H, focal, light_cam, light, clipped)
+    cam = b200.make_camera((0, 0, 0, 1), focal, h.identity_R(), W, H)
+    L = b200.make_rast_light(light_cam, light["power"], light["indirect"])
+    for ts in tiles:
+        renderer.set_option(b200.OPT_RAST_TILE_LOG2, ts)
+        got = renderer.render_raster_clipped(clipped, cam, L)
+        st = renderer.stats()
+        buf = renderer.raster_read_buffers(W, H)
+        tag = f"{what} [tile {1 << ts}]"
+        assert np.array_equal(got["index"], want["index"]), f"{tag}: owner differs at {np.count_nonzero(got['index'] != want['index'])} px"
+        assert np.array_equal(bits(got["depth"]), bits(want["depth"])), f"{tag}: depth"
+        assert np.array_equal(buf["shadow"], want["shadow"]), f"{tag}: shadow mask differs at {np.count_nonzero(buf['shadow'] != want['shadow'])} px"
+        for key in ("screen", "low", "high"):
+            assert np.array_equal(bits(buf[key]), bits(want[key])), f"{tag}: {key}"
+        assert np.array_equal(bits(got["rgb"]), bits(want["rgb"])), f"{tag}: final colour"
+        assert st["fragments"] == want["fragments"], f"{tag}: fragments {st['fragments']} vs {want['fragments']}"
+    renderer.set_option(b200.OPT_RAST_TILE_LOG2, 4)
+    return want
+
+
+@pytest.mark.parametrize("name", ["rast_ref_cornell_64x48", "rast_ref_cornell_320x240", "rast_ref_cornell_320x240_yaw",
+                                  "rast_ref_random60_64x48"])
+def test_committed_reference_outputs(b200, renderer, name):
+    g = load_golden(name + ".npz")
+    W, H = int(g["W"]), int(g["H"])
+    clipped = g["clipped"].view(h.RAST_TRI).copy()
+    cam = b200.make_camera((0, 0, 0, 1), float(g["focal"]), h.identity_R(), W, H)
+    L = b200.make_rast_light(g["light_cam"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
+    got = renderer.render_raster_clipped(clipped, cam, L)
+    buf = renderer.raster_read_buffers(W, H)
+    assert np.array_equal(bits(got["rgb"]), bits(g["rgb"]))
+    assert np.array_equal(bits(got["depth"]), bits(g["depth"]))
+    assert np.array_equal(buf["shadow"], g["shadow"])
+    assert np.array_equal(got["index"], g["index"])
+    if "argb" in g.files:
+        want = g["argb"]
+        assert np.array_equal(b200.quantise(got["rgb"])[1:-1, 1:-1], want[1:-1, 1:-1])
+
+
+def test_cornell_default_config(b200, renderer):
+    """BASELINE config 2: 900x720, f = 512, the reference's own clipped list."""
+    g = load_golden("rast_ref_cornell_320x240.npz")
+    # the 900x720 list is produced by the oracle-side geometry of the compiled
+    # reference when available; otherwise the 320x240 list re-rendered at 900x720
+    # still exercises big spans (clipping is resolution dependent only at the borders)
+    clipped = g["clipped"].view(h.RAST_TRI).copy()
+    want = compare(b200, renderer, 900, 720, 512.0, g["light_cam"], h.DEFAULT_RAST_LIGHT, clipped, "cornell 900x720",
+                   tiles=(4, 5))
+    assert want["fragments"] > 2_000_000
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_random_lists(b200, renderer, seed):
+    rng = np.random.default_rng(seed)
+    W, H = int(rng.integers(20, 150)), int(rng.integers(20, 120))
+    f = float(rng.uniform(20, 120))
+    tl = h.random_clipped_list(int(rng.integers(1, 400)), 70 + seed, W, H, f, size=float(rng.uniform(0.05, 0.8)))
+    compare(b200, renderer, W, H, f, h.f32(0.1, -0.3, 1.2, 1.0), h.DEFAULT_RAST_LIGHT, tl, f"random {seed}")
+
+
+def test_equal_depth_later_triangle_wins(b200, renderer):
+    """Two coplanar opaque triangles + a coplanar shadow triangle: `zinv >= depth`
+    lets the later one win, `zinv > depth` keeps the shadow flag clear."""
+    W, H, f = 48, 40, 30.0
+    t = np.zeros(3, h.RAST_TRI)
+    for i in range(3):
+        t[i]["v0"] = (-0.8, -0.6, 2.0, 2.0 / f)
+        t[i]["v1"] = (0.9, -0.5, 2.0, 2.0 / f)
+        t[i]["v2"] = (0.1, 0.7, 2.0, 2.0 / f)
+    t["color"][0] = (0.2, 0.3, 0.4)
+    t["color"][1] = (0.7, 0.6, 0.5)
+    t["color"][2] = (-1, -1, -1)
+    h.compute_normals(t)
+    want = compare(b200, renderer, W, H, f, h.f32(0, 0, 0, 1), h.DEFAULT_RAST_LIGHT, t, "coplanar")
+    assert (want["index"][want["index"] >= 0] == 1).all() and not want["shadow"].any()
+
+
+def test_edge_cases(b200, renderer):
+    W, H, f = 40, 30, 25.0
+    L = h.DEFAULT_RAST_LIGHT
+    lc = h.f32(0, 0, 0.5, 1)
+    # empty list
+    want = compare(b200, renderer, W, H, f, lc, L, np.zeros(0, h.RAST_TRI), "empty")
+    assert not want["rgb"].any()
+    # degenerate (single pixel / single row / single column) triangles and off-screen ones
+    t = h.random_clipped_list(12, 9, W, H, f, shadow_frac=0.0, size=0.02)
+    t["v1"][:4] = t["v0"][:4]; t["v2"][:4] = t["v0"][:4]              # points
+    t["v1"][4:8, 1] = t["v0"][4:8, 1]; t["v2"][4:8, 1] = t["v0"][4:8, 1]  # horizontal slivers
+    t["v0"][8:, 0] += 50.0; t["v1"][8:, 0] += 50.0; t["v2"][8:, 0] += 50.0   # off screen to the right
+    compare(b200, renderer, W, H, f, lc, L, t, "degenerate")
+    # one huge triangle covering everything, partly off screen on every side
+    big = np.zeros(1, h.RAST_TRI)
+    big[0]["v0"] = (-9, -7, 1.5, 1.5 / f); big[0]["v1"] = (9, -6, 1.6, 1.6 / f); big[0]["v2"] = (0.5, 11, 1.4, 1.4 / f)
+    big["color"][0] = (0.5, 0.6, 0.7)
+    h.compute_normals(big)
+    compare(b200, renderer, W, H, f, lc, L, big, "huge")
+    # 1x1 .. 3x3 frames (no interior pixel below 3x3)
+    for w, hh in [(1, 1), (2, 5), (3, 3)]:
+        compare(b200, renderer, w, hh, 2.0, lc, L, big, f"{w}x{hh}", tiles=(4,))
+
+
+def test_long_tile_list_uses_global_sort(b200, renderer):
+    """More triangles over one tile than the shared-memory list holds (2048)."""
+    W, H, f = 24, 20, 20.0
+    rng = np.random.default_rng(11)
+    n = 2600
+    t = np.zeros(n, h.RAST_TRI)
+    z = rng.uniform(1.0, 3.0, n).astype(np.float32)
+    for name in ("v0", "v1", "v2"):
+        t[name][:, 0] = rng.uniform(-0.3, 0.3, n).astype(np.float32) * z
+        t[name][:, 1] = rng.uniform(-0.3, 0.3, n).astype(np.float32) * z
+        t[name][:, 2] = z
+        t[name][:, 3] = z / np.float32(f)
+    t["color"] = rng.uniform(0.15, 0.75, (n, 3)).astype(np.float32)
+    t["color"][rng.uniform(0, 1, n) < 0.3] = -1
+    h.compute_normals(t)
+    compare(b200, renderer, W, H, f, h.f32(0, 0.2, 0.5, 1), h.DEFAULT_RAST_LIGHT, t, "2600 over one tile", tiles=(5, 4))
+
+
+def test_bands_tile_the_frame(b200, renderer):
+    g = load_golden("rast_ref_cornell_320x240.npz")
+    clipped = g["clipped"].view(h.RAST_TRI).copy()
+    W, H = 320, 240
+    import torch
+    cam = b200.make_camera((0, 0, 0, 1), float(g["focal"]), h.identity_R(), W, H)
+    L = b200.make_rast_light(g["light_cam"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
+    renderer.rast_upload_clipped(clipped)
+    rgb = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+    depth = torch.zeros((H, W), dtype=torch.float32, device="cuda")
+    for r0, r1 in [(0, 37), (37, 38), (38, 160), (160, 240)]:
+        renderer.rast_render_device(cam, L, r0, r1, rgb.data_ptr(), depth.data_ptr())
+    renderer.synchronize()
+    assert np.array_equal(bits(rgb.cpu().numpy()), bits(g["rgb"]))
+    assert np.array_equal(bits(depth.cpu().numpy()), bits(g["depth"]))
+
+
+def test_invalid_arguments(b200, renderer):
+    t = h.random_clipped_list(3, 1, 32, 32, 20.0)
+    t["texture"][1] = 2
+    cam = b200.make_camera((0, 0, 0, 1), 20.0, h.identity_R(), 32, 32)
+    L = b200.make_rast_light((0, 0, 0, 1), (1, 1, 1), (0.2, 0.2, 0.2))
+    with pytest.raises(b200.B200Error):
+        renderer.render_raster_clipped(t, cam, L)
