@@ -63,7 +63,8 @@ ABI_SYMBOLS = [
     "b200_set_stream", "b200_set_option", "b200_get_stats",
     "b200_scene_cornell_rt", "b200_scene_cornell_rt_tessellated", "b200_scene_cornell_rast",
     "b200_scene_soup_rast",
-    "render_raytrace", "render_raytrace_band", "draw_raytrace", "rt_upload_scene", "rt_render_device",
+    "render_raytrace", "render_raytrace_band", "draw_raytrace", "draw_raytrace_band",
+    "b200_measure_fp32_peak", "rt_upload_scene", "rt_render_device",
     "render_raster_clipped", "render_raster", "draw_raster", "raster_read_buffers",
     "raster_read_clipped", "rast_upload_clipped", "rast_render_device",
     "b200_quantise", "b200_save_bmp",
@@ -194,6 +195,19 @@ class Renderer:
                                     len(lights), _ptr(argb))
         self._check(rc, "draw_raytrace")
         return argb
+
+    def draw_raytrace_band(self, tris, spheres, cam, lights, row_begin, row_end, out_ptr):
+        """out_ptr: host address (e.g. pinned memory) of a band-sized uint32 buffer."""
+        la = make_lights(lights)
+        rc = self.lib.draw_raytrace_band(self.ctx, _ptr(tris), len(tris), _ptr(spheres),
+                                         0 if spheres is None else len(spheres), ctypes.byref(cam), la,
+                                         len(lights), int(row_begin), int(row_end), _ptr(out_ptr))
+        self._check(rc, "draw_raytrace_band")
+
+    def measure_fp32_peak(self):
+        v = ctypes.c_float(0)
+        self._check(self.lib.b200_measure_fp32_peak(self.ctx, ctypes.byref(v)), "b200_measure_fp32_peak")
+        return float(v.value)
 
     def rt_upload_scene(self, tris, spheres):
         rc = self.lib.rt_upload_scene(self.ctx, _ptr(tris), len(tris), _ptr(spheres),

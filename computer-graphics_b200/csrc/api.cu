@@ -249,20 +249,65 @@ int render_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt
                               rgb_out, depth_out, index_out);
 }
 
-int draw_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres,
-                  int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
-                  uint32_t *argb_out) {
+int draw_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres,
+                       int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
+                       int row_begin, int row_end, uint32_t *argb_out) {
   if (!ctx) return B200_EINVAL;
   if (!argb_out) return ctx_fail(ctx, B200_EINVAL, "null framebuffer");
   if (int rc = check_camera(ctx, cam)) return rc;
   if (int rc = rt_upload_scene(ctx, tris, n_tris, spheres, n_spheres)) return rc;
   const size_t npix = (size_t)cam->width * cam->height;
   if (int rc = ensure(ctx, ctx->out_argb, npix * sizeof(uint32_t))) return rc;
-  if (int rc = rt_render_device(ctx, cam, lights, n_lights, 0, cam->height, nullptr, nullptr, nullptr,
+  if (int rc = rt_render_device(ctx, cam, lights, n_lights, row_begin, row_end, nullptr, nullptr, nullptr,
                                 (uint32_t *)ctx->out_argb.p))
     return rc;
-  if (int rc = copy_out(ctx, argb_out, ctx->out_argb.p, npix * sizeof(uint32_t))) return rc;
+  const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
+  if (int rc = copy_out(ctx, argb_out, (uint32_t *)ctx->out_argb.p + off, cnt * sizeof(uint32_t))) return rc;
   return finish_stats(ctx);
+}
+
+int draw_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres,
+                  int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
+                  uint32_t *argb_out) {
+  if (!ctx) return B200_EINVAL;
+  if (int rc = check_camera(ctx, cam)) return rc;
+  return draw_raytrace_band(ctx, tris, n_tris, spheres, n_spheres, cam, lights, n_lights, 0, cam->height,
+                            argb_out);
+}
+
+// ---- roofline denominator: FP32 FFMA peak of this GPU ------------------------------------
+__global__ void b200_ffma_peak_kernel(float *out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int b200_measure_fp32_peak(b200_ctx *ctx, float *tflops_out) {
+  if (!ctx || !tflops_out) return B200_EINVAL;
+  cudaSetDevice(ctx->device);
+  const int blocks = ctx->sm_count * 2, threads = 1024, iters = 4096;
+  DevBuf tmp;
+  if (int rc = ensure(ctx, tmp, sizeof(float) * (size_t)blocks * threads)) return rc;
+  float best = 0.f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    b200_ffma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((float *)tmp.p, iters, 1.0001f, 0.5f);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaFree(tmp.p); return ctx_fail(ctx, B200_ECUDA, "ffma peak"); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    const double fl = 2.0 * 128.0 * iters * (double)blocks * threads;
+    if (rep > 0 && ms > 0.f) best = fmaxf(best, (float)(fl / ms / 1e9));
+  }
+  cudaFree(tmp.p);
+  *tflops_out = best;
+  return B200_OK;
 }
 
 // ---- RAST -------------------------------------------------------------------------------

@@ -159,6 +159,15 @@ int draw_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_s
                   int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
                   uint32_t *argb_out);
 
+/* Band variant: argb_out is band-sized, (row_end - row_begin) * W. */
+int draw_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris,
+                       const rt_sphere *spheres, int n_spheres, const camera_t *cam,
+                       const light_t *lights, int n_lights, int row_begin, int row_end,
+                       uint32_t *argb_out);
+
+/* Measures this GPU's FP32 FFMA rate (the raytracer's roofline denominator). */
+int b200_measure_fp32_peak(b200_ctx *ctx, float *tflops_out);
+
 /* Device-resident path: upload the scene once, render many times. */
 int rt_upload_scene(b200_ctx *ctx, const rt_triangle *tris, int n_tris,
                     const rt_sphere *spheres, int n_spheres);
