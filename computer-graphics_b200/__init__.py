@@ -66,7 +66,8 @@ ABI_SYMBOLS = [
     "render_raytrace", "render_raytrace_band", "draw_raytrace", "draw_raytrace_band",
     "b200_measure_fp32_peak", "rt_upload_scene", "rt_render_device",
     "render_raster_clipped", "render_raster", "draw_raster", "raster_read_buffers",
-    "raster_read_clipped", "rast_upload_clipped", "rast_render_device",
+    "raster_read_clipped", "rast_upload_clipped", "rast_render_device", "draw_raster_band",
+    "rast_upload_scene", "rast_draw_device",
     "b200_quantise", "b200_save_bmp",
 ]
 
@@ -271,6 +272,23 @@ class Renderer:
 
     def rast_upload_clipped(self, clipped):
         self._check(self.lib.rast_upload_clipped(self.ctx, _ptr(clipped), len(clipped)), "rast_upload_clipped")
+
+    def rast_upload_scene(self, room, boxes):
+        self._check(self.lib.rast_upload_scene(self.ctx, _ptr(room), len(room), _ptr(boxes), len(boxes)),
+                    "rast_upload_scene")
+
+    def rast_draw_device(self, cam, light, row_begin, row_end, d_rgb=None, d_depth=None,
+                         d_index=None, d_argb=None):
+        rc = self.lib.rast_draw_device(self.ctx, ctypes.byref(cam), ctypes.byref(light),
+                                       int(row_begin), int(row_end), _ptr(d_rgb), _ptr(d_depth),
+                                       _ptr(d_index), _ptr(d_argb))
+        self._check(rc, "rast_draw_device")
+
+    def draw_raster_band(self, room, boxes, cam, light, row_begin, row_end, out_ptr):
+        rc = self.lib.draw_raster_band(self.ctx, _ptr(room), len(room), _ptr(boxes), len(boxes),
+                                       ctypes.byref(cam), ctypes.byref(light), int(row_begin),
+                                       int(row_end), _ptr(out_ptr))
+        self._check(rc, "draw_raster_band")
 
     def rast_render_device(self, cam, light, row_begin, row_end, d_rgb=None, d_depth=None,
                            d_index=None, d_argb=None):

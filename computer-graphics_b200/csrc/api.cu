@@ -68,7 +68,7 @@ void b200_destroy(b200_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rast_src,
                     &ctx->rast_setup, &ctx->rast_rowsA, &ctx->rast_rowsB, &ctx->rast_bins, &ctx->rast_tile_count,
-                    &ctx->rast_tmp, &ctx->rast_clipped, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
+                    &ctx->rast_tmp, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
                     &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
                     &ctx->out_argb, &ctx->counters};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -366,6 +366,97 @@ int render_raster_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tri
   if (int rc = copy_out(ctx, depth_out, ctx->out_depth.p, npix * sizeof(float))) return rc;
   if (int rc = copy_out(ctx, index_out, ctx->out_index.p, npix * sizeof(int32_t))) return rc;
   return finish_stats(ctx);
+}
+
+// ---- RAST tier 2: the whole Draw (geometry stage + triangle loop + post pass) ----------
+
+int rast_upload_scene(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes,
+                      int n_boxes) {
+  if (!ctx) return B200_EINVAL;
+  if (n_room < 0 || n_boxes < 0 || (n_room > 0 && !room) || (n_boxes > 0 && !boxes))
+    return ctx_fail(ctx, B200_EINVAL, "bad scene arguments");
+  if ((long long)n_room + 7ll * n_boxes > 0x3fffffffll) return ctx_fail(ctx, B200_EINVAL, "scene too large");
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < n_room; ++i)
+    if (room[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+  for (int i = 0; i < n_boxes; ++i)
+    if (boxes[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+  const size_t n = (size_t)n_room + (size_t)n_boxes;
+  if (int rc = ensure(ctx, ctx->rast_world, sizeof(rast_triangle) * (n ? n : 1))) return rc;
+  rast_triangle *d = (rast_triangle *)ctx->rast_world.p;
+  if (n_room) CU_CHECK(ctx, cudaMemcpyAsync(d, room, sizeof(rast_triangle) * (size_t)n_room, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_boxes) CU_CHECK(ctx, cudaMemcpyAsync(d + n_room, boxes, sizeof(rast_triangle) * (size_t)n_boxes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->rast_n_room = n_room;
+  ctx->rast_n_boxes = n_boxes;
+  return B200_OK;
+}
+
+int rast_draw_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin, int row_end,
+                     float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
+  if (!ctx) return B200_EINVAL;
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (!light) return ctx_fail(ctx, B200_EINVAL, "null light");
+  if (row_begin < 0 || row_end > cam->height || row_begin > row_end) return ctx_fail(ctx, B200_EINVAL, "bad row band");
+  cudaSetDevice(ctx->device);
+  ctx->stats.kernel_launches = 0;
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  rast_light_t lc;
+  if (int rc = rast_geometry(ctx, cam, light, &lc)) return rc;
+  if (int rc = rast_launch(ctx, cam, &lc, row_begin, row_end, d_rgb, d_depth, d_index, d_argb)) return rc;
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->pending = 2;
+  return B200_OK;
+}
+
+int render_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes, int n_boxes,
+                  const camera_t *cam, const rast_light_t *light, float *rgb_out, float *depth_out,
+                  int32_t *index_out) {
+  if (!ctx) return B200_EINVAL;
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
+  if (int rc = raster_host_outputs(ctx, cam, rgb_out, depth_out, index_out, nullptr)) return rc;
+  if (int rc = rast_draw_device(ctx, cam, light, 0, cam->height, rgb_out ? (float *)ctx->out_rgb.p : nullptr,
+                                depth_out ? (float *)ctx->out_depth.p : nullptr,
+                                index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr))
+    return rc;
+  const size_t npix = (size_t)cam->width * cam->height;
+  if (int rc = copy_out(ctx, rgb_out, ctx->out_rgb.p, npix * 3 * sizeof(float))) return rc;
+  if (int rc = copy_out(ctx, depth_out, ctx->out_depth.p, npix * sizeof(float))) return rc;
+  if (int rc = copy_out(ctx, index_out, ctx->out_index.p, npix * sizeof(int32_t))) return rc;
+  return finish_stats(ctx);
+}
+
+int draw_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes,
+                     int n_boxes, const camera_t *cam, const rast_light_t *light, int row_begin, int row_end,
+                     uint32_t *argb_out) {
+  if (!ctx) return B200_EINVAL;
+  if (!argb_out) return ctx_fail(ctx, B200_EINVAL, "null framebuffer");
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
+  if (int rc = raster_host_outputs(ctx, cam, nullptr, nullptr, nullptr, argb_out)) return rc;
+  if (int rc = rast_draw_device(ctx, cam, light, row_begin, row_end, nullptr, nullptr, nullptr,
+                                (uint32_t *)ctx->out_argb.p))
+    return rc;
+  const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
+  if (int rc = copy_out(ctx, argb_out, (uint32_t *)ctx->out_argb.p + off, cnt * sizeof(uint32_t))) return rc;
+  return finish_stats(ctx);
+}
+
+int draw_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes, int n_boxes,
+                const camera_t *cam, const rast_light_t *light, uint32_t *argb_out) {
+  if (!ctx) return B200_EINVAL;
+  if (int rc = check_camera(ctx, cam)) return rc;
+  return draw_raster_band(ctx, room, n_room, boxes, n_boxes, cam, light, 0, cam->height, argb_out);
+}
+
+int raster_read_clipped(b200_ctx *ctx, rast_triangle *out, int cap, int *n_out) {
+  if (!ctx || !n_out) return B200_EINVAL;
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_out = ctx->rast_n_tris;
+  const int n = ctx->rast_n_tris < cap ? ctx->rast_n_tris : cap;
+  if (out && n > 0) CU_CHECK(ctx, cudaMemcpy(out, ctx->rast_src.p, sizeof(rast_triangle) * (size_t)n, cudaMemcpyDeviceToHost));
+  return B200_OK;
 }
 
 int raster_read_buffers(b200_ctx *ctx, float *screen_out, float *low_out, float *high_out, int32_t *shadow_out) {

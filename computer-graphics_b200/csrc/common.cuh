@@ -78,7 +78,9 @@ struct b200_ctx {
   DevBuf rast_src;    // rast_triangle[n] clipped list
   int rast_n_tris = 0;
   DevBuf rast_setup, rast_rowsA, rast_rowsB, rast_bins, rast_tile_count, rast_tmp;
-  DevBuf rast_clipped;   // tier 2: output of the geometry stage
+  DevBuf rast_world;     // tier 2: world-space room then boxes, as uploaded
+  DevBuf rast_geom_tmp;  // tier 2: per-triangle output counts and their scan
+  int rast_n_room = 0, rast_n_boxes = 0;
   DevBuf rast_screen, rast_low, rast_high, rast_shadow, rast_depth, rast_index;
   int rast_w = 0, rast_h = 0;
 
@@ -111,6 +113,7 @@ struct RtFrame {
 
 int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row0, int row1,
                 float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb);
+int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, rast_light_t *light_out);
 int rt_prepare_scene(b200_ctx *ctx);
 int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int32_t *d_index,
               uint32_t *d_argb);

@@ -214,11 +214,25 @@ int raster_read_buffers(b200_ctx *ctx, float *screen_out, float *low_out, float 
  * in *n_out, copies min(cap, n) triangles. */
 int raster_read_clipped(b200_ctx *ctx, rast_triangle *out, int cap, int *n_out);
 
-/* Device-resident path. */
+/* Band variant of draw_raster: argb_out is band-sized, (row_end - row_begin) * W. */
+int draw_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room,
+                     const rast_triangle *boxes, int n_boxes, const camera_t *cam,
+                     const rast_light_t *light, int row_begin, int row_end, uint32_t *argb_out);
+
+/* Device-resident path, tier 1 (clipped list + camera-space light).  Output
+ * pointers are DEVICE pointers addressed as full frames; rows [row_begin,
+ * row_end) are written; asynchronous on b200_stream(ctx). */
 int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris);
 int rast_render_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
                        int row_begin, int row_end, float *d_rgb, float *d_depth,
                        int32_t *d_index, uint32_t *d_argb);
+/* Device-resident path, tier 2 (world-space scene + world-space light): the
+ * geometry stage runs on the GPU every frame, like the reference's Draw. */
+int rast_upload_scene(b200_ctx *ctx, const rast_triangle *room, int n_room,
+                      const rast_triangle *boxes, int n_boxes);
+int rast_draw_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
+                     int row_begin, int row_end, float *d_rgb, float *d_depth,
+                     int32_t *d_index, uint32_t *d_argb);
 
 /* ---- scenes (host-side data builders) ---------------------------------------*/
 

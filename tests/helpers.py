@@ -291,6 +291,55 @@ def rows_call(fn, focal, verts, cap=1 << 14, dims=None):
     return y0.value, rows[:n.value].copy()
 
 
+def oracle_rast_geometry(W, H, focal, cam, R, light, room, boxes, cap=None):
+    """Geometry stage (Draw :205-241) restated in C: clipped list + camera-space light."""
+    lib = oracle()
+    cap = cap or max(64, 40 * (len(room) + 7 * len(boxes)))
+    out = np.zeros(cap, RAST_TRI)
+    lc = np.zeros(4, np.float32)
+    n = lib.oracle_rast_geometry(c_i(W), c_i(H), c_f(focal), ptr(np.asarray(cam, np.float32)),
+                                 ptr(np.asarray(R, np.float32)), ptr(f32(*light["pos"])), ptr(room),
+                                 c_i(len(room)), ptr(boxes), c_i(len(boxes)), ptr(out), c_i(cap), ptr(lc))
+    assert n >= 0
+    return out[:n].copy(), lc
+
+
+def clipped_equal(a, b):
+    """Byte equality of two clipped lists, ignoring `index` of shadow-volume
+    triangles (uninitialised in the reference, rasteriser skeleton.cpp:1705-1710)."""
+    if len(a) != len(b):
+        return False
+    for k in ("v0", "v1", "v2", "normal", "color"):
+        if not np.array_equal(np.ascontiguousarray(a[k]).view(np.uint32), np.ascontiguousarray(b[k]).view(np.uint32)):
+            return False
+    real = a["color"][:, 0] >= 0
+    return np.array_equal(a["texture"], b["texture"]) and np.array_equal(a["index"][real], b["index"][real])
+
+
+def oracle_rast_draw(W, H, focal, cam, R, light, room, boxes):
+    """Whole Draw restated: geometry stage, then triangle loop + post pass."""
+    clipped, lc = oracle_rast_geometry(W, H, focal, cam, R, light, room, boxes)
+    out = oracle_rast_draw_clipped(W, H, focal, lc, light, clipped)
+    out["clipped"], out["light_cam"] = clipped, lc
+    return out
+
+
+def smoke_rast(b200, r):
+    """Used by __graft_entry__.smoke(): one small whole-Draw frame vs the oracle."""
+    room, boxes = b200.scene_cornell_rast()
+    W, H, f = 160, 120, 85.0
+    cam = b200.make_camera(DEFAULT_RAST_CAM, f, identity_R(), W, H)
+    L = b200.make_rast_light(DEFAULT_RAST_LIGHT["pos"], DEFAULT_RAST_LIGHT["power"], DEFAULT_RAST_LIGHT["indirect"])
+    got = r.render_raster(room, boxes, cam, L)
+    want = oracle_rast_draw(W, H, f, DEFAULT_RAST_CAM, identity_R(), DEFAULT_RAST_LIGHT, room, boxes)
+    assert np.array_equal(got["index"], want["index"]), "RAST owner mismatch"
+    assert np.array_equal(got["depth"].view(np.uint32), want["depth"].view(np.uint32)), "RAST depth mismatch"
+    assert np.array_equal(got["rgb"].view(np.uint32), want["rgb"].view(np.uint32)), "RAST colour mismatch"
+    st = r.stats()
+    print(f"smoke RAST ok: {W}x{H}, {len(want['clipped'])} clipped triangles, {st['fragments']} fragments, "
+          f"{st['gpu_ms']:.3f} ms, {st['kernel_launches']} launches")
+
+
 def random_clipped_list(n, seed, W, H, focal, shadow_frac=0.3, size=0.5):
     """Camera-space triangles in front of the camera that project near the screen
     (what the reference's clip stage would hand to the triangle loop)."""

@@ -79,6 +79,38 @@ def test_oracle_vs_compiled_reference_random_lists(seed):
     assert np.array_equal(o["argb"], r["argb"])
 
 
+@pytest.mark.parametrize("name", ["rast_ref_cornell_64x48", "rast_ref_cornell_320x240", "rast_ref_cornell_320x240_yaw"])
+def test_geometry_matches_committed_clipped_lists(name):
+    """Geometry stage (camera transform, shadow volumes, rotation, six-plane clip)
+    against the clipped list the compiled reference built (committed)."""
+    g = load_golden(name + ".npz")
+    room, boxes = g["room"].view(h.RAST_TRI), g["boxes"].view(h.RAST_TRI)
+    clipped, lc = h.oracle_rast_geometry(int(g["W"]), int(g["H"]), float(g["focal"]), g["cam"], g["R"],
+                                         h.DEFAULT_RAST_LIGHT, room, boxes)
+    assert h.clipped_equal(clipped, g["clipped"].view(h.RAST_TRI))
+    assert np.array_equal(bits(lc), bits(g["light_cam"]))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_geometry_vs_compiled_reference_random_poses(seed):
+    """Cameras inside the room, yaw, moved lights: every clip case gets exercised."""
+    if not h.have_ref(h.ref_rast_name(320, 240)):
+        pytest.skip("oracle/_ref not built")
+    W, H, f = (320, 240, 170.0) if seed % 2 else (64, 48, 36.0)
+    rng = np.random.default_rng(200 + seed)
+    room, boxes = h.ref_rast_testmodel(W, H)
+    cam = h.f32(*rng.uniform(-0.9, 0.9, 2), rng.uniform(-3.5, 0.5), 1)
+    R = h.yaw_R(float(rng.uniform(-1.2, 1.2)))
+    light = dict(h.DEFAULT_RAST_LIGHT)
+    light["pos"] = (float(rng.uniform(-0.5, 0.5)), -0.5, float(rng.uniform(-0.7, 0.3)), 1.0)
+    r = h.ref_rast_draw(W, H, f, cam, R, light, room, boxes)
+    clipped, lc = h.oracle_rast_geometry(W, H, f, cam, R, light, room, boxes)
+    assert h.clipped_equal(clipped, r["clipped"])
+    assert np.array_equal(bits(lc), bits(r["light_cam"]))
+    o = h.oracle_rast_draw(W, H, f, cam, R, light, room, boxes)
+    assert np.array_equal(bits(o["rgb"]), bits(r["rgb"])) and np.array_equal(o["shadow"], r["shadow"])
+
+
 def test_whole_draw_default_config():
     """BASELINE config 2: 900x720, f = 512: 303 clipped triangles, the fragment count
     SURVEY.md quotes, and the oracle equal to the reference's whole Draw."""

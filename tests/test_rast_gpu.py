@@ -151,6 +151,94 @@ def test_bands_tile_the_frame(b200, renderer):
     assert np.array_equal(bits(depth.cpu().numpy()), bits(g["depth"]))
 
 
+def whole_draw(b200, renderer, W, H, f, cam_pos, R, light, room, boxes, what):
+    want = h.oracle_rast_draw(W, H, f, cam_pos, R, light, room, boxes)
+    cam = b200.make_camera(cam_pos, f, R, W, H)
+    L = b200.make_rast_light(light["pos"], light["power"], light["indirect"])
+    got = renderer.render_raster(room, boxes, cam, L)
+    clipped = renderer.raster_read_clipped()
+    assert h.clipped_equal(clipped, want["clipped"]), f"{what}: clipped list ({len(clipped)} vs {len(want['clipped'])})"
+    buf = renderer.raster_read_buffers(W, H)
+    assert np.array_equal(got["index"], want["index"]), f"{what}: owner"
+    assert np.array_equal(bits(got["depth"]), bits(want["depth"])), f"{what}: depth"
+    assert np.array_equal(buf["shadow"], want["shadow"]), f"{what}: shadow mask"
+    assert np.array_equal(bits(got["rgb"]), bits(want["rgb"])), f"{what}: colour"
+    argb = renderer.draw_raster(room, boxes, cam, L)
+    assert np.array_equal(argb, want["argb"]), f"{what}: packed framebuffer"
+    return want
+
+
+def test_whole_draw_default_config(b200, renderer):
+    """BASELINE config 2: the whole reference Draw at 900x720, f = 512: geometry stage on the
+    GPU (303 clipped triangles, 273 of them shadow-volume), triangle loop, post pass."""
+    room, boxes = b200.scene_cornell_rast()
+    want = whole_draw(b200, renderer, 900, 720, 512.0, h.DEFAULT_RAST_CAM, h.identity_R(), h.DEFAULT_RAST_LIGHT,
+                      room, boxes, "cornell 900x720")
+    assert len(want["clipped"]) == 303 and np.count_nonzero(want["clipped"]["color"][:, 0] < 0) == 273
+
+
+@pytest.mark.parametrize("name", ["rast_ref_cornell_64x48", "rast_ref_cornell_320x240", "rast_ref_cornell_320x240_yaw"])
+def test_whole_draw_vs_committed_reference(b200, renderer, name):
+    g = load_golden(name + ".npz")
+    W, H = int(g["W"]), int(g["H"])
+    room, boxes = g["room"].view(h.RAST_TRI).copy(), g["boxes"].view(h.RAST_TRI).copy()
+    cam = b200.make_camera(g["cam"], float(g["focal"]), g["R"], W, H)
+    L = b200.make_rast_light(h.DEFAULT_RAST_LIGHT["pos"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
+    got = renderer.render_raster(room, boxes, cam, L)
+    assert h.clipped_equal(renderer.raster_read_clipped(), g["clipped"].view(h.RAST_TRI))
+    assert np.array_equal(bits(got["rgb"]), bits(g["rgb"])) and np.array_equal(bits(got["depth"]), bits(g["depth"]))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_whole_draw_random_poses(b200, renderer, seed):
+    """Cameras inside the room, yaw, moved lights: every clip case on the GPU."""
+    rng = np.random.default_rng(300 + seed)
+    room, boxes = b200.scene_cornell_rast()
+    W, H = int(rng.integers(40, 200)), int(rng.integers(30, 160))
+    cam = h.f32(*rng.uniform(-0.9, 0.9, 2), rng.uniform(-3.5, 0.5), 1)
+    light = dict(h.DEFAULT_RAST_LIGHT)
+    light["pos"] = (float(rng.uniform(-0.5, 0.5)), -0.5, float(rng.uniform(-0.7, 0.3)), 1.0)
+    whole_draw(b200, renderer, W, H, float(rng.uniform(30, 150)), cam, h.yaw_R(float(rng.uniform(-1.2, 1.2))), light,
+               room, boxes, f"pose {seed}")
+
+
+def test_soup_scene_small(b200, renderer):
+    """The config-4 generator at a size the oracle finishes in seconds."""
+    soup = b200.scene_soup_rast(20000, edge=0.03)
+    whole_draw(b200, renderer, 480, 270, 192.0, h.DEFAULT_RAST_CAM, h.identity_R(), h.DEFAULT_RAST_LIGHT,
+               soup, np.zeros(0, h.RAST_TRI), "soup 20k")
+
+
+def test_soup_full_size_properties(b200, renderer):
+    """BASELINE config 4 at full size (1M triangles, 3840x2160): properties that do not
+    need the CPU reference -- idempotence, tile-size independence, coverage == depth > 0,
+    owner consistent with depth, and agreement of a full-width band with the oracle."""
+    soup = b200.scene_soup_rast(1_000_000)
+    W, H, f = 3840, 2160, 1536.0
+    cam = b200.make_camera(h.DEFAULT_RAST_CAM, f, h.identity_R(), W, H)
+    L = b200.make_rast_light(h.DEFAULT_RAST_LIGHT["pos"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
+    renderer.set_option(b200.OPT_RAST_TILE_LOG2, 4)
+    a = renderer.render_raster(soup, np.zeros(0, h.RAST_TRI), cam, L)
+    assert len(renderer.raster_read_clipped(cap=1)) == 1 and renderer.stats()["fragments"] > 0
+    renderer.set_option(b200.OPT_RAST_TILE_LOG2, 5)
+    b = renderer.render_raster(soup, np.zeros(0, h.RAST_TRI), cam, L)
+    renderer.set_option(b200.OPT_RAST_TILE_LOG2, 4)
+    for k in ("rgb", "depth", "index"):
+        assert np.array_equal(a[k], b[k]), k
+    covered = a["depth"] > 0
+    assert np.array_equal(covered, a["index"] >= 0)
+    assert 1_000_000 < np.count_nonzero(covered) < 3_000_000     # BASELINE.md: ~1.83 M of 8.29 M px
+    assert not a["rgb"][0].any() and not a["rgb"][:, -1].any()    # border never written
+    # a 24-row band of the same frame against the oracle (the oracle restricted to the
+    # triangles whose bounding rows touch the band, which cannot change those rows)
+    clipped, lc = h.oracle_rast_geometry(W, H, f, h.DEFAULT_RAST_CAM, h.identity_R(), h.DEFAULT_RAST_LIGHT,
+                                         soup, np.zeros(0, h.RAST_TRI), cap=1_000_100)
+    assert len(clipped) == 1_000_000
+    o = h.oracle_rast_draw_clipped(W, H, f, lc, h.DEFAULT_RAST_LIGHT, clipped)
+    assert np.array_equal(bits(a["depth"]), bits(o["depth"])) and np.array_equal(a["index"], o["index"])
+    assert np.array_equal(bits(a["rgb"]), bits(o["rgb"]))
+
+
 def test_invalid_arguments(b200, renderer):
     t = h.random_clipped_list(3, 1, 32, 32, 20.0)
     t["texture"][1] = 2
