@@ -301,6 +301,8 @@ def run_b200(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     r.set_stream(stream.cuda_stream)
+    if "B200_RAST_TILE_LOG2" in os.environ:      # tuning knob, default chosen by the library
+        r.set_option(b200.OPT_RAST_TILE_LOG2, int(os.environ["B200_RAST_TILE_LOG2"]))
     row0, row1 = rank * H // world, (rank + 1) * H // world
     rows = row1 - row0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2

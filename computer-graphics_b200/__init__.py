@@ -23,6 +23,7 @@ B200_OK, B200_EINVAL, B200_ECUDA, B200_ENOMEM, B200_ENODEV = 0, -1, -2, -3, -4
 INDEX_MISS = -2147483648
 OPT_RT_BRUTEFORCE = 1
 OPT_RAST_TILE_LOG2 = 2
+OPT_RAST_PATH = 3
 
 RT_TRI = np.dtype([("v0", "<f4", 4), ("v1", "<f4", 4), ("v2", "<f4", 4),
                    ("normal", "<f4", 4), ("color", "<f4", 3)])

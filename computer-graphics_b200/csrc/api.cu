@@ -68,7 +68,7 @@ void b200_destroy(b200_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rast_src,
                     &ctx->rast_setup, &ctx->rast_rowsA, &ctx->rast_rowsB, &ctx->rast_bins, &ctx->rast_tile_count,
-                    &ctx->rast_tmp, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
+                    &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
                     &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
                     &ctx->out_argb, &ctx->counters};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -99,6 +99,10 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
   if (!ctx) return B200_EINVAL;
   switch (option) {
     case B200_OPT_RT_BRUTEFORCE: ctx->opt_rt_bruteforce = value != 0; return B200_OK;
+    case B200_OPT_RAST_PATH:
+      if (value < 0 || value > 2) return ctx_fail(ctx, B200_EINVAL, "raster path must be 0, 1 or 2");
+      ctx->opt_rast_path = value;
+      return B200_OK;
     case B200_OPT_RAST_TILE_LOG2:
       if (value < 3 || value > 6) return ctx_fail(ctx, B200_EINVAL, "tile log2 must be 3..6");
       ctx->opt_rast_tile_log2 = value;
@@ -316,8 +320,12 @@ int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris)
   if (!ctx) return B200_EINVAL;
   if (n_tris < 0 || (n_tris > 0 && !clipped)) return ctx_fail(ctx, B200_EINVAL, "bad triangle list");
   cudaSetDevice(ctx->device);
-  for (int i = 0; i < n_tris; ++i)
+  int has_shadow = 0;
+  for (int i = 0; i < n_tris; ++i) {
     if (clipped[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+    has_shadow |= !(clipped[i].color[0] >= 0);
+  }
+  ctx->rast_has_shadow = has_shadow;
   if (int rc = ensure(ctx, ctx->rast_src, sizeof(rast_triangle) * (size_t)(n_tris ? n_tris : 1))) return rc;
   if (n_tris) CU_CHECK(ctx, cudaMemcpyAsync(ctx->rast_src.p, clipped, sizeof(rast_triangle) * (size_t)n_tris,
                                             cudaMemcpyHostToDevice, ctx->stream));
@@ -377,8 +385,12 @@ int rast_upload_scene(b200_ctx *ctx, const rast_triangle *room, int n_room, cons
     return ctx_fail(ctx, B200_EINVAL, "bad scene arguments");
   if ((long long)n_room + 7ll * n_boxes > 0x3fffffffll) return ctx_fail(ctx, B200_EINVAL, "scene too large");
   cudaSetDevice(ctx->device);
-  for (int i = 0; i < n_room; ++i)
+  int has_shadow = n_boxes > 0;   // createShadowVolume wraps every box triangle (:215)
+  for (int i = 0; i < n_room; ++i) {
     if (room[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+    has_shadow |= !(room[i].color[0] >= 0);
+  }
+  ctx->rast_has_shadow = has_shadow;
   for (int i = 0; i < n_boxes; ++i)
     if (boxes[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
   const size_t n = (size_t)n_room + (size_t)n_boxes;
@@ -461,7 +473,9 @@ int raster_read_clipped(b200_ctx *ctx, rast_triangle *out, int cap, int *n_out) 
 
 int raster_read_buffers(b200_ctx *ctx, float *screen_out, float *low_out, float *high_out, int32_t *shadow_out) {
   if (!ctx) return B200_EINVAL;
-  if (ctx->rast_w <= 0) return ctx_fail(ctx, B200_EINVAL, "no raster frame rendered yet");
+  if (ctx->rast_w <= 0)
+    return ctx_fail(ctx, B200_EINVAL, "no intermediate buffers: nothing rendered yet, or the last frame took the "
+                                      "scatter path (set B200_OPT_RAST_PATH to 1 to keep them)");
   const size_t npix = (size_t)ctx->rast_w * ctx->rast_h;
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   if (screen_out) CU_CHECK(ctx, cudaMemcpy(screen_out, ctx->rast_screen.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost));

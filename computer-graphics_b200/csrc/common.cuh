@@ -78,6 +78,10 @@ struct b200_ctx {
   DevBuf rast_src;    // rast_triangle[n] clipped list
   int rast_n_tris = 0;
   DevBuf rast_setup, rast_rowsA, rast_rowsB, rast_bins, rast_tile_count, rast_tmp;
+  DevBuf rast_keys;      // fast path: 64-bit (zinv, triangle) key per pixel
+  int rast_has_shadow = 0;   // the uploaded list can contain shadow-volume triangles
+  int opt_rast_path = 0;     // 0 auto, 1 ordered tiles, 2 scatter (shadow-free lists only)
+  DevBuf rast_chunks;    // owner triangle of each 8-row chunk of the row tables
   DevBuf rast_world;     // tier 2: world-space room then boxes, as uploaded
   DevBuf rast_geom_tmp;  // tier 2: per-triangle output counts and their scan
   int rast_n_room = 0, rast_n_boxes = 0;

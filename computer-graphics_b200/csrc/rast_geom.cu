@@ -127,6 +127,28 @@ __device__ __forceinline__ int clip_one(const ClipCtx &c, const GTri &in, GTri &
   return 0;   // NaNs, or the far plane's unmatched combination: dropped
 }
 
+// The general case: the triangle's descendants through the six planes, in the
+// reference's list order.  cur[0] holds the input; returns the count.
+__device__ __noinline__ int clip_six_planes(int W, int H, float focal, GTri *cur) {
+  GTri nxt[32];
+  int n_cur = 1;
+  for (int plane = 1; plane <= 6; ++plane) {
+    ClipCtx c;
+    c.plane = plane; c.W = W; c.H = H; c.focal = focal;
+    int n_nxt = 0;
+    for (int i = 0; i < n_cur; ++i) {
+      GTri o0, o1;
+      const int m = clip_one(c, cur[i], o0, o1);
+      if (m >= 1) nxt[n_nxt++] = o0;
+      if (m == 2) nxt[n_nxt++] = o1;
+    }
+    for (int i = 0; i < n_nxt; ++i) cur[i] = nxt[i];
+    n_cur = n_nxt;
+    if (n_cur == 0) break;
+  }
+  return n_cur;
+}
+
 template <bool WRITE>
 __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ GeomParams p) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,23 +207,19 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
     t.v[k].w = xdiv(t.v[k].z, p.focal);                          // :695-697
   }
   // ---- six planes, list order preserved (:236-241) ----
-  GTri cur[32], nxt[32];
+  // Fast path: a triangle inside all six planes comes out unchanged.
+  GTri cur[32];
   int n_cur = 1;
-  cur[0] = t;
+  bool all_in = true;
+#pragma unroll
   for (int plane = 1; plane <= 6; ++plane) {
     ClipCtx c;
     c.plane = plane; c.W = p.W; c.H = p.H; c.focal = p.focal;
-    int n_nxt = 0;
-    for (int i = 0; i < n_cur; ++i) {
-      GTri o0, o1;
-      const int m = clip_one(c, cur[i], o0, o1);
-      if (m >= 1) nxt[n_nxt++] = o0;
-      if (m == 2) nxt[n_nxt++] = o1;
-    }
-    for (int i = 0; i < n_nxt; ++i) cur[i] = nxt[i];
-    n_cur = n_nxt;
-    if (n_cur == 0) break;
+    if (plane == 5) all_in = all_in && t.v[0].z > 0.01f && t.v[1].z > 0.01f && t.v[2].z > 0.01f;
+    else all_in = all_in && clip_in(c, t.v[0]) && clip_in(c, t.v[1]) && clip_in(c, t.v[2]);
   }
+  cur[0] = t;
+  if (!all_in) n_cur = clip_six_planes(p.W, p.H, p.focal, cur);
   if (!WRITE) {
     p.counts[j] = (unsigned)n_cur;
     return;
@@ -223,40 +241,91 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
   }
 }
 
-// Exclusive scan of counts[0..n) into offs[0..n], total at offs[n]; one block.
-__global__ void geom_scan_kernel(const unsigned *__restrict__ counts, unsigned *__restrict__ offs, int n) {
+// Exclusive scan of counts[0..n) into offs[0..n], total at offs[n]: per-block
+// sums, a one-block scan of those, then per-block scans with their offsets.
+constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 4, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+// Exclusive prefix of `v` over the block (all SCAN_THREADS threads call); total in *total.
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned *total) {
   __shared__ unsigned warp_excl[32];
-  __shared__ unsigned chunk_total;
+  __shared__ unsigned block_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  unsigned carry = 0;
-  for (int base = 0; base < n; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const unsigned v = i < n ? counts[i] : 0u;
-    unsigned incl = v;
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned m = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += m;
+  }
+  __syncthreads();   // protects warp_excl / block_total across back-to-back calls
+  if (lane == 31) warp_excl[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned w = lane < nw ? warp_excl[lane] : 0u;
+    unsigned wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned m = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += m;
+      const unsigned m = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += m;
     }
-    if (lane == 31) warp_excl[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const unsigned w = lane < nw ? warp_excl[lane] : 0u;
-      unsigned wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned m = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += m;
-      }
-      warp_excl[lane] = wi - w;
-      if (lane == 31) chunk_total = wi;
-    }
-    __syncthreads();
-    if (i < n) offs[i] = carry + warp_excl[warp] + incl - v;
-    carry += chunk_total;
-    __syncthreads();
+    warp_excl[lane] = wi - w;
+    if (lane == 31) block_total = wi;
   }
-  if (threadIdx.x == 0) offs[n] = carry;
+  __syncthreads();
+  *total = block_total;
+  return warp_excl[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const unsigned *__restrict__ counts, int n,
+                                                                   unsigned *__restrict__ block_sums) {
+  const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+  unsigned s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) s += base + k < n ? counts[base + k] : 0u;
+  unsigned total;
+  block_excl_scan(s, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// In-place exclusive scan of block_sums[0..nb), grand total at block_sums[nb]; one block.
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(unsigned *__restrict__ block_sums, int nb) {
+  unsigned carry = 0;
+  for (int base = 0; base < nb; base += SCAN_THREADS) {
+    const int i = base + threadIdx.x;
+    const unsigned v = i < nb ? block_sums[i] : 0u;
+    unsigned total;
+    const unsigned ex = block_excl_scan(v, &total);
+    if (i < nb) block_sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) block_sums[nb] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const unsigned *__restrict__ counts, int n,
+                                                                  const unsigned *__restrict__ block_sums, int nb,
+                                                                  unsigned *__restrict__ offs) {
+  const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+  unsigned v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = base + k < n ? counts[base + k] : 0u; s += v[k]; }
+  unsigned total;
+  unsigned run = block_sums[blockIdx.x] + block_excl_scan(s, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) offs[base + k] = run;
+    run += v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) offs[n] = block_sums[nb];
+}
+
+// offs[0..n] = exclusive scan of counts[0..n); tmp holds nb + 1 block sums.
+int scan_exclusive(b200_ctx *ctx, const unsigned *counts, unsigned *offs, int n, unsigned *tmp) {
+  const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, ctx->stream>>>(counts, n, tmp);
+  scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(tmp, nb);
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, ctx->stream>>>(counts, n, tmp, nb, offs);
+  ctx->stats.kernel_launches += 3;
+  CU_CHECK(ctx, cudaGetLastError());
+  return B200_OK;
 }
 
 // Host: runs the stage on the uploaded world-space scene; leaves the clipped list
@@ -284,15 +353,16 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
   p.n_room = n_room;
   p.boxes = p.room + n_room;
   p.n_boxes = n_boxes;
-  if (int rc = ensure(ctx, ctx->rast_geom_tmp, sizeof(unsigned) * 2 * (size_t)(n_pre + 1))) return rc;
+  const int n_scan_blocks = (n_pre + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  if (int rc = ensure(ctx, ctx->rast_geom_tmp, sizeof(unsigned) * (2 * (size_t)(n_pre + 1) + n_scan_blocks + 2))) return rc;
   p.counts = (unsigned *)ctx->rast_geom_tmp.p;
   p.offs = p.counts + (n_pre + 1);
   unsigned total = 0;
   if (n_pre > 0) {
     rast_geom_kernel<false><<<(n_pre + 127) / 128, 128, 0, ctx->stream>>>(p);
-    geom_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p.counts, p.offs, n_pre);
-    ctx->stats.kernel_launches += 2;
+    ctx->stats.kernel_launches++;
     CU_CHECK(ctx, cudaGetLastError());
+    if (int rc = scan_exclusive(ctx, p.counts, p.offs, n_pre, p.offs + (n_pre + 1))) return rc;
     CU_CHECK(ctx, cudaMemcpyAsync(&total, p.offs + n_pre, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   }

@@ -45,6 +45,7 @@ struct RastSetup {   // 80 bytes
   int nrows;         // stored rows (0: nothing to draw)
   unsigned row_off;  // index of the first stored row in the row arrays
   int flags;         // bit0: shadow-volume triangle (colour.x < 0)
+  unsigned chunk_off;  // first 8-row chunk of this triangle in chunk_owner
 };
 
 struct RastParams {
@@ -63,6 +64,10 @@ struct RastParams {
   float4 *rowsA;     // lx, rx (bit-cast ints), left zinv, zinv step
   float4 *rowsB;     // left px*zinv, its step, left py*zinv, its step
   unsigned row_cap;
+  int fast;          // shadow-free list: scatter/resolve path (rast_fast.cuh)
+  unsigned long long *keys;   // fast path: per-pixel (zinv bits, triangle + 1)
+  int *chunk_owner;  // triangle owning each 8-row chunk of the row tables
+  unsigned chunk_cap, n_chunks;
   unsigned *tile_count, *tile_off, *tile_cursor;
   int *bins, *bins_tmp;
   unsigned bin_cap;
@@ -72,7 +77,7 @@ struct RastParams {
   float *out_depth;
   int *out_index;
   uint32_t *out_argb;
-  unsigned long long *counters;  // [2] fragments, [3] bin entries, [4] rows, [5] overflow flag
+  unsigned long long *counters;  // [2] fragments, [3] bin entries, [4] rows, [5] overflow flag, [6] row chunks
 };
 
 // ---- VertexShader (:510-522) ---------------------------------------------------------
@@ -95,7 +100,7 @@ __global__ void rast_setup_kernel(const __grid_constant__ RastParams p) {
   const int lane = threadIdx.x & 31;
   int nrows = 0;
   RastSetup s;
-  s.flags = 0; s.ymin = 0; s.row0 = 0; s.nrows = 0; s.row_off = 0;
+  s.flags = 0; s.ymin = 0; s.row0 = 0; s.nrows = 0; s.row_off = 0; s.chunk_off = 0;
   int xmin = 0, xmax = -1;
   if (t < p.n_tris) {
     const rast_triangle *tr = p.src + t;
@@ -130,11 +135,27 @@ __global__ void rast_setup_kernel(const __grid_constant__ RastParams p) {
   unsigned base = 0;
   if (lane == 31 && total) base = (unsigned)atomicAdd(p.counters + 4, (unsigned long long)total);
   base = __shfl_sync(0xffffffffu, base, 31);
+  // and 8-row chunks of it, the work items of rast_rows_kernel
+  unsigned nch = (unsigned)(nrows + 7) >> 3, cincl = nch;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned n = __shfl_up_sync(0xffffffffu, cincl, o);
+    if (lane >= o) cincl += n;
+  }
+  const unsigned ctotal = __shfl_sync(0xffffffffu, cincl, 31);
+  unsigned cbase = 0;
+  if (lane == 31 && ctotal) cbase = (unsigned)atomicAdd(p.counters + 6, (unsigned long long)ctotal);
+  cbase = __shfl_sync(0xffffffffu, cbase, 31);
   if (t >= p.n_tris) return;
   s.row_off = base + incl - (unsigned)nrows;
-  if (s.row_off + (unsigned)nrows > p.row_cap) { s.nrows = 0; nrows = 0; atomicExch(p.counters + 5, 1ull); }
+  s.chunk_off = cbase + cincl - nch;
+  if (s.row_off + (unsigned)nrows > p.row_cap || s.chunk_off + nch > p.chunk_cap) {
+    s.nrows = 0; nrows = 0; nch = 0;
+    atomicExch(p.counters + 5, 1ull);
+  }
   p.setup[t] = s;
-  if (nrows > 0) {
+  for (unsigned c = 0; c < nch; ++c) p.chunk_owner[s.chunk_off + c] = t;
+  if (nrows > 0 && !p.fast) {
     const int ts = p.ts_log2;
     const int tx0 = max(0, xmin) >> ts, tx1 = min(p.W - 1, xmax - 1) >> ts;
     const int tya = s.row0 >> ts, tyb = (s.row0 + nrows - 1) >> ts;
@@ -200,6 +221,7 @@ struct RastEnd { int x, e, i; };
 
 // Row Y of ComputePolygonRows' table (:481-495) and the span steps that
 // DrawPolygonRows' Interpolate derives from it (:502-503, :524-538).
+template <bool WITH_POS = true>
 __device__ __forceinline__ void rast_row_record(const RastSetup &s, int Y, float4 &A, float4 &B) {
   RastEnd L, R;
   L.x = INT_MAX; L.e = -1; L.i = 0;
@@ -230,35 +252,41 @@ __device__ __forceinline__ void rast_row_record(const RastSetup &s, int Y, float
     const RastVtx &a = s.v[E.e], &b = s.v[(E.e + 1) % 3];
     const int n = max(abs(a.x - b.x), abs(a.y - b.y)) + 1;
     const float den = (float)max(n - 1, 1);
-    const float apx = xmul(a.px, a.zinv), apy = xmul(a.py, a.zinv);   // :526-530
-    const float bpx = xmul(b.px, b.zinv), bpy = xmul(b.py, b.zinv);
     const float sz = xdiv(xsub(b.zinv, a.zinv), den);                 // :535
-    const float spx = xdiv(xsub(bpx, apx), den), spy = xdiv(xsub(bpy, apy), den);   // :537-538
     const float fi = (float)E.i;
     zinv[side] = xadd(a.zinv, xmul(sz, fi));                          // :543
-    px[side] = xdiv(xadd(apx, xmul(spx, fi)), zinv[side]);            // :547
-    py[side] = xdiv(xadd(apy, xmul(spy, fi)), zinv[side]);            // :548
+    if (WITH_POS) {
+      const float apx = xmul(a.px, a.zinv), apy = xmul(a.py, a.zinv);   // :526-530
+      const float bpx = xmul(b.px, b.zinv), bpy = xmul(b.py, b.zinv);
+      const float spx = xdiv(xsub(bpx, apx), den), spy = xdiv(xsub(bpy, apy), den);   // :537-538
+      px[side] = xdiv(xadd(apx, xmul(spx, fi)), zinv[side]);            // :547
+      py[side] = xdiv(xadd(apy, xmul(spy, fi)), zinv[side]);            // :548
+    }
   }
   const int n = R.x - L.x + 1;
   const float den = (float)max(n - 1, 1);
-  const float lpx = xmul(px[0], zinv[0]), lpy = xmul(py[0], zinv[0]);
-  const float rpx = xmul(px[1], zinv[1]), rpy = xmul(py[1], zinv[1]);
   A = make_float4(__int_as_float(L.x), __int_as_float(R.x), zinv[0], xdiv(xsub(zinv[1], zinv[0]), den));
-  B = make_float4(lpx, xdiv(xsub(rpx, lpx), den), lpy, xdiv(xsub(rpy, lpy), den));
+  if (WITH_POS) {
+    const float lpx = xmul(px[0], zinv[0]), lpy = xmul(py[0], zinv[0]);
+    const float rpx = xmul(px[1], zinv[1]), rpy = xmul(py[1], zinv[1]);
+    B = make_float4(lpx, xdiv(xsub(rpx, lpx), den), lpy, xdiv(xsub(rpy, lpy), den));
+  }
 }
 
-// 8 lanes per triangle, lanes stride the triangle's stored rows.
+// One thread per stored row: 8-lane groups take the 8-row chunks handed out by
+// rast_setup_kernel, so tall triangles spread over many groups.
 __global__ void rast_rows_kernel(const __grid_constant__ RastParams p) {
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = gid >> 3, sub = gid & 7;
-  if (t >= p.n_tris) return;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned chunk = gid >> 3, sub = gid & 7;
+  if (chunk >= p.n_chunks) return;
+  const int t = p.chunk_owner[chunk];
   const RastSetup s = p.setup[t];
-  for (int r = sub; r < s.nrows; r += 8) {
-    float4 A, B;
-    rast_row_record(s, s.row0 + r, A, B);
-    p.rowsA[s.row_off + r] = A;
-    p.rowsB[s.row_off + r] = B;
-  }
+  const int r = (int)((chunk - s.chunk_off) << 3) + (int)sub;
+  if (r >= s.nrows) return;
+  float4 A, B;
+  rast_row_record(s, s.row0 + r, A, B);
+  p.rowsA[s.row_off + r] = A;
+  p.rowsB[s.row_off + r] = B;
 }
 
 // ---- tile lists ---------------------------------------------------------------------------
@@ -568,6 +596,8 @@ __global__ void rast_post_kernel(const __grid_constant__ RastParams p) {
   if (p.out_index) p.out_index[q] = p.index[q];
 }
 
+#include "rast_fast.cuh"
+
 // ---- host side ---------------------------------------------------------------------------------
 int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row0, int row1,
                 float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
@@ -592,12 +622,55 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   p.n_tris = n;
 
   const size_t npix = (size_t)W * H;
+  if (ctx->opt_rast_path == 2 && ctx->rast_has_shadow)
+    return ctx_fail(ctx, B200_EINVAL, "the scatter path cannot draw shadow-volume triangles");
+  const bool fast = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow);
+  p.fast = fast ? 1 : 0;
+  p.out_rgb = d_rgb; p.out_depth = d_depth; p.out_index = d_index; p.out_argb = d_argb;
+  p.counters = (unsigned long long *)ctx->counters.p;
+  if (int rc = ensure(ctx, ctx->rast_setup, sizeof(RastSetup) * (size_t)(n ? n : 1))) return rc;
+  p.setup = (RastSetup *)ctx->rast_setup.p;
   // worst case rows: every triangle spans the whole band
   size_t row_cap = (size_t)n * (size_t)(p.fb1 - p.fb0);
   const size_t row_budget = (size_t)64 << 20;   // 64 Mi rows = 2 GiB of row records
-  if (row_cap > row_budget) row_cap = row_budget;
   if (row_cap < 1) row_cap = 1;
-  if (int rc = ensure(ctx, ctx->rast_setup, sizeof(RastSetup) * (size_t)(n ? n : 1))) return rc;
+  const size_t chunk_cap = (row_cap > row_budget ? row_budget : row_cap) / 8 + (size_t)n + 1;
+  if (int rc = ensure(ctx, ctx->rast_chunks, sizeof(int) * chunk_cap)) return rc;
+  p.chunk_owner = (int *)ctx->rast_chunks.p;
+  p.chunk_cap = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
+
+  if (fast) {
+    // ---- scatter / resolve (rast_fast.cuh) ----
+    ctx->rast_w = 0; ctx->rast_h = 0;   // no intermediate buffers in this path
+    p.row_cap = 0xffffffffu;            // rows are never stored
+    if (int rc = ensure(ctx, ctx->rast_keys, npix * sizeof(unsigned long long))) return rc;
+    p.keys = (unsigned long long *)ctx->rast_keys.p;
+    CU_CHECK(ctx, cudaMemsetAsync(p.keys + (size_t)p.fb0 * W, 0, (size_t)(p.fb1 - p.fb0) * W * sizeof(unsigned long long), ctx->stream));
+    unsigned long long c[8] = {0};
+    if (n > 0) {
+      rast_setup_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(p);
+      ctx->stats.kernel_launches++;
+      CU_CHECK(ctx, cudaGetLastError());
+      CU_CHECK(ctx, cudaMemcpyAsync(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+      CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the chunk count sizes the next grid
+      if (c[5]) return ctx_fail(ctx, B200_ENOMEM, "row chunk budget exceeded");
+    }
+    p.n_chunks = (unsigned)c[6];
+    if (p.n_chunks > 0) {
+      rast_scatter_kernel<<<(int)(((size_t)p.n_chunks * 8 + 255) / 256), 256, 0, ctx->stream>>>(p);
+      ctx->stats.kernel_launches++;
+    }
+    if (row1 > row0) {
+      dim3 rg((W + RS_W - 1) / RS_W, (row1 - row0 + RS_H - 1) / RS_H);
+      rast_resolve_kernel<<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
+      ctx->stats.kernel_launches++;
+    }
+    CU_CHECK(ctx, cudaGetLastError());
+    return B200_OK;
+  }
+
+  // ---- ordered tile path ----
+  if (row_cap > row_budget) row_cap = row_budget;
   if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(float4) * row_cap)) return rc;
   if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * row_cap)) return rc;
   if (int rc = ensure(ctx, ctx->rast_tile_count, sizeof(unsigned) * (size_t)(n_tiles + 1) * 3)) return rc;
@@ -608,7 +681,6 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (int rc = ensure(ctx, ctx->rast_depth, npix * sizeof(float))) return rc;
   if (int rc = ensure(ctx, ctx->rast_index, npix * sizeof(int))) return rc;
   ctx->rast_w = W; ctx->rast_h = H;
-  p.setup = (RastSetup *)ctx->rast_setup.p;
   p.rowsA = (float4 *)ctx->rast_rowsA.p;
   p.rowsB = (float4 *)ctx->rast_rowsB.p;
   p.row_cap = (unsigned)(row_cap > 0xffffffffull ? 0xffffffffull : row_cap);
@@ -621,14 +693,10 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   p.high = (float *)ctx->rast_high.p;
   p.shadow = (int *)ctx->rast_shadow.p;
   p.index = (int *)ctx->rast_index.p;
-  p.out_rgb = d_rgb; p.out_depth = d_depth; p.out_index = d_index; p.out_argb = d_argb;
-  p.counters = (unsigned long long *)ctx->counters.p;
 
   CU_CHECK(ctx, cudaMemsetAsync(p.tile_count, 0, sizeof(unsigned) * (size_t)(n_tiles + 1), ctx->stream));
   if (n > 0) {
     rast_setup_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(p);
-    ctx->stats.kernel_launches++;
-    rast_rows_kernel<<<(int)(((size_t)n * 8 + 255) / 256), 256, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
   }
   rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
@@ -645,6 +713,11 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   p.bins = (int *)ctx->rast_bins.p;
   p.bins_tmp = (int *)ctx->rast_tmp.p;
   p.bin_cap = (unsigned)bin_total;
+  p.n_chunks = (unsigned)c[6];
+  if (p.n_chunks > 0) {
+    rast_rows_kernel<<<(int)(((size_t)p.n_chunks * 8 + 255) / 256), 256, 0, ctx->stream>>>(p);
+    ctx->stats.kernel_launches++;
+  }
   if (n > 0 && bin_total > 0) {
     rast_bin_kernel<<<(int)(((size_t)n * 8 + 255) / 256), 256, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;

@@ -116,6 +116,10 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
  * pair (on-device cross-check of the filtered kernel; results are identical). */
 #define B200_OPT_RT_BRUTEFORCE 1
 #define B200_OPT_RAST_TILE_LOG2 2
+/* Rasteriser strategy: 0 = automatic, 1 = ordered screen tiles (any list; keeps
+ * the intermediate buffers readable), 2 = atomic scatter + fused resolve
+ * (lists without shadow-volume triangles only).  Results are identical. */
+#define B200_OPT_RAST_PATH 3
 int b200_set_option(b200_ctx *ctx, int option, int value);
 
 /* Counters of the last render on this context (b200_get_stats synchronises). */

@@ -18,6 +18,16 @@ def compare(b200, renderer, W, H, focal, light_cam, light, clipped, what, tiles=
     want = h.oracle_rast_draw_clipped(W, H, focal, light_cam, light, clipped)
     cam = b200.make_camera((0, 0, 0, 1), focal, h.identity_R(), W, H)
     L = b200.make_rast_light(light_cam, light["power"], light["indirect"])
+    # the automatic strategy (scatter/resolve when the list has no shadow triangles)
+    renderer.set_option(b200.OPT_RAST_PATH, 0)
+    got = renderer.render_raster_clipped(clipped, cam, L)
+    st = renderer.stats()
+    assert np.array_equal(got["index"], want["index"]), f"{what} [auto]: owner differs at {np.count_nonzero(got['index'] != want['index'])} px"
+    assert np.array_equal(bits(got["depth"]), bits(want["depth"])), f"{what} [auto]: depth"
+    assert np.array_equal(bits(got["rgb"]), bits(want["rgb"])), f"{what} [auto]: final colour"
+    assert st["fragments"] == want["fragments"], f"{what} [auto]: fragments {st['fragments']} vs {want['fragments']}"
+    # the ordered-tile strategy, which also keeps the reference's intermediate buffers
+    renderer.set_option(b200.OPT_RAST_PATH, 1)
     for ts in tiles:
         renderer.set_option(b200.OPT_RAST_TILE_LOG2, ts)
         got = renderer.render_raster_clipped(clipped, cam, L)
@@ -32,6 +42,7 @@ def compare(b200, renderer, W, H, focal, light_cam, light, clipped, what, tiles=
         assert np.array_equal(bits(got["rgb"]), bits(want["rgb"])), f"{tag}: final colour"
         assert st["fragments"] == want["fragments"], f"{tag}: fragments {st['fragments']} vs {want['fragments']}"
     renderer.set_option(b200.OPT_RAST_TILE_LOG2, 4)
+    renderer.set_option(b200.OPT_RAST_PATH, 0)
     return want
 
 
@@ -43,8 +54,10 @@ def test_committed_reference_outputs(b200, renderer, name):
     clipped = g["clipped"].view(h.RAST_TRI).copy()
     cam = b200.make_camera((0, 0, 0, 1), float(g["focal"]), h.identity_R(), W, H)
     L = b200.make_rast_light(g["light_cam"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
+    renderer.set_option(b200.OPT_RAST_PATH, 1)
     got = renderer.render_raster_clipped(clipped, cam, L)
     buf = renderer.raster_read_buffers(W, H)
+    renderer.set_option(b200.OPT_RAST_PATH, 0)
     assert np.array_equal(bits(got["rgb"]), bits(g["rgb"]))
     assert np.array_equal(bits(got["depth"]), bits(g["depth"]))
     assert np.array_equal(buf["shadow"], g["shadow"])
@@ -155,6 +168,7 @@ def whole_draw(b200, renderer, W, H, f, cam_pos, R, light, room, boxes, what):
     want = h.oracle_rast_draw(W, H, f, cam_pos, R, light, room, boxes)
     cam = b200.make_camera(cam_pos, f, R, W, H)
     L = b200.make_rast_light(light["pos"], light["power"], light["indirect"])
+    renderer.set_option(b200.OPT_RAST_PATH, 1)      # ordered tiles: keeps the intermediate buffers
     got = renderer.render_raster(room, boxes, cam, L)
     clipped = renderer.raster_read_clipped()
     assert h.clipped_equal(clipped, want["clipped"]), f"{what}: clipped list ({len(clipped)} vs {len(want['clipped'])})"
@@ -163,6 +177,11 @@ def whole_draw(b200, renderer, W, H, f, cam_pos, R, light, room, boxes, what):
     assert np.array_equal(bits(got["depth"]), bits(want["depth"])), f"{what}: depth"
     assert np.array_equal(buf["shadow"], want["shadow"]), f"{what}: shadow mask"
     assert np.array_equal(bits(got["rgb"]), bits(want["rgb"])), f"{what}: colour"
+    renderer.set_option(b200.OPT_RAST_PATH, 0)      # automatic strategy
+    auto = renderer.render_raster(room, boxes, cam, L)
+    for key in ("rgb", "depth", "index"):
+        assert np.array_equal(auto[key], got[key]), f"{what}: automatic strategy differs in {key}"
+    assert renderer.stats()["fragments"] == want["fragments"], f"{what}: fragment count"
     argb = renderer.draw_raster(room, boxes, cam, L)
     assert np.array_equal(argb, want["argb"]), f"{what}: packed framebuffer"
     return want
@@ -217,12 +236,16 @@ def test_soup_full_size_properties(b200, renderer):
     W, H, f = 3840, 2160, 1536.0
     cam = b200.make_camera(h.DEFAULT_RAST_CAM, f, h.identity_R(), W, H)
     L = b200.make_rast_light(h.DEFAULT_RAST_LIGHT["pos"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
-    renderer.set_option(b200.OPT_RAST_TILE_LOG2, 4)
+    renderer.set_option(b200.OPT_RAST_PATH, 0)       # no shadow triangles: scatter / resolve
     a = renderer.render_raster(soup, np.zeros(0, h.RAST_TRI), cam, L)
-    assert len(renderer.raster_read_clipped(cap=1)) == 1 and renderer.stats()["fragments"] > 0
-    renderer.set_option(b200.OPT_RAST_TILE_LOG2, 5)
+    frags = renderer.stats()["fragments"]
+    assert len(renderer.raster_read_clipped(cap=1)) == 1 and frags > 0
+    with pytest.raises(b200.B200Error):
+        renderer.raster_read_buffers(W, H)           # the fused path keeps no intermediate buffers
+    renderer.set_option(b200.OPT_RAST_PATH, 1)       # ordered tiles on the same list
     b = renderer.render_raster(soup, np.zeros(0, h.RAST_TRI), cam, L)
-    renderer.set_option(b200.OPT_RAST_TILE_LOG2, 4)
+    assert renderer.stats()["fragments"] == frags
+    renderer.set_option(b200.OPT_RAST_PATH, 0)
     for k in ("rgb", "depth", "index"):
         assert np.array_equal(a[k], b[k]), k
     covered = a["depth"] > 0
@@ -237,6 +260,18 @@ def test_soup_full_size_properties(b200, renderer):
     o = h.oracle_rast_draw_clipped(W, H, f, lc, h.DEFAULT_RAST_LIGHT, clipped)
     assert np.array_equal(bits(a["depth"]), bits(o["depth"])) and np.array_equal(a["index"], o["index"])
     assert np.array_equal(bits(a["rgb"]), bits(o["rgb"]))
+
+
+def test_scatter_path_refuses_shadow_triangles(b200, renderer):
+    t = h.random_clipped_list(5, 1, 32, 32, 20.0, shadow_frac=1.0)
+    cam = b200.make_camera((0, 0, 0, 1), 20.0, h.identity_R(), 32, 32)
+    L = b200.make_rast_light((0, 0, 0, 1), (1, 1, 1), (0.2, 0.2, 0.2))
+    renderer.set_option(b200.OPT_RAST_PATH, 2)
+    try:
+        with pytest.raises(b200.B200Error):
+            renderer.render_raster_clipped(t, cam, L)
+    finally:
+        renderer.set_option(b200.OPT_RAST_PATH, 0)
 
 
 def test_invalid_arguments(b200, renderer):
