@@ -18,6 +18,19 @@ __device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
 
+// IEEE-exact x / C for the constants the reference divides by (5, 3, 9):
+// q = x*rc; r = fma(-C, q, x); q' = fma(r, rc, q) with rc = RN(1/C) is the
+// correctly rounded quotient for EVERY finite x except -0.0 (sign of zero);
+// checked exhaustively over all 2^32 inputs by oracle/tools/check_constdiv.c.
+template <int C>
+__device__ __forceinline__ float xdiv_const(float x) {
+  constexpr float c = (float)C, rc = 1.0f / (float)C;
+  const float q = __fmul_rn(x, rc);
+  const float r = __fmaf_rn(-c, q, x);
+  const float v = __fmaf_rn(r, rc, q);
+  return (x == 0.0f || !(fabsf(x) < INFINITY)) ? x : v;   // +-0, +-inf and NaN divide to themselves
+}
+
 // glm::determinant(mat3) with columns a, b, c
 // (glm/glm/detail/func_matrix.inl:235-238), one rounding per operation.
 __device__ __forceinline__ float xdet3(float ax, float ay, float az, float bx, float by, float bz,

@@ -27,12 +27,12 @@ __device__ __forceinline__ unsigned long long rast_key(float zinv, int tri) {
 
 __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned chunk = gid >> 3, sub = gid & 7;
+  const unsigned chunk = gid >> RAST_CHUNK_LOG2, sub = gid & (RAST_CHUNK - 1);
   unsigned long long n_frag = 0;
   if (chunk < p.n_chunks) {
     const int t = p.chunk_owner[chunk];
-    const RastSetup s = p.setup[t];
-    const int r = (int)((chunk - s.chunk_off) << 3) + (int)sub;
+    const RastSetup &s = p.setup[t];
+    const int r = (int)((chunk - s.chunk_off) << RAST_CHUNK_LOG2) + (int)sub;
     if (r < s.nrows) {
       const int y = s.row0 + r;
       float4 A, B;
@@ -57,9 +57,10 @@ constexpr int RS_W = 32, RS_H = 8, RS_HW = RS_W + 2, RS_HH = RS_H + 2, RS_N = RS
 __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_constant__ RastParams p) {
   __shared__ float col[RS_N][10];           // screen rgb, low rgb, high rgb, depth
   __shared__ int owner[RS_N];
-  __shared__ unsigned short work[RS_N];
+  __shared__ unsigned short work[RS_N], lead[RS_N];
+  __shared__ float4 recA[RS_N], recB[RS_N];
   __shared__ int warp_base[RS_W * RS_H / 32 + 1];
-  __shared__ int n_work;
+  __shared__ int n_work, n_lead;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int x0 = blockIdx.x * RS_W - 1, y0 = p.row0 + blockIdx.y * RS_H - 1;   // halo origin
@@ -91,14 +92,47 @@ __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_
     __syncthreads();
   }
 
+  // ---- row records: one per run of winners sharing (triangle, row) ----
+  // work[] is in row-major order, so such winners are neighbours; the first of a
+  // run (its leader) derives the record -- the expensive part -- and the others
+  // reuse it.  Leaders are compacted so that they fill warps densely.
+  if (tid == 0) n_lead = 0;
+  __syncthreads();
+  for (int base = 0; base < n_work; base += RS_W * RS_H) {
+    const int k = base + tid;
+    bool leader = false;
+    if (k < n_work) {
+      const int pos = work[k];
+      leader = k == 0 || owner[pos] != owner[work[k - 1]] || pos / RS_HW != work[k - 1] / RS_HW;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, leader);
+    if (lane == 0) warp_base[warp] = __popc(m);
+    __syncthreads();
+    if (tid == 0) {
+      int acc = n_lead;
+      for (int w = 0; w < RS_W * RS_H / 32; ++w) { const int c = warp_base[w]; warp_base[w] = acc; acc += c; }
+      n_lead = acc;
+    }
+    __syncthreads();
+    if (leader) lead[warp_base[warp] + __popc(m & ((1u << lane) - 1))] = (unsigned short)k;
+    __syncthreads();
+  }
+  for (int j = tid; j < n_lead; j += RS_W * RS_H) {
+    const int k = lead[j], pos = work[k];
+    float4 A, B;
+    rast_row_record<true>(p.setup[owner[pos]], y0 + pos / RS_HW, A, B);
+    recA[k] = A; recB[k] = B;
+  }
+  __syncthreads();
+
   // ---- deferred PixelShader of every winner (:575-586) ----
   for (int k = tid; k < n_work; k += RS_W * RS_H) {
     const int pos = work[k];
-    const int gx = x0 + pos % RS_HW, gy = y0 + pos / RS_HW;
+    const int gx = x0 + pos % RS_HW;
     const int t = owner[pos];
-    const RastSetup s = p.setup[t];
-    float4 A, B;
-    rast_row_record<true>(s, gy, A, B);
+    int lk = k;
+    while (lk > 0 && owner[work[lk - 1]] == t && work[lk - 1] / RS_HW == pos / RS_HW) --lk;
+    const float4 A = recA[lk], B = recB[lk];
     const float fi = (float)(gx - __float_as_int(A.x));
     const float zinv = xadd(A.z, xmul(A.w, fi));
     const float pz = xdiv(1.0f, zinv);                              // :546
@@ -137,9 +171,9 @@ __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_
         a = xadd(a, col[c0 + RS_HW][k]);
         a = xadd(a, col[c0 - 1][k]);
         a = xadd(a, col[c0 + 1][k]);
-        acc[b] = xdiv(a, 5.0f);
+        acc[b] = xdiv_const<5>(a);
       }
-      out[c] = xdiv(xadd(xadd(acc[0], acc[1]), acc[2]), 3.0f);     // :1750
+      out[c] = xdiv_const<3>(xadd(xadd(acc[0], acc[1]), acc[2]));     // :1750
     }
   }
   if (p.out_rgb) { p.out_rgb[3 * q] = out[0]; p.out_rgb[3 * q + 1] = out[1]; p.out_rgb[3 * q + 2] = out[2]; }

@@ -32,20 +32,26 @@
 
 constexpr int RAST_LIST_CAP = 2048;   // tile list entries sorted in shared memory
 constexpr int RAST_BATCH = 32;        // triangles per shared-memory row batch
+constexpr int RAST_CHUNK_LOG2 = 1;    // rows per work item of the per-row kernels (2^k consecutive rows of one triangle)
+constexpr int RAST_CHUNK = 1 << RAST_CHUNK_LOG2;
 
 struct RastVtx {
   int x, y;
   float zinv, px, py;
 };
 
-struct RastSetup {   // 80 bytes
+struct RastSetup {   // 160 bytes
   RastVtx v[3];
   int ymin;          // smallest vertex y (row 0 of the reference's row table)
   int row0;          // first stored row (clamped to the band being rendered)
   int nrows;         // stored rows (0: nothing to draw)
   unsigned row_off;  // index of the first stored row in the row arrays
   int flags;         // bit0: shadow-volume triangle (colour.x < 0)
-  unsigned chunk_off;  // first 8-row chunk of this triangle in chunk_owner
+  unsigned chunk_off;  // first row chunk of this triangle in chunk_owner
+  // Interpolate's per-edge steps for edge e = v[e] -> v[(e+1)%3] with
+  // N = max(|dx|,|dy|)+1 samples (:533-538): they depend on the edge only
+  float sx[3], sy[3], sz[3], spx[3], spy[3];
+  float pad[4];
 };
 
 struct RastParams {
@@ -66,7 +72,7 @@ struct RastParams {
   unsigned row_cap;
   int fast;          // shadow-free list: scatter/resolve path (rast_fast.cuh)
   unsigned long long *keys;   // fast path: per-pixel (zinv bits, triangle + 1)
-  int *chunk_owner;  // triangle owning each 8-row chunk of the row tables
+  int *chunk_owner;  // triangle owning each RAST_CHUNK-row chunk
   unsigned chunk_cap, n_chunks;
   unsigned *tile_count, *tile_off, *tile_cursor;
   int *bins, *bins_tmp;
@@ -111,6 +117,18 @@ __global__ void rast_setup_kernel(const __grid_constant__ RastParams p) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) ok = rast_vertex(v[k], p.focal, p.W, p.H, s.v[k]) && ok;
     s.flags = tr->color[0] < 0 ? 1 : 0;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {                                  // Interpolate :531-538, per edge
+      const RastVtx &a = s.v[e], &b = s.v[(e + 1) % 3];
+      const float den = (float)max(max(abs(a.x - b.x), abs(a.y - b.y)), 1);
+      const float apx = xmul(a.px, a.zinv), apy = xmul(a.py, a.zinv);
+      const float bpx = xmul(b.px, b.zinv), bpy = xmul(b.py, b.zinv);
+      s.sx[e] = xdiv((float)(b.x - a.x), den);
+      s.sy[e] = xdiv((float)(b.y - a.y), den);
+      s.sz[e] = xdiv(xsub(b.zinv, a.zinv), den);
+      s.spx[e] = xdiv(xsub(bpx, apx), den);
+      s.spy[e] = xdiv(xsub(bpy, apy), den);
+    }
     if (ok) {
       const int ymin = min(s.v[0].y, min(s.v[1].y, s.v[2].y));
       const int ymax = max(s.v[0].y, max(s.v[1].y, s.v[2].y));
@@ -135,8 +153,8 @@ __global__ void rast_setup_kernel(const __grid_constant__ RastParams p) {
   unsigned base = 0;
   if (lane == 31 && total) base = (unsigned)atomicAdd(p.counters + 4, (unsigned long long)total);
   base = __shfl_sync(0xffffffffu, base, 31);
-  // and 8-row chunks of it, the work items of rast_rows_kernel
-  unsigned nch = (unsigned)(nrows + 7) >> 3, cincl = nch;
+  // and chunks of it, the work items of the per-row kernels
+  unsigned nch = (unsigned)(nrows + RAST_CHUNK - 1) >> RAST_CHUNK_LOG2, cincl = nch;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned n = __shfl_up_sync(0xffffffffu, cincl, o);
@@ -179,7 +197,7 @@ __device__ __forceinline__ int edge_py(const RastEdge &e, int i) {
 
 // Smallest i in [0, n] with (up ? y(i) >= Y : y(i) <= Y); y(i) is monotone in i.
 __device__ __forceinline__ int edge_first(const RastEdge &e, int Y, bool up) {
-  float est = ceilf(((float)(Y - e.ay)) / e.sy);
+  float est = ceilf(__fdividef((float)(Y - e.ay), e.sy));   // an estimate: the loops below make it exact
   int i = est >= 0.f ? (est <= (float)e.n ? (int)est : e.n) : 0;   // NaN -> 0
   if (up) {
     while (i > 0 && edge_py(e, i - 1) >= Y) --i;
@@ -193,13 +211,14 @@ __device__ __forceinline__ int edge_first(const RastEdge &e, int Y, bool up) {
 
 // The samples of edge a->b (Interpolate with N = max(|dx|,|dy|)+1, :472-479) whose
 // floor(y) equals Y form one run [i0, i1]; returns false when the run is empty.
-__device__ __forceinline__ bool edge_run(const RastVtx &a, const RastVtx &b, int Y, RastEdge &e, int &i0, int &i1) {
+__device__ __forceinline__ bool edge_run(const RastSetup &s, int ei, int Y, RastEdge &e, int &i0, int &i1) {
+  const RastVtx &a = s.v[ei], &b = s.v[(ei + 1) % 3];
   const int dx = abs(a.x - b.x), dy = abs(a.y - b.y);
   e.ax = a.x; e.ay = a.y;
   e.n = max(dx, dy) + 1;
   e.den = (float)max(e.n - 1, 1);
-  e.sx = xdiv((float)(b.x - a.x), e.den);   // :533
-  e.sy = xdiv((float)(b.y - a.y), e.den);   // :534
+  e.sx = s.sx[ei];   // :533, computed once per edge by rast_setup_kernel
+  e.sy = s.sy[ei];   // :534
   if (dy == 0) {                     // step_y = 0: every sample is in row a.y
     if (Y != a.y) return false;
     i0 = 0; i1 = e.n - 1;
@@ -230,7 +249,7 @@ __device__ __forceinline__ void rast_row_record(const RastSetup &s, int Y, float
   for (int e = 0; e < 3; ++e) {
     RastEdge ed;
     int i0, i1;
-    if (!edge_run(s.v[e], s.v[(e + 1) % 3], Y, ed, i0, i1)) continue;
+    if (!edge_run(s, e, Y, ed, i0, i1)) continue;
     const int x0 = edge_px(ed, i0);
     if (x0 <= L.x) { L.x = x0; L.e = e; L.i = i0; }
     if (x0 >= R.x) { R.x = x0; R.e = e; R.i = i0; }
@@ -249,18 +268,13 @@ __device__ __forceinline__ void rast_row_record(const RastSetup &s, int Y, float
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
     const RastEnd &E = side ? R : L;
-    const RastVtx &a = s.v[E.e], &b = s.v[(E.e + 1) % 3];
-    const int n = max(abs(a.x - b.x), abs(a.y - b.y)) + 1;
-    const float den = (float)max(n - 1, 1);
-    const float sz = xdiv(xsub(b.zinv, a.zinv), den);                 // :535
+    const RastVtx &a = s.v[E.e];
     const float fi = (float)E.i;
-    zinv[side] = xadd(a.zinv, xmul(sz, fi));                          // :543
+    zinv[side] = xadd(a.zinv, xmul(s.sz[E.e], fi));                   // :543 (step_z :535 from setup)
     if (WITH_POS) {
-      const float apx = xmul(a.px, a.zinv), apy = xmul(a.py, a.zinv);   // :526-530
-      const float bpx = xmul(b.px, b.zinv), bpy = xmul(b.py, b.zinv);
-      const float spx = xdiv(xsub(bpx, apx), den), spy = xdiv(xsub(bpy, apy), den);   // :537-538
-      px[side] = xdiv(xadd(apx, xmul(spx, fi)), zinv[side]);            // :547
-      py[side] = xdiv(xadd(apy, xmul(spy, fi)), zinv[side]);            // :548
+      const float apx = xmul(a.px, a.zinv), apy = xmul(a.py, a.zinv);   // :526-527
+      px[side] = xdiv(xadd(apx, xmul(s.spx[E.e], fi)), zinv[side]);     // :547 (steps :537-538 from setup)
+      py[side] = xdiv(xadd(apy, xmul(s.spy[E.e], fi)), zinv[side]);     // :548
     }
   }
   const int n = R.x - L.x + 1;
@@ -273,15 +287,15 @@ __device__ __forceinline__ void rast_row_record(const RastSetup &s, int Y, float
   }
 }
 
-// One thread per stored row: 8-lane groups take the 8-row chunks handed out by
+// One thread per stored row: lane groups take the row chunks handed out by
 // rast_setup_kernel, so tall triangles spread over many groups.
 __global__ void rast_rows_kernel(const __grid_constant__ RastParams p) {
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned chunk = gid >> 3, sub = gid & 7;
+  const unsigned chunk = gid >> RAST_CHUNK_LOG2, sub = gid & (RAST_CHUNK - 1);
   if (chunk >= p.n_chunks) return;
   const int t = p.chunk_owner[chunk];
-  const RastSetup s = p.setup[t];
-  const int r = (int)((chunk - s.chunk_off) << 3) + (int)sub;
+  const RastSetup &s = p.setup[t];
+  const int r = (int)((chunk - s.chunk_off) << RAST_CHUNK_LOG2) + (int)sub;
   if (r >= s.nrows) return;
   float4 A, B;
   rast_row_record(s, s.row0 + r, A, B);
@@ -330,7 +344,7 @@ __global__ void rast_bin_kernel(const __grid_constant__ RastParams p) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = gid >> 3, sub = gid & 7;
   if (t >= p.n_tris) return;
-  const RastSetup s = p.setup[t];
+  const RastSetup &s = p.setup[t];
   if (s.nrows <= 0) return;
   const int ts = p.ts_log2;
   const int xmin = min(s.v[0].x, min(s.v[1].x, s.v[2].x)) - 1;
@@ -576,18 +590,18 @@ __global__ void rast_post_kernel(const __grid_constant__ RastParams p) {
       a = xadd(a, S[3 * (q + W)]);
       a = xadd(a, c2);
       a = xadd(a, S[3 * (q + 1)]);
-      a = xdiv(a, 5.0f);
+      a = xdiv_const<5>(a);
       float b = xadd(L[3 * q], L[3 * (q - W)]);
       b = xadd(b, L[3 * (q + W)]);
       b = xadd(b, L[3 * (q - 1)]);
       b = xadd(b, L[3 * (q + 1)]);
-      b = xdiv(b, 5.0f);
+      b = xdiv_const<5>(b);
       float c = xadd(Hh[3 * q], Hh[3 * (q - W)]);
       c = xadd(c, Hh[3 * (q + W)]);
       c = xadd(c, Hh[3 * (q - 1)]);
       c = xadd(c, Hh[3 * (q + 1)]);
-      c = xdiv(c, 5.0f);
-      out[k] = xdiv(xadd(xadd(a, b), c), 3.0f);   // :1750
+      c = xdiv_const<5>(c);
+      out[k] = xdiv_const<3>(xadd(xadd(a, b), c));   // :1750
     }
   }
   if (p.out_rgb) { p.out_rgb[3 * q] = out[0]; p.out_rgb[3 * q + 1] = out[1]; p.out_rgb[3 * q + 2] = out[2]; }
@@ -634,7 +648,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   size_t row_cap = (size_t)n * (size_t)(p.fb1 - p.fb0);
   const size_t row_budget = (size_t)64 << 20;   // 64 Mi rows = 2 GiB of row records
   if (row_cap < 1) row_cap = 1;
-  const size_t chunk_cap = (row_cap > row_budget ? row_budget : row_cap) / 8 + (size_t)n + 1;
+  const size_t chunk_cap = (row_cap > row_budget ? row_budget : row_cap) / RAST_CHUNK + (size_t)n + 1;
   if (int rc = ensure(ctx, ctx->rast_chunks, sizeof(int) * chunk_cap)) return rc;
   p.chunk_owner = (int *)ctx->rast_chunks.p;
   p.chunk_cap = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
@@ -657,7 +671,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     }
     p.n_chunks = (unsigned)c[6];
     if (p.n_chunks > 0) {
-      rast_scatter_kernel<<<(int)(((size_t)p.n_chunks * 8 + 255) / 256), 256, 0, ctx->stream>>>(p);
+      rast_scatter_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
     }
     if (row1 > row0) {
@@ -715,7 +729,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   p.bin_cap = (unsigned)bin_total;
   p.n_chunks = (unsigned)c[6];
   if (p.n_chunks > 0) {
-    rast_rows_kernel<<<(int)(((size_t)p.n_chunks * 8 + 255) / 256), 256, 0, ctx->stream>>>(p);
+    rast_rows_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
   }
   if (n > 0 && bin_total > 0) {

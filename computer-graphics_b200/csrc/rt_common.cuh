@@ -45,7 +45,7 @@ __device__ __forceinline__ void rt_surface(const RtKParams &p, int idx, float px
 // optional PutPixelSDL quantisation.
 __device__ __forceinline__ void rt_store_pixel(const RtKParams &p, size_t pid, bool valid, const float *pix) {
   float o[3] = {0.f, 0.f, 0.f};
-  if (valid) { o[0] = xdiv(pix[0], 9.0f); o[1] = xdiv(pix[1], 9.0f); o[2] = xdiv(pix[2], 9.0f); }
+  if (valid) { o[0] = xdiv_const<9>(pix[0]); o[1] = xdiv_const<9>(pix[1]); o[2] = xdiv_const<9>(pix[2]); }
   if (p.rgb) { p.rgb[3 * pid] = o[0]; p.rgb[3 * pid + 1] = o[1]; p.rgb[3 * pid + 2] = o[2]; }
   if (p.argb) p.argb[pid] = put_pixel_argb(o[0], o[1], o[2]);
 }
