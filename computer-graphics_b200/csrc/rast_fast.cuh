@@ -9,15 +9,17 @@
 // (non-negative floats order like their bit patterns; fragments with zinv < 0 or
 // NaN fail `zinv >= depth` against the cleared buffer and are never drawn).
 //
-//   rast_scatter_kernel  one thread per (triangle,row): span ends and zinv step
-//                        (depth part of the row record only), atomicMax per pixel
+//   rast_scatter_kernel  one thread per (triangle,row): the row record (span ends,
+//                        zinv and position steps) is derived and stored, then one
+//                        atomicMax per pixel of the span
 //   rast_resolve_kernel  per 32x8 pixel tile + 1-pixel halo: the winners are
-//                        compacted, each is re-derived exactly (row record with
-//                        positions, fragment, three calculateIllumination) into
-//                        shared memory, then the 5-tap AA / HDR mean of the post
-//                        pass (:283-307; no shadow flags => nothing is darkened)
-//                        is taken from shared memory and the frame written once.
-// No per-pixel colour buffers, no row tables and no tile lists touch HBM.
+//                        compacted, each winning fragment is re-derived exactly
+//                        from its row record (fragment, three
+//                        calculateIllumination) into shared memory, then the 5-tap
+//                        AA / HDR mean of the post pass (:283-307; no shadow flags
+//                        => nothing is darkened) is taken from shared memory and
+//                        the frame written once.
+// No per-pixel colour buffers and no tile lists touch HBM.
 #pragma once
 
 __device__ __forceinline__ unsigned long long rast_key(float zinv, int tri) {
@@ -36,7 +38,9 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
     if (r < s.nrows) {
       const int y = s.row0 + r;
       float4 A, B;
-      rast_row_record<false>(s, y, A, B);
+      rast_row_record<true>(s, y, A, B);
+      p.rowsA[s.row_off + r] = A;      // kept for the resolve pass: the winner's fragment is
+      p.rowsB[s.row_off + r] = B;      // re-derived from its row record
       const int lx = __float_as_int(A.x), rx = __float_as_int(A.y);
       const int x0 = max(lx, 0), x1 = min(rx, p.W);      // right end excluded (:504); bounds (:573)
       unsigned long long *row = p.keys + (size_t)y * p.W;
@@ -57,10 +61,9 @@ constexpr int RS_W = 32, RS_H = 8, RS_HW = RS_W + 2, RS_HH = RS_H + 2, RS_N = RS
 __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_constant__ RastParams p) {
   __shared__ float col[RS_N][10];           // screen rgb, low rgb, high rgb, depth
   __shared__ int owner[RS_N];
-  __shared__ unsigned short work[RS_N], lead[RS_N];
-  __shared__ float4 recA[RS_N], recB[RS_N];
+  __shared__ unsigned short work[RS_N];
   __shared__ int warp_base[RS_W * RS_H / 32 + 1];
-  __shared__ int n_work, n_lead;
+  __shared__ int n_work;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int x0 = blockIdx.x * RS_W - 1, y0 = p.row0 + blockIdx.y * RS_H - 1;   // halo origin
@@ -92,47 +95,14 @@ __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_
     __syncthreads();
   }
 
-  // ---- row records: one per run of winners sharing (triangle, row) ----
-  // work[] is in row-major order, so such winners are neighbours; the first of a
-  // run (its leader) derives the record -- the expensive part -- and the others
-  // reuse it.  Leaders are compacted so that they fill warps densely.
-  if (tid == 0) n_lead = 0;
-  __syncthreads();
-  for (int base = 0; base < n_work; base += RS_W * RS_H) {
-    const int k = base + tid;
-    bool leader = false;
-    if (k < n_work) {
-      const int pos = work[k];
-      leader = k == 0 || owner[pos] != owner[work[k - 1]] || pos / RS_HW != work[k - 1] / RS_HW;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, leader);
-    if (lane == 0) warp_base[warp] = __popc(m);
-    __syncthreads();
-    if (tid == 0) {
-      int acc = n_lead;
-      for (int w = 0; w < RS_W * RS_H / 32; ++w) { const int c = warp_base[w]; warp_base[w] = acc; acc += c; }
-      n_lead = acc;
-    }
-    __syncthreads();
-    if (leader) lead[warp_base[warp] + __popc(m & ((1u << lane) - 1))] = (unsigned short)k;
-    __syncthreads();
-  }
-  for (int j = tid; j < n_lead; j += RS_W * RS_H) {
-    const int k = lead[j], pos = work[k];
-    float4 A, B;
-    rast_row_record<true>(p.setup[owner[pos]], y0 + pos / RS_HW, A, B);
-    recA[k] = A; recB[k] = B;
-  }
-  __syncthreads();
-
   // ---- deferred PixelShader of every winner (:575-586) ----
   for (int k = tid; k < n_work; k += RS_W * RS_H) {
     const int pos = work[k];
     const int gx = x0 + pos % RS_HW;
     const int t = owner[pos];
-    int lk = k;
-    while (lk > 0 && owner[work[lk - 1]] == t && work[lk - 1] / RS_HW == pos / RS_HW) --lk;
-    const float4 A = recA[lk], B = recB[lk];
+    const RastSetup &s = p.setup[t];
+    const unsigned rr = s.row_off + (unsigned)(y0 + pos / RS_HW - s.row0);
+    const float4 A = p.rowsA[rr], B = p.rowsB[rr];
     const float fi = (float)(gx - __float_as_int(A.x));
     const float zinv = xadd(A.z, xmul(A.w, fi));
     const float pz = xdiv(1.0f, zinv);                              // :546

@@ -151,14 +151,25 @@ __device__ __noinline__ int clip_six_planes(int W, int H, float focal, GTri *cur
 
 template <bool WRITE>
 __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ GeomParams p) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int GT = 128, TW = sizeof(rast_triangle) / 4;
+  __shared__ uint32_t stage[GT * TW];   // coalesced word streams in and out of the 84-byte records
+  const int j0 = blockIdx.x * GT;
+  const int j = j0 + threadIdx.x;
   const int n_pre = p.n_room + 7 * p.n_boxes;
-  if (j >= n_pre) return;
+  // a block whose triangles all come from `room` reads them through shared memory
+  const bool staged_in = j0 + GT <= p.n_room;
+  if (staged_in) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.room + j0);
+    for (int i = threadIdx.x; i < GT * TW; i += GT) stage[i] = __ldg(src + i);
+    __syncthreads();
+  }
   // ---- the pre-clip triangle j (Draw :205-220) ----
   const rast_triangle *srcp;
   int s = 0;
-  if (j < p.n_room) srcp = p.room + j;
-  else { srcp = p.boxes + (j - p.n_room) / 7; s = (j - p.n_room) % 7; }
+  const int jj = j < n_pre ? j : n_pre - 1;   // tail threads repeat the last triangle, their output is dropped
+  if (staged_in) srcp = reinterpret_cast<const rast_triangle *>(stage + threadIdx.x * TW);
+  else if (jj < p.n_room) srcp = p.room + jj;
+  else { srcp = p.boxes + (jj - p.n_room) / 7; s = (jj - p.n_room) % 7; }
   GTri t;
   float attr[9];   // normal[4], color[3], texture, index (bit-cast)
   {
@@ -221,9 +232,27 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
   cur[0] = t;
   if (!all_in) n_cur = clip_six_planes(p.W, p.H, p.focal, cur);
   if (!WRITE) {
-    p.counts[j] = (unsigned)n_cur;
+    if (j < n_pre) p.counts[j] = (unsigned)n_cur;
     return;
   }
+  // Common case: the whole block is unclipped (one output each, contiguous in the
+  // list): write the records through shared memory as one coalesced stream.
+  if (__syncthreads_and(staged_in && n_cur == 1)) {
+    float *o = reinterpret_cast<float *>(stage) + threadIdx.x * TW;
+    const GTri &g = cur[0];
+    o[0] = g.v[0].x; o[1] = g.v[0].y; o[2] = g.v[0].z; o[3] = g.v[0].w;
+    o[4] = g.v[1].x; o[5] = g.v[1].y; o[6] = g.v[1].z; o[7] = g.v[1].w;
+    o[8] = g.v[2].x; o[9] = g.v[2].y; o[10] = g.v[2].z; o[11] = g.v[2].w;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[12 + k] = attr[k];
+    __syncthreads();
+    const unsigned off0 = p.offs[j0];
+    uint32_t *dst = reinterpret_cast<uint32_t *>(p.out + off0);
+    if (off0 + GT <= p.out_cap)
+      for (int i = threadIdx.x; i < GT * TW; i += GT) dst[i] = stage[i];
+    return;
+  }
+  if (j >= n_pre) return;
   const unsigned off = p.offs[j];
   for (int i = 0; i < n_cur; ++i) {
     if (off + i >= p.out_cap) break;

@@ -101,22 +101,35 @@ __device__ __forceinline__ bool rast_vertex(const float *v, float focal, int W, 
   return true;
 }
 
-__global__ void rast_setup_kernel(const __grid_constant__ RastParams p) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int SETUP_THREADS = 256;
+constexpr int TRI_WORDS = sizeof(rast_triangle) / 4, SETUP_WORDS = sizeof(RastSetup) / 4;
+
+__global__ void __launch_bounds__(SETUP_THREADS) rast_setup_kernel(const __grid_constant__ RastParams p) {
+  // The 84-byte triangles and the 160-byte setup records are staged through shared
+  // memory so that global memory only sees fully coalesced word streams.
+  __shared__ uint32_t stage[SETUP_THREADS * (SETUP_WORDS + 1)];   // +1: conflict-free record stride
+  const int t0 = blockIdx.x * SETUP_THREADS;
+  const int t = t0 + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  const int n_here = min(SETUP_THREADS, p.n_tris - t0);
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.src + t0);
+    for (int i = threadIdx.x; i < n_here * TRI_WORDS; i += SETUP_THREADS) stage[i] = __ldg(src + i);
+  }
+  __syncthreads();
   int nrows = 0;
   RastSetup s;
   s.flags = 0; s.ymin = 0; s.row0 = 0; s.nrows = 0; s.row_off = 0; s.chunk_off = 0;
   int xmin = 0, xmax = -1;
   if (t < p.n_tris) {
-    const rast_triangle *tr = p.src + t;
+    const float *tr = reinterpret_cast<const float *>(stage) + threadIdx.x * TRI_WORDS;   // v0[4] v1[4] v2[4] normal[4] color[3]
     float v[3][3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { v[0][k] = tr->v0[k]; v[1][k] = tr->v1[k]; v[2][k] = tr->v2[k]; }
+    for (int k = 0; k < 3; ++k) { v[0][k] = tr[k]; v[1][k] = tr[4 + k]; v[2][k] = tr[8 + k]; }
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) ok = rast_vertex(v[k], p.focal, p.W, p.H, s.v[k]) && ok;
-    s.flags = tr->color[0] < 0 ? 1 : 0;
+    s.flags = tr[16] < 0 ? 1 : 0;
 #pragma unroll
     for (int e = 0; e < 3; ++e) {                                  // Interpolate :531-538, per edge
       const RastVtx &a = s.v[e], &b = s.v[(e + 1) % 3];
@@ -164,14 +177,25 @@ __global__ void rast_setup_kernel(const __grid_constant__ RastParams p) {
   unsigned cbase = 0;
   if (lane == 31 && ctotal) cbase = (unsigned)atomicAdd(p.counters + 6, (unsigned long long)ctotal);
   cbase = __shfl_sync(0xffffffffu, cbase, 31);
-  if (t >= p.n_tris) return;
   s.row_off = base + incl - (unsigned)nrows;
   s.chunk_off = cbase + cincl - nch;
-  if (s.row_off + (unsigned)nrows > p.row_cap || s.chunk_off + nch > p.chunk_cap) {
+  if (t < p.n_tris && (s.row_off + (unsigned)nrows > p.row_cap || s.chunk_off + nch > p.chunk_cap)) {
     s.nrows = 0; nrows = 0; nch = 0;
     atomicExch(p.counters + 5, 1ull);
   }
-  p.setup[t] = s;
+  __syncthreads();   // every thread has read its triangle: the buffer now carries the records out
+  if (t < p.n_tris) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(&s);
+#pragma unroll
+    for (int k = 0; k < SETUP_WORDS; ++k) stage[threadIdx.x * (SETUP_WORDS + 1) + k] = w[k];
+  }
+  __syncthreads();
+  {
+    uint32_t *dst = reinterpret_cast<uint32_t *>(p.setup + t0);
+    for (int i = threadIdx.x; i < n_here * SETUP_WORDS; i += SETUP_THREADS)
+      dst[i] = stage[(i / SETUP_WORDS) * (SETUP_WORDS + 1) + i % SETUP_WORDS];
+  }
+  if (t >= p.n_tris) return;
   for (unsigned c = 0; c < nch; ++c) p.chunk_owner[s.chunk_off + c] = t;
   if (nrows > 0 && !p.fast) {
     const int ts = p.ts_log2;
@@ -662,7 +686,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     CU_CHECK(ctx, cudaMemsetAsync(p.keys + (size_t)p.fb0 * W, 0, (size_t)(p.fb1 - p.fb0) * W * sizeof(unsigned long long), ctx->stream));
     unsigned long long c[8] = {0};
     if (n > 0) {
-      rast_setup_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(p);
+      rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
       CU_CHECK(ctx, cudaGetLastError());
       CU_CHECK(ctx, cudaMemcpyAsync(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
@@ -670,6 +694,13 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
       if (c[5]) return ctx_fail(ctx, B200_ENOMEM, "row chunk budget exceeded");
     }
     p.n_chunks = (unsigned)c[6];
+    {
+      const size_t n_rows = (size_t)c[4] ? (size_t)c[4] : 1;     // exact: the setup kernel counted them
+      if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(float4) * n_rows)) return rc;
+      if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * n_rows)) return rc;
+      p.rowsA = (float4 *)ctx->rast_rowsA.p;
+      p.rowsB = (float4 *)ctx->rast_rowsB.p;
+    }
     if (p.n_chunks > 0) {
       rast_scatter_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
@@ -710,7 +741,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
 
   CU_CHECK(ctx, cudaMemsetAsync(p.tile_count, 0, sizeof(unsigned) * (size_t)(n_tiles + 1), ctx->stream));
   if (n > 0) {
-    rast_setup_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(p);
+    rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
   }
   rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
