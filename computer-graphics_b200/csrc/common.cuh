@@ -83,6 +83,7 @@ struct b200_ctx {
   DevBuf rt_geom;     // float4[3n]: v0, e1, e2 for the exact test
   DevBuf rt_spheres;  // rt_sphere[n]
   DevBuf rt_planes;   // float4[..]: per-origin edge-function planes for the filter
+  DevBuf rt_dtcam;    // float[n]: per-frame numerator of t for primary rays
   int rt_n_tris = 0, rt_n_spheres = 0;
   float rt_world_abs = 0.f;   // max |coordinate| over the uploaded scene
   int pending = 0;            // 1 = RT, 2 = RAST render whose counters are not read back yet

@@ -15,6 +15,7 @@ struct RtKParams {
   int n_tris, n_sph;
   // filtered kernel only
   const float4 *planes;      // see rt_filtered.cuh
+  const float *dt_cam;       // per triangle: det(camera - v0, e1, e2)
   int tris_per_tile;
   // outputs: full-frame addressing (pixel (x, y) at y*W + x); any may be null
   float *rgb;

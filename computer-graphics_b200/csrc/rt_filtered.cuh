@@ -87,6 +87,7 @@ struct RtPrepParams {
   float lights[B200_MAX_LIGHTS][3];
   float4 *planes;    // [(1 + n_lights)][n_tiles * RT_TILE][3]
   size_t origin_stride_f4;
+  float *dt_cam;     // [n_tris] det(start - v0, e1, e2) for start = camera, in the reference's own arithmetic
 };
 
 __global__ void rt_prep_planes_kernel(const __grid_constant__ RtPrepParams p) {
@@ -156,6 +157,11 @@ __global__ void rt_prep_planes_kernel(const __grid_constant__ RtPrepParams p) {
   }
   float4 *dst = p.planes + (size_t)o * p.origin_stride_f4 + (size_t)i * RT_REC_F4;
   dst[0] = q0; dst[1] = q1; dst[2] = q2;
+  if (o == 0) {
+    // numerator of t (skeleton.cpp:305-306): the same for every primary ray, exact float ops
+    const float sx = xsub(p.cam[0], v0[0]), sy = xsub(p.cam[1], v0[1]), sz = xsub(p.cam[2], v0[2]);
+    p.dt_cam[i] = xdet3(sx, sy, sz, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x);
+  }
 }
 
 // ---- warp helpers -------------------------------------------------------------------

@@ -23,17 +23,18 @@ __device__ __forceinline__ void rt_surface2(const rt_triangle *__restrict__ src,
 
 // Reference arithmetic for one (primary ray, triangle) pair; `inside` = the
 // filter proved `check` (:328) true, so u and v need not be formed.
-__device__ __noinline__ RtHit rt_ex_primary(const float4 *__restrict__ geom, float cx, float cy, float cz, int tri,
-                                            int inside, float dx, float dy, float dz, float len, RtHit best) {
+__device__ __noinline__ RtHit rt_ex_primary(const float4 *__restrict__ geom, const float *__restrict__ dt_cam,
+                                            float cx, float cy, float cz, int tri, int inside, float dx, float dy,
+                                            float dz, float len, RtHit best) {
   const float4 g0 = __ldg(geom + 3 * tri), g1 = __ldg(geom + 3 * tri + 1), g2 = __ldg(geom + 3 * tri + 2);
   const float e1x = g0.w, e1y = g1.x, e1z = g1.y, e2x = g1.z, e2y = g1.w, e2z = g2.x;
-  const float sx = xsub(cx, g0.x), sy = xsub(cy, g0.y), sz = xsub(cz, g0.z);
   const float D = xdet3(-dx, -dy, -dz, e1x, e1y, e1z, e2x, e2y, e2z);
-  const float t = xdiv(xdet3(sx, sy, sz, e1x, e1y, e1z, e2x, e2y, e2z), D);
+  const float t = xdiv(__ldg(dt_cam + tri), D);   // numerator: the same for every primary ray (rt_prep_planes_kernel)
   const float distance = xmul(t, len);
   if (distance < 0.0f) return best;
   if (distance >= best.dist || distance > FLT_MAX) return best;
   if (!inside) {
+    const float sx = xsub(cx, g0.x), sy = xsub(cy, g0.y), sz = xsub(cz, g0.z);
     const float u = xdiv(xdet3(-dx, -dy, -dz, sx, sy, sz, e2x, e2y, e2z), D);
     const float v = xdiv(xdet3(-dx, -dy, -dz, e1x, e1y, e1z, sx, sy, sz), D);
     if (!((u >= 0) && (v >= 0) && (xadd(u, v) <= 1))) return best;
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(RT_THREADS, 2) rt_filtered_kernel(const __grid
               const bool farther = (mN > E) && (dt_lo * len[k] >= best[k].dist * (mN + E));
               if (!farther) {
                 ++n_exact;
-                best[k] = rt_ex_primary(p.geom, cx, cy, cz, tri, m3 >= E ? 1 : 0, dx, dy, dz, len[k], best[k]);
+                best[k] = rt_ex_primary(p.geom, p.dt_cam, cx, cy, cz, tri, m3 >= E ? 1 : 0, dx, dy, dz, len[k], best[k]);
               }
             }
           }

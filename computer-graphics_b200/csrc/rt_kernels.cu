@@ -152,6 +152,8 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
   const size_t origin_stride = (size_t)n_tiles * RT_TILE * RT_REC_F4;
   if (int rc = ensure(ctx, ctx->rt_planes, sizeof(float4) * (origin_stride * (1 + f.n_lights) + 1))) return rc;
   p.planes = (const float4 *)ctx->rt_planes.p;
+  if (int rc = ensure(ctx, ctx->rt_dtcam, sizeof(float) * (size_t)(n > 0 ? n : 1))) return rc;
+  p.dt_cam = (const float *)ctx->rt_dtcam.p;
 
   if (n > 0) {
     RtPrepParams q;
@@ -182,6 +184,7 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
     q.world_S = 2.0f * m * 1.001f + 1e-4f;
     q.planes = (float4 *)ctx->rt_planes.p;
     q.origin_stride_f4 = origin_stride;
+    q.dt_cam = (float *)ctx->rt_dtcam.p;
     dim3 grid((n + 127) / 128, 1 + f.n_lights);
     rt_prep_planes_kernel<<<grid, 128, 0, ctx->stream>>>(q);
     ctx->stats.kernel_launches++;
