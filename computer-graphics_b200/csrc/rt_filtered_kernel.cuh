@@ -54,13 +54,22 @@ __device__ __noinline__ int rt_ex_shadow(const float4 *__restrict__ geom, const 
   const float rx = xsub(Lx, px), ry = xsub(Ly, py), rz = xsub(Lz, pz);                          // :370
   const float ox = xadd(px, xmul(nx, 0.00001f)), oy = xadd(py, xmul(ny, 0.00001f)),
               oz = xadd(pz, xmul(nz, 0.00001f));                                                 // :394
-  const float len = xsqrt(xdot3(rx, ry, rz, rx, ry, rz));
-  const float r_mag = rt_exact_rmag(rx, ry, rz);
   const float4 g0 = __ldg(geom + 3 * tri), g1 = __ldg(geom + 3 * tri + 1), g2 = __ldg(geom + 3 * tri + 2);
   const float e1x = g0.w, e1y = g1.x, e1z = g1.y, e2x = g1.z, e2y = g1.w, e2z = g2.x;
   const float sx = xsub(ox, g0.x), sy = xsub(oy, g0.y), sz = xsub(oz, g0.z);
   const float D = xdet3(-rx, -ry, -rz, e1x, e1y, e1z, e2x, e2y, e2z);
-  const float t = xdiv(xdet3(sx, sy, sz, e1x, e1y, e1z, e2x, e2y, e2z), D);
+  const float Dt = xdet3(sx, sy, sz, e1x, e1y, e1z, e2x, e2y, e2z);
+  const float rr = xdot3(rx, ry, rz, rx, ry, rz);
+  // The usual outcome for the triangle the ray starts on: t = Dt / D is negative, so
+  // `distance < 0` (:311) rejects it.  The sign of an IEEE quotient is the sign of
+  // its operands and neither t nor t * len can underflow to -0 under the guards
+  // below, so the division, the length and the double-precision r_magnitude are
+  // not needed to know that.
+  if (((Dt < 0.0f) != (D < 0.0f)) && fabsf(Dt) > 1e-20f * fabsf(D) && fabsf(D) < 1e30f && rr > 1e-30f && rr < 1e30f)
+    return 0;
+  const float len = xsqrt(rr);
+  const float r_mag = rt_exact_rmag(rx, ry, rz);
+  const float t = xdiv(Dt, D);
   const float distance = xmul(t, len);
   if (distance < 0.0f) return 0;
   if (!(distance < r_mag) || distance > FLT_MAX) return 0;
