@@ -312,26 +312,57 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- where each rank's band goes --------------------------------------------------
+    # N == 1: plain device buffers.  N > 1: the frame lives on rank 0 and
+    #   "p2p_store"  (default) every rank is handed a peer mapping of rank 0's frame
+    #                (torch symmetric memory over NVLink) and its kernels store the band
+    #                straight into it -- the exchange happens in the epilogue of the render
+    #                kernels, followed by one device-side barrier;
+    #   "nccl"       each rank renders into a local band, then an NCCL gather to rank 0.
+    # The device entry points address outputs as full frames (pixel (x, y) at y*W + x).
+    gather, gather_note, symm_handles = "none", None, []
+    band_rgb = band_depth = full_rgb = full_depth = None
+    if world > 1 and args.gather == "p2p":
+        try:
+            import torch.distributed._symmetric_memory as symm
+            frame_rgb = symm.empty((H, W, 3), dtype=torch.float32, device="cuda")
+            frame_depth = symm.empty((H, W), dtype=torch.float32, device="cuda")
+            h_rgb = symm.rendezvous(frame_rgb, dist.group.WORLD)
+            h_depth = symm.rendezvous(frame_depth, dist.group.WORLD)
+            p_rgb, p_depth = int(h_rgb.buffer_ptrs[0]), int(h_depth.buffer_ptrs[0])
+            symm_handles = [h_rgb, h_depth, frame_rgb, frame_depth]
+            gather = "p2p_store"
+        except Exception as e:                      # both branches are GPU paths; say which one ran
+            gather_note = f"symmetric memory unavailable ({type(e).__name__}: {e}); NCCL gather used"
+    if gather != "p2p_store":
+        band_rgb = torch.empty((rows, W, 3), dtype=torch.float32, device="cuda")
+        band_depth = torch.empty((rows, W), dtype=torch.float32, device="cuda")
+        p_rgb = band_rgb.data_ptr() - row0 * W * 12     # frame origin above the band
+        p_depth = band_depth.data_ptr() - row0 * W * 4
+        if world > 1:
+            gather = "nccl_gather"
+            if rank == 0:
+                full_rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+                full_depth = torch.empty((H, W), dtype=torch.float32, device="cuda")
+
+    def exchange():
+        if gather == "p2p_store":
+            symm_handles[0].barrier(channel=0)      # every band has landed in rank 0's frame
+        elif gather == "nccl_gather":
+            dist.gather(band_rgb, list(full_rgb.view(world, rows, W, 3).unbind(0)) if rank == 0 else None, dst=0)
+            dist.gather(band_depth, list(full_depth.view(world, rows, W).unbind(0)) if rank == 0 else None, dst=0)
+
     result = {}
+    pinned = torch.empty(rows * W, dtype=torch.int32).pin_memory()
     if kind == "rt":
         tris, sph = b200.scene_cornell_rt_tessellated(60) if args.workload == "rt_tess100k_4k" else b200.scene_cornell_rt()
         cam = b200.make_camera(RT_CAM, focal, h.identity_R(), W, H)
         r.rt_upload_scene(tris, sph)
-        band_rgb = torch.empty((rows, W, 3), dtype=torch.float32, device="cuda")
-        band_depth = torch.empty((rows, W), dtype=torch.float32, device="cuda")
-        full_rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda") if rank == 0 and world > 1 else None
-        full_depth = torch.empty((H, W), dtype=torch.float32, device="cuda") if rank == 0 and world > 1 else None
-        # full-frame addressing: pixel (x, y) at y*W + x, so point the frame origin above the band
-        p_rgb = band_rgb.data_ptr() - row0 * W * 12
-        p_depth = band_depth.data_ptr() - row0 * W * 4
 
         def step():
             r.rt_render_device(cam, RT_LIGHTS, row0, row1, p_rgb, p_depth)
-            if world > 1:
-                dist.gather(band_rgb, list(full_rgb.view(world, rows, W, 3).unbind(0)) if rank == 0 else None, dst=0)
-                dist.gather(band_depth, list(full_depth.view(world, rows, W).unbind(0)) if rank == 0 else None, dst=0)
+            exchange()
 
-        pinned = torch.empty(rows * W, dtype=torch.int32).pin_memory()
         tris_pin = torch.from_numpy(tris.view(np.uint8).copy()).pin_memory()
         sph_pin = torch.from_numpy(sph.view(np.uint8).copy()).pin_memory()
         tris_h = tris_pin.numpy().view(b200.RT_TRI)
@@ -347,20 +378,11 @@ def run_b200(args):
         cam = b200.make_camera(RAST_CAM, focal, h.identity_R(), W, H)
         L = b200.make_rast_light(RAST_LIGHT["pos"], RAST_LIGHT["power"], RAST_LIGHT["indirect"])
         r.rast_upload_scene(room, boxes)
-        band_rgb = torch.empty((rows, W, 3), dtype=torch.float32, device="cuda")
-        band_depth = torch.empty((rows, W), dtype=torch.float32, device="cuda")
-        full_rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda") if rank == 0 and world > 1 else None
-        full_depth = torch.empty((H, W), dtype=torch.float32, device="cuda") if rank == 0 and world > 1 else None
-        p_rgb = band_rgb.data_ptr() - row0 * W * 12
-        p_depth = band_depth.data_ptr() - row0 * W * 4
 
         def step():
             r.rast_draw_device(cam, L, row0, row1, p_rgb, p_depth)
-            if world > 1:
-                dist.gather(band_rgb, list(full_rgb.view(world, rows, W, 3).unbind(0)) if rank == 0 else None, dst=0)
-                dist.gather(band_depth, list(full_depth.view(world, rows, W).unbind(0)) if rank == 0 else None, dst=0)
+            exchange()
 
-        pinned = torch.empty(rows * W, dtype=torch.int32).pin_memory()
         room_pin = torch.from_numpy(room.view(np.uint8).copy()).pin_memory()
         boxes_pin = torch.from_numpy(boxes.view(np.uint8).copy() if len(boxes) else np.zeros(84, np.uint8)).pin_memory()
         room_h = room_pin.numpy().view(b200.RAST_TRI)
@@ -425,7 +447,7 @@ def run_b200(args):
                     "exact_evals": st["exact_evals"]}
         config = {"workload": args.workload, "width": W, "height": H, "focal": focal, "spp": 9,
                   "triangles": int(len(tris)), "spheres": int(len(sph)), "lights": len(RT_LIGHTS),
-                  "rays_per_frame": rays, "parallelism": f"row bands x{world}",
+                  "rays_per_frame": rays, "parallelism": f"row bands x{world}", "gather": gather, "gather_note": gather_note,
                   "l2": "flushed between timed steps (256 MiB write); outputs 133 MB > L2"}
     else:
         frames = 1.0
@@ -439,7 +461,7 @@ def run_b200(args):
                     "kernel_ms": float(kernel_ms), "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})",
                     "algorithmic_work": f"{bytes_alg / 1e6:.1f} MB per frame (16 B/pixel + 84 B/triangle)"}
         config = {"workload": args.workload, "width": W, "height": H, "focal": focal, "triangles_in": int(n_in),
-                  "fragments_per_frame": float(units[1]), "parallelism": f"row bands x{world}",
+                  "fragments_per_frame": float(units[1]), "parallelism": f"row bands x{world}", "gather": gather, "gather_note": gather_note,
                   "l2": "flushed between timed steps (256 MiB write)"}
 
     cpu = None
@@ -470,6 +492,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="default", choices=["default"] + sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: peer stores into rank 0's frame (default) or an NCCL gather")
     args = ap.parse_args()
     both = args.workload == "default"
     if both:
