@@ -145,18 +145,18 @@ def sample_windows(H, n_windows, rows_each):
     return [(int(round(i * step)), rows_each) for i in range(n_windows)]
 
 
-def run_reference(args):
+def run_reference(args, workload):
     import helpers as h
     from multiprocessing import get_context
-    kind, W, H, focal = WORKLOADS[args.workload]
+    kind, W, H, focal = WORKLOADS[workload]
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     cores = os.cpu_count() or 1
     b200 = importlib.import_module("computer-graphics_b200")
     if kind != "rt":
-        return run_reference_rast(args, b200, cores)
-    if args.workload == "rt_tess100k_4k":
+        return run_reference_rast(args, workload, b200, cores)
+    if workload == "rt_tess100k_4k":
         tris, sph = b200.scene_cornell_rt_tessellated(60)
         rows_each, per_proc = 1, 1          # ~0.9 s per row per core at 100 800 triangles
     else:
@@ -180,42 +180,43 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": W, "height": H, "focal": focal, "spp": 9,
+            "config": {"workload": workload, "width": W, "height": H, "focal": focal, "spp": 9,
                        "triangles": int(len(tris)), "spheres": int(len(sph))},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    return line
 
 
-def run_reference_rast(args, b200, cores):
+def run_reference_rast(args, workload, b200, cores):
     """Rasteriser reference arm: whole reference Draw (geometry + clip + triangle loop +
     post) at the workload's resolution; single-threaded by construction, so `cores`
     independent frames are rendered concurrently and frames/s is their aggregate."""
     import helpers as h
     from multiprocessing import get_context
-    kind, W, H, focal = WORKLOADS[args.workload]
+    kind, W, H, focal = WORKLOADS[workload]
     n_proc = max(1, min(cores, 8))      # each process owns ~365 MB of static frame buffers at 4K
+    warmup, steps = min(args.warmup, 1), min(args.steps, 3)   # a soup frame takes seconds on a core
     ctx = get_context("fork")
     with ctx.Pool(n_proc) as pool:
         times = []
-        for step in range(args.warmup + args.steps):
+        for step in range(warmup + steps):
             t0 = time.perf_counter()
-            pool.map(_ref_rast_worker, [(args.workload,)] * n_proc, chunksize=1)
+            pool.map(_ref_rast_worker, [(workload,)] * n_proc, chunksize=1)
             dt = time.perf_counter() - t0
-            if step >= args.warmup:
+            if step >= warmup:
                 times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = n_proc / (ms * 1e-3)
     line = {"impl": "reference", "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": W, "height": H, "focal": focal},
+            "config": {"workload": workload, "width": W, "height": H, "focal": focal},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": n_proc, "kind": "reference",
                              "sample": f"{n_proc} whole frames per step, one per process"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 _rast_scene_cache = {}
@@ -283,7 +284,24 @@ def cpu_baseline_rast(workload):
             "sample": f"{n} whole frames (median), reference Draw incl. geometry and post pass"}
 
 
-def run_b200(args):
+def run_b200(args, workloads):
+    """Measures the given workloads in one process (one per GPU under torchrun); returns
+    the list of result dicts on rank 0."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = [run_b200_one(args, w) for w in workloads]
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def run_b200_one(args, workload):
     import torch
     import torch.distributed as dist
     import helpers as h
@@ -291,10 +309,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    kind, W, H, focal = WORKLOADS[args.workload]
+    kind, W, H, focal = WORKLOADS[workload]
     peaks, peaks_src = measured_peaks()
     r = b200.Renderer(local)
     # one non-default stream carries the kernels, the NCCL gathers and the timing events
@@ -355,7 +370,7 @@ def run_b200(args):
     result = {}
     pinned = torch.empty(rows * W, dtype=torch.int32).pin_memory()
     if kind == "rt":
-        tris, sph = b200.scene_cornell_rt_tessellated(60) if args.workload == "rt_tess100k_4k" else b200.scene_cornell_rt()
+        tris, sph = b200.scene_cornell_rt_tessellated(60) if workload == "rt_tess100k_4k" else b200.scene_cornell_rt()
         cam = b200.make_camera(RT_CAM, focal, h.identity_R(), W, H)
         r.rt_upload_scene(tris, sph)
 
@@ -374,7 +389,7 @@ def run_b200(args):
         h2d = tris.nbytes + sph.nbytes
         d2h = rows * W * 4
     else:
-        room, boxes = rast_scene(b200, args.workload)
+        room, boxes = rast_scene(b200, workload)
         cam = b200.make_camera(RAST_CAM, focal, h.identity_R(), W, H)
         L = b200.make_rast_light(RAST_LIGHT["pos"], RAST_LIGHT["power"], RAST_LIGHT["indirect"])
         r.rast_upload_scene(room, boxes)
@@ -445,7 +460,7 @@ def run_b200(args):
                     "peak_source": "FFMA microbenchmark run in this process (b200_measure_fp32_peak)",
                     "algorithmic_work": f"{FLOP_PER_RT_TEST:.0f} flop per ray-primitive test x {tests:.0f} tests",
                     "exact_evals": st["exact_evals"]}
-        config = {"workload": args.workload, "width": W, "height": H, "focal": focal, "spp": 9,
+        config = {"workload": workload, "width": W, "height": H, "focal": focal, "spp": 9,
                   "triangles": int(len(tris)), "spheres": int(len(sph)), "lights": len(RT_LIGHTS),
                   "rays_per_frame": rays, "parallelism": f"row bands x{world}", "gather": gather, "gather_note": gather_note,
                   "l2": "flushed between timed steps (256 MiB write); outputs 133 MB > L2"}
@@ -460,14 +475,14 @@ def run_b200(args):
                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "whole raster frame (all kernels)",
                     "kernel_ms": float(kernel_ms), "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})",
                     "algorithmic_work": f"{bytes_alg / 1e6:.1f} MB per frame (16 B/pixel + 84 B/triangle)"}
-        config = {"workload": args.workload, "width": W, "height": H, "focal": focal, "triangles_in": int(n_in),
+        config = {"workload": workload, "width": W, "height": H, "focal": focal, "triangles_in": int(n_in),
                   "fragments_per_frame": float(units[1]), "parallelism": f"row bands x{world}", "gather": gather, "gather_note": gather_note,
                   "l2": "flushed between timed steps (256 MiB write)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r.set_stream(None)
-        cpu = cpu_baseline_rt(b200, r, args.workload, W, H, focal, tris, sph) if kind == "rt" else cpu_baseline_rast(args.workload)
+        cpu = cpu_baseline_rt(b200, r, workload, W, H, focal, tris, sph) if kind == "rt" else cpu_baseline_rast(workload)
 
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
@@ -478,9 +493,8 @@ def run_b200(args):
                         "call": "draw_raytrace_band" if kind == "rt" else "draw_raster_band"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         result = line
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    r.set_stream(None)
+    r.close()
     return result
 
 
@@ -495,17 +509,21 @@ def main():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: peer stores into rank 0's frame (default) or an NCCL gather")
     args = ap.parse_args()
-    both = args.workload == "default"
-    if both:
-        args.workload = "rt_cornell_4k"
+    # default: the headline raytracer line (BASELINE config 3) carrying the rasteriser figure
+    # (BASELINE config 4) as a nested "raster" object
+    workloads = ["rt_cornell_4k", "rast_soup_4k"] if args.workload == "default" else [args.workload]
     if args.impl == "reference":
-        run_reference(args)
+        lines = [run_reference(args, w) for w in workloads]
+    else:
+        lines = run_b200(args, workloads)
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    line = run_b200(args)
-    if both and line is not None and "RAST_IN_DEFAULT" in os.environ:
-        pass
-    if int(os.environ.get("RANK", "0")) == 0:
-        print(json.dumps(line), flush=True)
+    line = lines[0]
+    if len(lines) > 1 and lines[1]:
+        keep = ("metric", "value", "unit", "ms_per_step", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline",
+                "steps", "warmup")
+        line["raster"] = {k: lines[1][k] for k in keep if k in lines[1]}
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
