@@ -385,14 +385,9 @@ int rast_upload_scene(b200_ctx *ctx, const rast_triangle *room, int n_room, cons
     return ctx_fail(ctx, B200_EINVAL, "bad scene arguments");
   if ((long long)n_room + 7ll * n_boxes > 0x3fffffffll) return ctx_fail(ctx, B200_EINVAL, "scene too large");
   cudaSetDevice(ctx->device);
-  int has_shadow = n_boxes > 0;   // createShadowVolume wraps every box triangle (:215)
-  for (int i = 0; i < n_room; ++i) {
-    if (room[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
-    has_shadow |= !(room[i].color[0] >= 0);
-  }
-  ctx->rast_has_shadow = has_shadow;
-  for (int i = 0; i < n_boxes; ++i)
-    if (boxes[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+  // texture != 0 and shadow-coloured input triangles are detected by the geometry
+  // kernel on the device (no host pass over the triangles)
+  ctx->rast_has_shadow = n_boxes > 0;   // createShadowVolume wraps every box triangle (:215)
   const size_t n = (size_t)n_room + (size_t)n_boxes;
   if (int rc = ensure(ctx, ctx->rast_world, sizeof(rast_triangle) * (n ? n : 1))) return rc;
   rast_triangle *d = (rast_triangle *)ctx->rast_world.p;

@@ -30,6 +30,7 @@ struct GeomParams {
   unsigned *offs;       // [n_pre + 1] exclusive scan, total at [n_pre]
   rast_triangle *out;
   unsigned out_cap;
+  unsigned long long *flags;   // bit0: a triangle with texture != 0, bit1: a shadow-coloured input triangle
 };
 
 struct GV { float x, y, z, w; };
@@ -232,7 +233,11 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
   cur[0] = t;
   if (!all_in) n_cur = clip_six_planes(p.W, p.H, p.focal, cur);
   if (!WRITE) {
-    if (j < n_pre) p.counts[j] = (unsigned)n_cur;
+    if (j < n_pre) {
+      p.counts[j] = (unsigned)n_cur;
+      if (__float_as_int(attr[7]) != 0) atomicOr(p.flags, 1ull);
+      if (s == 0 && !(attr[4] >= 0.0f)) atomicOr(p.flags, 2ull);
+    }
     return;
   }
   // Common case: the whole block is unclipped (one output each, contiguous in the
@@ -384,6 +389,7 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
   p.n_boxes = n_boxes;
   const int n_scan_blocks = (n_pre + SCAN_BLOCK - 1) / SCAN_BLOCK;
   if (int rc = ensure(ctx, ctx->rast_geom_tmp, sizeof(unsigned) * (2 * (size_t)(n_pre + 1) + n_scan_blocks + 2))) return rc;
+  p.flags = (unsigned long long *)ctx->counters.p + 7;
   p.counts = (unsigned *)ctx->rast_geom_tmp.p;
   p.offs = p.counts + (n_pre + 1);
   unsigned total = 0;
@@ -392,8 +398,12 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
     ctx->stats.kernel_launches++;
     CU_CHECK(ctx, cudaGetLastError());
     if (int rc = scan_exclusive(ctx, p.counts, p.offs, n_pre, p.offs + (n_pre + 1))) return rc;
+    unsigned long long flags = 0;
     CU_CHECK(ctx, cudaMemcpyAsync(&total, p.offs + n_pre, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(&flags, p.flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flags & 1ull) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+    ctx->rast_has_shadow = (n_boxes > 0 || (flags & 2ull)) ? 1 : 0;
   }
   if (int rc = ensure(ctx, ctx->rast_src, sizeof(rast_triangle) * (size_t)(total ? total : 1))) return rc;
   p.out = (rast_triangle *)ctx->rast_src.p;
