@@ -24,7 +24,7 @@
 //                      tile counts
 //   rast_rows_kernel   per (triangle,row): left/right span ends + steps
 //   rast_scan_kernel   exclusive scan of tile counts
-//   rast_bin_kernel    per triangle: append to the tiles' lists (atomics)
+//   rast_spread_kernel per triangle fan-out: row chunks, tile counts, tile lists (atomics)
 //   rast_fill_kernel   per tile: sort list, depth/shadow fold, deferred shading
 //   rast_post_kernel   shadow softening + 5-tap AA + "HDR" mean (:283-307)
 #include "common.cuh"
@@ -99,6 +99,24 @@ __device__ __forceinline__ bool rast_vertex(const float *v, float focal, int W, 
   o.px = v[0];
   o.py = v[1];
   return true;
+}
+
+// Every lane brings a range of `n` work items described by four ints; ranges of up to
+// 32 items are walked by their own lane, longer ones (a triangle covering thousands
+// of tiles or rows) are spread over the whole warp.  All 32 lanes must call this.
+template <typename F>
+__device__ __forceinline__ void warp_spread(int n, int a, int b, int c, int d, F body) {
+  const int lane = threadIdx.x & 31;
+  if (n <= 32) for (int k = 0; k < n; ++k) body(k, a, b, c, d);
+  unsigned big = __ballot_sync(0xffffffffu, n > 32);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const int ns = __shfl_sync(0xffffffffu, n, src);
+    const int as = __shfl_sync(0xffffffffu, a, src), bs = __shfl_sync(0xffffffffu, b, src);
+    const int cs = __shfl_sync(0xffffffffu, c, src), ds = __shfl_sync(0xffffffffu, d, src);
+    for (int k = lane; k < ns; k += 32) body(k, as, bs, cs, ds);
+  }
 }
 
 constexpr int SETUP_THREADS = 256;
@@ -194,15 +212,6 @@ __global__ void __launch_bounds__(SETUP_THREADS) rast_setup_kernel(const __grid_
     uint32_t *dst = reinterpret_cast<uint32_t *>(p.setup + t0);
     for (int i = threadIdx.x; i < n_here * SETUP_WORDS; i += SETUP_THREADS)
       dst[i] = stage[(i / SETUP_WORDS) * (SETUP_WORDS + 1) + i % SETUP_WORDS];
-  }
-  if (t >= p.n_tris) return;
-  for (unsigned c = 0; c < nch; ++c) p.chunk_owner[s.chunk_off + c] = t;
-  if (nrows > 0 && !p.fast) {
-    const int ts = p.ts_log2;
-    const int tx0 = max(0, xmin) >> ts, tx1 = min(p.W - 1, xmax - 1) >> ts;
-    const int tya = s.row0 >> ts, tyb = (s.row0 + nrows - 1) >> ts;
-    for (int ty = tya; ty <= tyb; ++ty)
-      for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(p.tile_count + (size_t)(ty - p.ty0) * p.tiles_x + tx, 1u);
   }
 }
 
@@ -363,26 +372,54 @@ __global__ void rast_scan_kernel(const __grid_constant__ RastParams p, int n_til
   if (threadIdx.x == 0) { p.tile_off[n_tiles] = carry; p.counters[3] = carry; }
 }
 
-// 8 lanes per triangle, lanes stride the overlapped tiles.
-__global__ void rast_bin_kernel(const __grid_constant__ RastParams p) {
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = gid >> 3, sub = gid & 7;
-  if (t >= p.n_tris) return;
-  const RastSetup &s = p.setup[t];
-  if (s.nrows <= 0) return;
-  const int ts = p.ts_log2;
-  const int xmin = min(s.v[0].x, min(s.v[1].x, s.v[2].x)) - 1;
-  const int xmax = max(s.v[0].x, max(s.v[1].x, s.v[2].x));
-  const int tx0 = max(0, xmin) >> ts, tx1 = min(p.W - 1, xmax - 1) >> ts;
-  const int tya = s.row0 >> ts, tyb = (s.row0 + s.nrows - 1) >> ts;
-  const int nx = tx1 - tx0 + 1, n = nx * (tyb - tya + 1);
-  for (int k = sub; k < n; k += 8) {
-    const int ty = tya + k / nx, tx = tx0 + k % nx;
-    const size_t tile = (size_t)(ty - p.ty0) * p.tiles_x + tx;
+// Per-triangle fan-out work: WHAT = 0 hands the triangle's row chunks to the per-row
+// kernels (chunk_owner), 1 counts the screen tiles its bounding box touches, 2 appends
+// it to those tiles' lists.  Two launch shapes: one thread per triangle (long lists;
+// outliers are spread over the warp) or one block per triangle (short lists of big
+// triangles, e.g. the Cornell box with its shadow volumes at 4K).
+template <int WHAT>
+__global__ void rast_spread_kernel(const __grid_constant__ RastParams p, int block_per_tri) {
+  const int t = block_per_tri ? (int)blockIdx.x : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  int n = 0, a = 0, b = 1, c = 0;
+  if (t < p.n_tris) {
+    const RastSetup &s = p.setup[t];
+    if (WHAT == 0) {
+      n = (p.fast && (s.flags & 2)) ? 0 : (s.nrows + RAST_CHUNK - 1) >> RAST_CHUNK_LOG2;
+      a = (int)s.chunk_off;
+    } else if (s.nrows > 0) {
+      const int ts = p.ts_log2;
+      const int xmin = min(s.v[0].x, min(s.v[1].x, s.v[2].x)) - 1;
+      const int xmax = max(s.v[0].x, max(s.v[1].x, s.v[2].x));
+      a = max(0, xmin) >> ts;                                   // first tile column
+      b = (min(p.W - 1, xmax - 1) >> ts) - a + 1;               // tile columns
+      c = s.row0 >> ts;                                         // first tile row
+      n = b * (((s.row0 + s.nrows - 1) >> ts) - c + 1);
+    }
+  }
+  auto body = [&](int k, int x0, int w, int y0, int tri) {
+    if (WHAT == 0) { p.chunk_owner[(unsigned)x0 + k] = tri; return; }
+    const size_t tile = (size_t)(y0 + k / w - p.ty0) * p.tiles_x + x0 + k % w;
+    if (WHAT == 1) { atomicAdd(p.tile_count + tile, 1u); return; }
     const unsigned pos = atomicAdd(p.tile_cursor + tile, 1u);
     const unsigned at = p.tile_off[tile] + pos;
-    if (at < p.bin_cap) p.bins[at] = t;
+    if (at < p.bin_cap) p.bins[at] = tri;
+  };
+  if (block_per_tri) {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) body(k, a, b, c, t);
+  } else {
+    warp_spread(n, a, b, c, t, body);
   }
+}
+
+static void rast_spread_launch(b200_ctx *ctx, const RastParams &p, int what) {
+  const int n = p.n_tris;
+  if (n <= 0) return;
+  const int per_block = n <= 8192;
+  const dim3 grid(per_block ? n : (n + 255) / 256);
+  if (what == 0) rast_spread_kernel<0><<<grid, 256, 0, ctx->stream>>>(p, per_block);
+  else if (what == 1) rast_spread_kernel<1><<<grid, 256, 0, ctx->stream>>>(p, per_block);
+  else rast_spread_kernel<2><<<grid, 256, 0, ctx->stream>>>(p, per_block);
+  ctx->stats.kernel_launches++;
 }
 
 // ---- calculateIllumination (:674-688) without the final "+ indirect" -----------------------
@@ -688,6 +725,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     if (n > 0) {
       rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
+      rast_spread_launch(ctx, p, 0);
       CU_CHECK(ctx, cudaGetLastError());
       CU_CHECK(ctx, cudaMemcpyAsync(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
       CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the chunk count sizes the next grid
@@ -743,6 +781,8 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (n > 0) {
     rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
+    rast_spread_launch(ctx, p, 0);
+    rast_spread_launch(ctx, p, 1);
   }
   rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
   ctx->stats.kernel_launches++;
@@ -763,10 +803,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     rast_rows_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
   }
-  if (n > 0 && bin_total > 0) {
-    rast_bin_kernel<<<(int)(((size_t)n * 8 + 255) / 256), 256, 0, ctx->stream>>>(p);
-    ctx->stats.kernel_launches++;
-  }
+  if (n > 0 && bin_total > 0) rast_spread_launch(ctx, p, 2);
   dim3 grid(p.tiles_x, p.tiles_y);
   switch (ts) {
     case 3: rast_fill_kernel<3><<<grid, 64, 0, ctx->stream>>>(p); break;
