@@ -514,3 +514,11 @@ int b200_save_bmp(const char *path, const uint32_t *argb, int width, int height)
 }
 
 }  // extern "C"
+
+// Raw device counters of the last render (diagnostics; not part of the public header).
+extern "C" int b200_debug_counters(b200_ctx *ctx, unsigned long long *out8) {
+  if (!ctx || !out8) return B200_EINVAL;
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_CHECK(ctx, cudaMemcpy(out8, ctx->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return B200_OK;
+}

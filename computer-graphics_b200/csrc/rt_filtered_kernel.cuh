@@ -146,7 +146,10 @@ __device__ __forceinline__ void rt_ring_issue(RtRing &ring, const float4 *src, i
 }
 
 template <bool MULTI>
-__global__ void __launch_bounds__(RT_THREADS, 2) rt_filtered_kernel(const __grid_constant__ RtKParams p) {
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(const __grid_constant__ RtKParams p) {
   extern __shared__ __align__(128) float4 tile_smem[];  // 2 x RT_TILE x 3 float4
   __shared__ __align__(8) uint64_t bars[2];
 
@@ -186,6 +189,12 @@ __global__ void __launch_bounds__(RT_THREADS, 2) rt_filtered_kernel(const __grid
     len[k] = xsqrt(xdot3(dxs[k / 3], dys[k % 3], dz, dxs[k / 3], dys[k % 3], dz));
   }
   unsigned n_exact = 0;
+#ifdef RT_PROFILE_COUNTERS
+  unsigned prof_cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+#define RT_PC(i) (++prof_cnt[i])
+#else
+#define RT_PC(i)
+#endif
 
   // ============================ primary rays ============================
   {
@@ -234,7 +243,9 @@ __global__ void __launch_bounds__(RT_THREADS, 2) rt_filtered_kernel(const __grid
           const float cu = fmaf(q0.x, dir0, fmaf(q0.y, dir1, q0.z));
           const float cv = fmaf(q0.w, dir0, fmaf(q1.x, dir1, q1.y));
           const float cw = fmaf(q1.z, dir0, fmaf(q1.w, dir1, q2.x));
+          RT_PC(0);
           if (fminf(fminf(cu, cv), cw) < -q2.w) continue;
+          RT_PC(1);
           const float E = q2.y, dt_lo = q2.z;
           // ---- L2 / EX: per ray ----
 #pragma unroll
@@ -245,6 +256,7 @@ __global__ void __launch_bounds__(RT_THREADS, 2) rt_filtered_kernel(const __grid
             const float mW = fmaf(q1.z, dx, fmaf(q1.w, dy, q2.x));
             const float m3 = fminf(fminf(mU, mV), mW);
             if (m3 >= -E) {
+              RT_PC(2);
               const float mN = mU + mV + mW;
               // reference distance >= dt_lo*len/(mN+E): cannot beat the current closest
               const bool farther = (mN > E) && (dt_lo * len[k] >= best[k].dist * (mN + E));
@@ -374,7 +386,9 @@ __global__ void __launch_bounds__(RT_THREADS, 2) rt_filtered_kernel(const __grid
             const float hw = fmaf(fabsf(q1.z), ph[0], fmaf(fabsf(q1.w), ph[1], fabsf(q2.x) * ph[2]));
             const float m3 = fminf(fminf(cu + hu, cv + hv), cw + hw);
             const float mN = (cu + cv + cw) + (hu + hv + hw);
+            RT_PC(3);
             if ((m3 < -Eg) || (mN + Eg < q2.z)) continue;
+            RT_PC(4);
           }
           // ---- L2 / EX: per shadow ray ----
 #pragma unroll
@@ -388,7 +402,9 @@ __global__ void __launch_bounds__(RT_THREADS, 2) rt_filtered_kernel(const __grid
             const float mW = fmaf(q1.z, gx, fmaf(q1.w, gy, q2.x * gz));
             const float m3 = fminf(fminf(mU, mV), mW);
             const float mN = mU + mV + mW;
+            RT_PC(5);
             if (m3 < -Eg || mN + Eg < q2.z) continue;          // definite miss / behind the start
+            RT_PC(6);
             if (m3 >= Eg && mN - Eg >= q2.w && q2.z >= 1e-4f * mN) {
               occluded |= 1u << k;                              // definite occluder
               continue;
@@ -443,6 +459,9 @@ __global__ void __launch_bounds__(RT_THREADS, 2) rt_filtered_kernel(const __grid
   }
   rt_count(p.counters + 0, (unsigned long long)__popc(active) * p.n_lights);
   rt_count(p.counters + 1, (unsigned long long)n_exact);
+#ifdef RT_PROFILE_COUNTERS
+  if (live) for (int i = 0; i < 6; ++i) atomicAdd(p.counters + 2 + i, (unsigned long long)prof_cnt[i + (i >= 2 ? 1 : 0)]);
+#endif
 }
 
 int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p);
