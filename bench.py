@@ -55,6 +55,17 @@ RAST_CAM = (0.0, 0.0, -3.001, 1.0)
 RAST_LIGHT = dict(pos=(0.0, -0.5, 0.0, 1.0), power=(20.0, 20.0, 20.0), indirect=(0.2, 0.2, 0.2))
 
 
+def captured_traffic(workload):
+    """DRAM bytes per launch of the workload's dominant kernel, from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f).get(workload)
+        return (t["traffic_bytes"], t["kernel"]) if t else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -479,6 +490,7 @@ def run_b200_one(args, workload):
                   "fragments_per_frame": float(units[1]), "parallelism": f"row bands x{world}", "gather": gather, "gather_note": gather_note,
                   "l2": "flushed between timed steps (256 MiB write)"}
 
+    roofline["traffic"], roofline["traffic_kernel"] = captured_traffic(workload)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r.set_stream(None)

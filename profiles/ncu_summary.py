@@ -1,0 +1,65 @@
+"""Reads .ncu-rep files (ncu -i ... --page raw --csv) and prints the per-kernel
+figures quoted in DESIGN.md / bench.py; also summarises launch-list CSVs.
+Usage: python profiles/ncu_summary.py report.ncu-rep [...]   |   launches.csv [...]"""
+import csv
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEYS = OrderedDict([
+    ("gpu__time_duration.sum", "duration"),
+    ("launch__registers_per_thread", "registers/thread"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active % of peak"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads per instruction"),
+    ("sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active", "FMA pipe % of peak"),
+    ("sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active", "ALU pipe % of peak"),
+    ("sm__inst_executed_pipe_fp64.sum.pct_of_peak_sustained_active", "FP64 pipe % of peak"),
+    ("sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active", "XU pipe % of peak"),
+    ("sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active", "LSU pipe % of peak"),
+    ("dram__bytes_read.sum", "DRAM read"),
+    ("dram__bytes_write.sum", "DRAM write"),
+    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+])
+
+
+def report(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        print(f"### {name}  (grid {r[hdr.index('Grid Size')]}, block {r[hdr.index('Block Size')]})")
+        for k, label in KEYS.items():
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"- {label}: {r[i]} {units[i]}  (`{k}`)")
+        print()
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    # the last frame of the run: walk back to the first kernel of the frame
+    frame, seen = [], set()
+    for r in reversed(rows):
+        key = r[4]
+        if key in seen and key.startswith(("rast_resolve", "rast_post", "void rt_filtered")):
+            break
+        seen.add(key)
+        frame.append(r)
+    frame.reverse()
+    total = sum(float(r[-1]) for r in frame)
+    print(f"### {path}: last frame, {len(frame)} launches, {total / 1e3:.1f} us in kernels")
+    print("| kernel | grid | block | us | share |")
+    print("|---|---|---|---|---|")
+    for r in frame:
+        print(f"| `{r[4][:60]}` | {r[8]} | {r[7]} | {float(r[-1]) / 1e3:.1f} | {100 * float(r[-1]) / total:.1f}% |")
+    print()
+
+
+for p in sys.argv[1:]:
+    (report if p.endswith(".ncu-rep") else launches)(p)
