@@ -57,7 +57,10 @@ int b200_init(int device, b200_ctx **out) {
     return B200_ECUDA;
   }
   ctx->stream = ctx->own_stream;
-  if (ensure(ctx, ctx->counters, 8 * sizeof(unsigned long long)) != B200_OK) { delete ctx; return B200_ENOMEM; }
+  if (ensure(ctx, ctx->counters, 16 * sizeof(unsigned long long)) != B200_OK || ensure_pinned(ctx, 256) != B200_OK) {
+    delete ctx;
+    return B200_ENOMEM;
+  }
   *out = ctx;
   return B200_OK;
 }
@@ -184,7 +187,7 @@ int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, 
   if (int rc = fill_frame(ctx, cam, lights, n_lights, row_begin, row_end, f)) return rc;
   cudaSetDevice(ctx->device);
   ctx->stats.kernel_launches = 0;
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (int rc = rt_launch(ctx, f, d_rgb, d_depth, d_index, d_argb)) return rc;
   CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -197,7 +200,7 @@ int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, 
 static int finish_stats(b200_ctx *ctx) {
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   if (!ctx->pending) return B200_OK;
-  unsigned long long c[8];
+  unsigned long long c[16];
   CU_CHECK(ctx, cudaMemcpy(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
@@ -341,7 +344,7 @@ int rast_render_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *l
   if (row_begin < 0 || row_end > cam->height || row_begin > row_end) return ctx_fail(ctx, B200_EINVAL, "bad row band");
   cudaSetDevice(ctx->device);
   ctx->stats.kernel_launches = 0;
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (int rc = rast_launch(ctx, cam, light, row_begin, row_end, d_rgb, d_depth, d_index, d_argb)) return rc;
   CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -406,7 +409,7 @@ int rast_draw_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *lig
   if (row_begin < 0 || row_end > cam->height || row_begin > row_end) return ctx_fail(ctx, B200_EINVAL, "bad row band");
   cudaSetDevice(ctx->device);
   ctx->stats.kernel_launches = 0;
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   rast_light_t lc;
   if (int rc = rast_geometry(ctx, cam, light, &lc)) return rc;
@@ -519,6 +522,6 @@ int b200_save_bmp(const char *path, const uint32_t *argb, int width, int height)
 extern "C" int b200_debug_counters(b200_ctx *ctx, unsigned long long *out8) {
   if (!ctx || !out8) return B200_EINVAL;
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  CU_CHECK(ctx, cudaMemcpy(out8, ctx->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CU_CHECK(ctx, cudaMemcpy(out8, ctx->counters.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return B200_OK;
 }

@@ -31,7 +31,7 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned chunk = gid >> RAST_CHUNK_LOG2, sub = gid & (RAST_CHUNK - 1);
   unsigned long long n_frag = 0;
-  if (chunk < p.n_chunks) {
+  if (chunk < rast_count_chunks(p)) {
     const int t = p.chunk_owner[chunk];
     const RastSetup &s = p.setup[t];
     const int r = (int)((chunk - s.chunk_off) << RAST_CHUNK_LOG2) + (int)sub;

@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(unsigned *__res
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const unsigned *__restrict__ counts, int n,
                                                                   const unsigned *__restrict__ block_sums, int nb,
-                                                                  unsigned *__restrict__ offs) {
+                                                                  unsigned *__restrict__ offs,
+                                                                  unsigned long long *__restrict__ total_out) {
   const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
   unsigned v[SCAN_ITEMS], s = 0;
 #pragma unroll
@@ -348,15 +349,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const unsigned
     if (base + k < n) offs[base + k] = run;
     run += v[k];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) offs[n] = block_sums[nb];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    offs[n] = block_sums[nb];
+    if (total_out) *total_out = block_sums[nb];
+  }
 }
 
 // offs[0..n] = exclusive scan of counts[0..n); tmp holds nb + 1 block sums.
-int scan_exclusive(b200_ctx *ctx, const unsigned *counts, unsigned *offs, int n, unsigned *tmp) {
+int scan_exclusive(b200_ctx *ctx, const unsigned *counts, unsigned *offs, int n, unsigned *tmp,
+                   unsigned long long *total_out) {
   const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
   scan_reduce_kernel<<<nb, SCAN_THREADS, 0, ctx->stream>>>(counts, n, tmp);
   scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(tmp, nb);
-  scan_apply_kernel<<<nb, SCAN_THREADS, 0, ctx->stream>>>(counts, n, tmp, nb, offs);
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, ctx->stream>>>(counts, n, tmp, nb, offs, total_out);
   ctx->stats.kernel_launches += 3;
   CU_CHECK(ctx, cudaGetLastError());
   return B200_OK;
@@ -397,11 +402,14 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
     rast_geom_kernel<false><<<(n_pre + 127) / 128, 128, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     CU_CHECK(ctx, cudaGetLastError());
-    if (int rc = scan_exclusive(ctx, p.counts, p.offs, n_pre, p.offs + (n_pre + 1))) return rc;
-    unsigned long long flags = 0;
-    CU_CHECK(ctx, cudaMemcpyAsync(&total, p.offs + n_pre, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_CHECK(ctx, cudaMemcpyAsync(&flags, p.flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long *dc = (unsigned long long *)ctx->counters.p;
+    if (int rc = scan_exclusive(ctx, p.counts, p.offs, n_pre, p.offs + (n_pre + 1), dc + 8)) return rc;
+    // one small read-back into pinned memory: [7] validation flags, [8] clipped-list length
+    unsigned long long *hc = (unsigned long long *)ctx->pinned;
+    CU_CHECK(ctx, cudaMemcpyAsync(hc, dc, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned long long flags = hc[7];
+    total = (unsigned)hc[8];
     if (flags & 1ull) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
     ctx->rast_has_shadow = (n_boxes > 0 || (flags & 2ull)) ? 1 : 0;
   }

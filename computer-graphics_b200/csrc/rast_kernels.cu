@@ -74,6 +74,9 @@ struct RastParams {
   unsigned long long *keys;   // fast path: per-pixel (zinv bits, triangle + 1)
   int *chunk_owner;  // triangle owning each RAST_CHUNK-row chunk
   unsigned chunk_cap, n_chunks;
+  // pipelined mode: the list length / chunk count are not known on the host yet; n_tris and
+  // n_chunks above are then launch bounds and the kernels clamp to these device values
+  const unsigned long long *n_tris_dev, *n_chunks_dev;
   unsigned *tile_count, *tile_off, *tile_cursor;
   int *bins, *bins_tmp;
   unsigned bin_cap;
@@ -85,6 +88,13 @@ struct RastParams {
   uint32_t *out_argb;
   unsigned long long *counters;  // [2] fragments, [3] bin entries, [4] rows, [5] overflow flag, [6] row chunks
 };
+
+__device__ __forceinline__ int rast_count_tris(const RastParams &p) {
+  return p.n_tris_dev ? (int)min((unsigned long long)p.n_tris, *p.n_tris_dev) : p.n_tris;
+}
+__device__ __forceinline__ unsigned rast_count_chunks(const RastParams &p) {
+  return p.n_chunks_dev ? (unsigned)min((unsigned long long)p.n_chunks, *p.n_chunks_dev) : p.n_chunks;
+}
 
 // ---- VertexShader (:510-522) ---------------------------------------------------------
 __device__ __forceinline__ bool rast_vertex(const float *v, float focal, int W, int H, RastVtx &o) {
@@ -129,7 +139,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) rast_setup_kernel(const __grid_
   const int t0 = blockIdx.x * SETUP_THREADS;
   const int t = t0 + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const int n_here = min(SETUP_THREADS, p.n_tris - t0);
+  const int n_tris = rast_count_tris(p);
+  const int n_here = max(0, min(SETUP_THREADS, n_tris - t0));
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.src + t0);
     for (int i = threadIdx.x; i < n_here * TRI_WORDS; i += SETUP_THREADS) stage[i] = __ldg(src + i);
@@ -139,7 +150,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) rast_setup_kernel(const __grid_
   RastSetup s;
   s.flags = 0; s.ymin = 0; s.row0 = 0; s.nrows = 0; s.row_off = 0; s.chunk_off = 0;
   int xmin = 0, xmax = -1;
-  if (t < p.n_tris) {
+  if (t < n_tris) {
     const float *tr = reinterpret_cast<const float *>(stage) + threadIdx.x * TRI_WORDS;   // v0[4] v1[4] v2[4] normal[4] color[3]
     float v[3][3];
 #pragma unroll
@@ -197,12 +208,12 @@ __global__ void __launch_bounds__(SETUP_THREADS) rast_setup_kernel(const __grid_
   cbase = __shfl_sync(0xffffffffu, cbase, 31);
   s.row_off = base + incl - (unsigned)nrows;
   s.chunk_off = cbase + cincl - nch;
-  if (t < p.n_tris && (s.row_off + (unsigned)nrows > p.row_cap || s.chunk_off + nch > p.chunk_cap)) {
+  if (t < n_tris && (s.row_off + (unsigned)nrows > p.row_cap || s.chunk_off + nch > p.chunk_cap)) {
     s.nrows = 0; nrows = 0; nch = 0;
     atomicExch(p.counters + 5, 1ull);
   }
   __syncthreads();   // every thread has read its triangle: the buffer now carries the records out
-  if (t < p.n_tris) {
+  if (t < n_tris) {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(&s);
 #pragma unroll
     for (int k = 0; k < SETUP_WORDS; ++k) stage[threadIdx.x * (SETUP_WORDS + 1) + k] = w[k];
@@ -325,7 +336,7 @@ __device__ __forceinline__ void rast_row_record(const RastSetup &s, int Y, float
 __global__ void rast_rows_kernel(const __grid_constant__ RastParams p) {
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned chunk = gid >> RAST_CHUNK_LOG2, sub = gid & (RAST_CHUNK - 1);
-  if (chunk >= p.n_chunks) return;
+  if (chunk >= rast_count_chunks(p)) return;
   const int t = p.chunk_owner[chunk];
   const RastSetup &s = p.setup[t];
   const int r = (int)((chunk - s.chunk_off) << RAST_CHUNK_LOG2) + (int)sub;
@@ -381,7 +392,7 @@ template <int WHAT>
 __global__ void rast_spread_kernel(const __grid_constant__ RastParams p, int block_per_tri) {
   const int t = block_per_tri ? (int)blockIdx.x : (int)(blockIdx.x * blockDim.x + threadIdx.x);
   int n = 0, a = 0, b = 1, c = 0;
-  if (t < p.n_tris) {
+  if (t < rast_count_tris(p)) {
     const RastSetup &s = p.setup[t];
     if (WHAT == 0) {
       n = (p.fast && (s.flags & 2)) ? 0 : (s.nrows + RAST_CHUNK - 1) >> RAST_CHUNK_LOG2;
@@ -727,8 +738,9 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
       ctx->stats.kernel_launches++;
       rast_spread_launch(ctx, p, 0);
       CU_CHECK(ctx, cudaGetLastError());
-      CU_CHECK(ctx, cudaMemcpyAsync(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+      CU_CHECK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
       CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the chunk count sizes the next grid
+      memcpy(c, ctx->pinned, sizeof c);
       if (c[5]) return ctx_fail(ctx, B200_ENOMEM, "row chunk budget exceeded");
     }
     p.n_chunks = (unsigned)c[6];
@@ -789,8 +801,9 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   CU_CHECK(ctx, cudaGetLastError());
   // the bin array is sized from the scanned total: read it back (tiny, one sync)
   unsigned long long c[8];
-  CU_CHECK(ctx, cudaMemcpyAsync(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(c, ctx->pinned, sizeof c);
   if (c[5]) return ctx_fail(ctx, B200_ENOMEM, "row table budget exceeded (triangles too tall for this band)");
   const size_t bin_total = (size_t)c[3];
   if (int rc = ensure(ctx, ctx->rast_bins, sizeof(int) * (bin_total ? bin_total : 1))) return rc;
