@@ -404,9 +404,15 @@ def run_b200_one(args, workload):
         cam = b200.make_camera(RAST_CAM, focal, h.identity_R(), W, H)
         L = b200.make_rast_light(RAST_LIGHT["pos"], RAST_LIGHT["power"], RAST_LIGHT["indirect"])
         r.rast_upload_scene(room, boxes)
+        # frames sized from the last verified frame instead of mid-frame read-backs; the
+        # verification (b200_synchronize) is part of the step, so a frame that had to be
+        # rendered twice would be timed twice
+        r.set_option(b200.OPT_RAST_PIPELINED, 0 if args.rast_sync else 1)
+        respec0 = r.stats()["respeculated"]
 
         def step():
             r.rast_draw_device(cam, L, row0, row1, p_rgb, p_depth)
+            r.synchronize()
             exchange()
 
         room_pin = torch.from_numpy(room.view(np.uint8).copy()).pin_memory()
@@ -488,6 +494,7 @@ def run_b200_one(args, workload):
                     "algorithmic_work": f"{bytes_alg / 1e6:.1f} MB per frame (16 B/pixel + 84 B/triangle)"}
         config = {"workload": workload, "width": W, "height": H, "focal": focal, "triangles_in": int(n_in),
                   "fragments_per_frame": float(units[1]), "parallelism": f"row bands x{world}", "gather": gather, "gather_note": gather_note,
+                  "pipelined": not args.rast_sync, "frames_rendered_twice": int(r.stats()["respeculated"] - respec0),
                   "l2": "flushed between timed steps (256 MiB write)"}
 
     roofline["traffic"], roofline["traffic_kernel"] = captured_traffic(workload)
@@ -518,6 +525,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="default", choices=["default"] + sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rast-sync", action="store_true",
+                    help="rasteriser: read list/table sizes back mid-frame instead of pipelined frames")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: peer stores into rank 0's frame (default) or an NCCL gather")
     args = ap.parse_args()

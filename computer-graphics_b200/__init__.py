@@ -24,6 +24,7 @@ INDEX_MISS = -2147483648
 OPT_RT_BRUTEFORCE = 1
 OPT_RAST_TILE_LOG2 = 2
 OPT_RAST_PATH = 3
+OPT_RAST_PIPELINED = 4
 
 RT_TRI = np.dtype([("v0", "<f4", 4), ("v1", "<f4", 4), ("v2", "<f4", 4),
                    ("normal", "<f4", 4), ("color", "<f4", 3)])
@@ -52,7 +53,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("primary_rays", ctypes.c_uint64), ("shadow_rays", ctypes.c_uint64),
                 ("prim_tests", ctypes.c_uint64), ("exact_evals", ctypes.c_uint64),
                 ("kernel_launches", ctypes.c_uint64), ("fragments", ctypes.c_uint64),
-                ("bin_entries", ctypes.c_uint64), ("gpu_ms", ctypes.c_float)]
+                ("bin_entries", ctypes.c_uint64), ("respeculated", ctypes.c_uint64),
+                ("gpu_ms", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

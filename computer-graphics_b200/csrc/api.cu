@@ -85,15 +85,18 @@ void b200_destroy(b200_ctx *ctx) {
 const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void *b200_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
+static int finish_stats(b200_ctx *ctx);
+
+// Also the point where a pipelined raster frame is verified (and re-rendered if its
+// size guess was too small), so what is on the device afterwards is always exact.
 int b200_synchronize(b200_ctx *ctx) {
   if (!ctx) return B200_EINVAL;
-  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  return B200_OK;
+  return finish_stats(ctx);
 }
 
 int b200_set_stream(b200_ctx *ctx, void *cuda_stream) {
   if (!ctx) return B200_EINVAL;
-  cudaStreamSynchronize(ctx->stream);
+  if (int rc = finish_stats(ctx)) return rc;
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return B200_OK;
 }
@@ -106,6 +109,10 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
       if (value < 0 || value > 2) return ctx_fail(ctx, B200_EINVAL, "raster path must be 0, 1 or 2");
       ctx->opt_rast_path = value;
       return B200_OK;
+    case B200_OPT_RAST_PIPELINED:
+      ctx->opt_rast_pipelined = value != 0;
+      ctx->rast_spec.valid = 0;
+      return B200_OK;
     case B200_OPT_RAST_TILE_LOG2:
       if (value < 3 || value > 6) return ctx_fail(ctx, B200_EINVAL, "tile log2 must be 3..6");
       ctx->opt_rast_tile_log2 = value;
@@ -114,12 +121,17 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
   return ctx_fail(ctx, B200_EINVAL, "unknown option");
 }
 
-static int finish_stats(b200_ctx *ctx);
-
 int b200_get_stats(b200_ctx *ctx, b200_stats *out) {
   if (!ctx || !out) return B200_EINVAL;
   if (int rc = finish_stats(ctx)) return rc;
   *out = ctx->stats;
+  return B200_OK;
+}
+
+// Every render ends by copying its counters into the second half of the pinned scratch.
+static int enqueue_counter_readback(b200_ctx *ctx) {
+  CU_CHECK(ctx, cudaMemcpyAsync((unsigned long long *)ctx->pinned + 16, ctx->counters.p, 16 * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, ctx->stream));
   return B200_OK;
 }
 
@@ -186,22 +198,48 @@ int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, 
   RtFrame f;
   if (int rc = fill_frame(ctx, cam, lights, n_lights, row_begin, row_end, f)) return rc;
   cudaSetDevice(ctx->device);
+  if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // the counters are shared
   ctx->stats.kernel_launches = 0;
   CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (int rc = rt_launch(ctx, f, d_rgb, d_depth, d_index, d_argb)) return rc;
   CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->stats.primary_rays = (uint64_t)f.W * (uint64_t)(row_end - row_begin) * 9u;
+  if (int rc = enqueue_counter_readback(ctx)) return rc;
   ctx->pending = 1;
   return B200_OK;
 }
 
-// Waits for the last render and reads its device counters back.
+static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const rast_light_t *light, int row_begin,
+                      int row_end, float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb, bool allow_spec);
+
+// Waits for the last render and reads its device counters back.  A pipelined raster
+// frame is checked here against the sizes it was launched with.
 static int finish_stats(b200_ctx *ctx) {
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   if (!ctx->pending) return B200_OK;
-  unsigned long long c[16];
-  CU_CHECK(ctx, cudaMemcpy(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost));
+  const unsigned long long *c = (const unsigned long long *)ctx->pinned + 16;
+  if (ctx->pending == 2 && ctx->rast_inflight.active) {
+    b200_ctx::RastInflight &f = ctx->rast_inflight;
+    f.active = 0;
+    bool ok = c[5] == 0 && (f.fast || c[3] <= f.cap_bins);
+    if (f.whole_draw) {
+      const int has_shadow = (ctx->rast_n_boxes > 0 || (c[7] & 2ull)) ? 1 : 0;
+      ok = ok && c[8] <= f.cap_tris && !(c[7] & 1ull) && has_shadow == ctx->rast_has_shadow;
+    }
+    if (!ok) {
+      // the frame outgrew the guess: render it again with exact sizes
+      ctx->rast_spec.valid = 0;
+      ctx->pending = 0;
+      ctx->stats.respeculated++;
+      if (int rc = rast_frame(ctx, f.whole_draw != 0, &f.cam, &f.light, f.row0, f.row1, f.rgb, f.depth, f.index,
+                              f.argb, false))
+        return rc;
+      CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    } else if (f.whole_draw) {
+      ctx->rast_n_tris = (int)c[8];
+    }
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->stats.gpu_ms = ms;
@@ -213,6 +251,12 @@ static int finish_stats(b200_ctx *ctx) {
   } else {
     ctx->stats.fragments = c[2];
     ctx->stats.bin_entries = c[3];
+    // what this frame needed sizes the next pipelined frame of the same shape
+    b200_ctx::RastSpec &sp = ctx->rast_spec;
+    sp.tris = (unsigned long long)ctx->rast_n_tris;
+    sp.chunks = c[6]; sp.rows = c[4]; sp.bins = c[3];
+    sp.has_shadow = ctx->rast_has_shadow;
+    sp.valid = 1;
   }
   ctx->pending = 0;
   return B200_OK;
@@ -323,6 +367,7 @@ int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris)
   if (!ctx) return B200_EINVAL;
   if (n_tris < 0 || (n_tris > 0 && !clipped)) return ctx_fail(ctx, B200_EINVAL, "bad triangle list");
   cudaSetDevice(ctx->device);
+  if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // a re-render must see its own scene
   int has_shadow = 0;
   for (int i = 0; i < n_tris; ++i) {
     if (clipped[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
@@ -336,20 +381,63 @@ int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris)
   return B200_OK;
 }
 
-int rast_render_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin,
-                       int row_end, float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
-  if (!ctx) return B200_EINVAL;
+// One raster frame: the triangle loop on the uploaded clipped list, or (whole_draw) the
+// geometry stage first.  With allow_spec and a verified frame of the same shape behind
+// it, the frame is enqueued without any host synchronisation (see common.cuh).
+static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const rast_light_t *light, int row_begin,
+                      int row_end, float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb, bool allow_spec) {
+  if (ctx->pending == 2) if (int rc = finish_stats(ctx)) return rc;   // settles a pipelined frame still in flight
+  b200_ctx::RastSpec &sp = ctx->rast_spec;
+  const int n_list = whole_draw ? -1 : ctx->rast_n_tris;
+  const bool same = sp.valid && sp.whole_draw == (whole_draw ? 1 : 0) && sp.W == cam->width && sp.H == cam->height &&
+                    sp.row0 == row_begin && sp.row1 == row_end && sp.ts == ctx->opt_rast_tile_log2 &&
+                    sp.fast == ctx->opt_rast_path && sp.n_list == n_list &&
+                    (!whole_draw || (sp.n_room == ctx->rast_n_room && sp.n_boxes == ctx->rast_n_boxes));
+  const bool spec = allow_spec && same;
+  sp.valid = 0;
+  sp.whole_draw = whole_draw ? 1 : 0; sp.W = cam->width; sp.H = cam->height; sp.row0 = row_begin; sp.row1 = row_end;
+  sp.ts = ctx->opt_rast_tile_log2; sp.fast = ctx->opt_rast_path; sp.n_list = n_list;
+  sp.n_room = ctx->rast_n_room; sp.n_boxes = ctx->rast_n_boxes;
+  b200_ctx::RastInflight &f = ctx->rast_inflight;
+  f.active = 0;
+  if (spec) {
+    if (whole_draw) ctx->rast_has_shadow = sp.has_shadow;   // checked against this frame's own flags later
+    f.whole_draw = whole_draw ? 1 : 0;
+    f.cam = *cam; f.light = *light; f.row0 = row_begin; f.row1 = row_end;
+    f.rgb = d_rgb; f.depth = d_depth; f.index = d_index; f.argb = d_argb;
+    f.cap_tris = 0; f.cap_bins = 0;
+  }
+  ctx->stats.kernel_launches = 0;
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  rast_light_t lc = *light;
+  if (whole_draw) {
+    if (int rc = rast_geometry(ctx, cam, light, &lc, spec)) return rc;
+    if (spec) f.cap_tris = (unsigned long long)ctx->rast_n_tris;
+  }
+  if (int rc = rast_launch(ctx, cam, &lc, row_begin, row_end, d_rgb, d_depth, d_index, d_argb, spec)) return rc;
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  if (int rc = enqueue_counter_readback(ctx)) return rc;
+  f.active = spec ? 1 : 0;
+  ctx->pending = 2;
+  return B200_OK;
+}
+
+static int rast_check_frame_args(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin,
+                                 int row_end) {
   if (int rc = check_camera(ctx, cam)) return rc;
   if (!light) return ctx_fail(ctx, B200_EINVAL, "null light");
   if (row_begin < 0 || row_end > cam->height || row_begin > row_end) return ctx_fail(ctx, B200_EINVAL, "bad row band");
   cudaSetDevice(ctx->device);
-  ctx->stats.kernel_launches = 0;
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
-  CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  if (int rc = rast_launch(ctx, cam, light, row_begin, row_end, d_rgb, d_depth, d_index, d_argb)) return rc;
-  CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->pending = 2;
   return B200_OK;
+}
+
+int rast_render_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin,
+                       int row_end, float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
+  if (!ctx) return B200_EINVAL;
+  if (int rc = rast_check_frame_args(ctx, cam, light, row_begin, row_end)) return rc;
+  return rast_frame(ctx, false, cam, light, row_begin, row_end, d_rgb, d_depth, d_index, d_argb,
+                    ctx->opt_rast_pipelined != 0);
 }
 
 static int raster_host_outputs(b200_ctx *ctx, const camera_t *cam, float *rgb_out, float *depth_out,
@@ -368,10 +456,12 @@ int render_raster_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tri
   if (int rc = check_camera(ctx, cam)) return rc;
   if (int rc = rast_upload_clipped(ctx, clipped, n_tris)) return rc;
   if (int rc = raster_host_outputs(ctx, cam, rgb_out, depth_out, index_out, nullptr)) return rc;
-  if (int rc = rast_render_device(ctx, cam, light, 0, cam->height, rgb_out ? (float *)ctx->out_rgb.p : nullptr,
-                                  depth_out ? (float *)ctx->out_depth.p : nullptr,
-                                  index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr))
+  if (int rc = rast_check_frame_args(ctx, cam, light, 0, cam->height)) return rc;
+  if (int rc = rast_frame(ctx, false, cam, light, 0, cam->height, rgb_out ? (float *)ctx->out_rgb.p : nullptr,
+                          depth_out ? (float *)ctx->out_depth.p : nullptr,
+                          index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr, true))
     return rc;
+  if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // verified before anything leaves
   const size_t npix = (size_t)cam->width * cam->height;
   if (int rc = copy_out(ctx, rgb_out, ctx->out_rgb.p, npix * 3 * sizeof(float))) return rc;
   if (int rc = copy_out(ctx, depth_out, ctx->out_depth.p, npix * sizeof(float))) return rc;
@@ -388,6 +478,7 @@ int rast_upload_scene(b200_ctx *ctx, const rast_triangle *room, int n_room, cons
     return ctx_fail(ctx, B200_EINVAL, "bad scene arguments");
   if ((long long)n_room + 7ll * n_boxes > 0x3fffffffll) return ctx_fail(ctx, B200_EINVAL, "scene too large");
   cudaSetDevice(ctx->device);
+  if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // a re-render must see its own scene
   // texture != 0 and shadow-coloured input triangles are detected by the geometry
   // kernel on the device (no host pass over the triangles)
   ctx->rast_has_shadow = n_boxes > 0;   // createShadowVolume wraps every box triangle (:215)
@@ -404,19 +495,9 @@ int rast_upload_scene(b200_ctx *ctx, const rast_triangle *room, int n_room, cons
 int rast_draw_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin, int row_end,
                      float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
   if (!ctx) return B200_EINVAL;
-  if (int rc = check_camera(ctx, cam)) return rc;
-  if (!light) return ctx_fail(ctx, B200_EINVAL, "null light");
-  if (row_begin < 0 || row_end > cam->height || row_begin > row_end) return ctx_fail(ctx, B200_EINVAL, "bad row band");
-  cudaSetDevice(ctx->device);
-  ctx->stats.kernel_launches = 0;
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
-  CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  rast_light_t lc;
-  if (int rc = rast_geometry(ctx, cam, light, &lc)) return rc;
-  if (int rc = rast_launch(ctx, cam, &lc, row_begin, row_end, d_rgb, d_depth, d_index, d_argb)) return rc;
-  CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->pending = 2;
-  return B200_OK;
+  if (int rc = rast_check_frame_args(ctx, cam, light, row_begin, row_end)) return rc;
+  return rast_frame(ctx, true, cam, light, row_begin, row_end, d_rgb, d_depth, d_index, d_argb,
+                    ctx->opt_rast_pipelined != 0);
 }
 
 int render_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes, int n_boxes,
@@ -426,10 +507,12 @@ int render_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const ra
   if (int rc = check_camera(ctx, cam)) return rc;
   if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
   if (int rc = raster_host_outputs(ctx, cam, rgb_out, depth_out, index_out, nullptr)) return rc;
-  if (int rc = rast_draw_device(ctx, cam, light, 0, cam->height, rgb_out ? (float *)ctx->out_rgb.p : nullptr,
-                                depth_out ? (float *)ctx->out_depth.p : nullptr,
-                                index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr))
+  if (int rc = rast_check_frame_args(ctx, cam, light, 0, cam->height)) return rc;
+  if (int rc = rast_frame(ctx, true, cam, light, 0, cam->height, rgb_out ? (float *)ctx->out_rgb.p : nullptr,
+                          depth_out ? (float *)ctx->out_depth.p : nullptr,
+                          index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr, true))
     return rc;
+  if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;
   const size_t npix = (size_t)cam->width * cam->height;
   if (int rc = copy_out(ctx, rgb_out, ctx->out_rgb.p, npix * 3 * sizeof(float))) return rc;
   if (int rc = copy_out(ctx, depth_out, ctx->out_depth.p, npix * sizeof(float))) return rc;
@@ -445,9 +528,11 @@ int draw_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room, const
   if (int rc = check_camera(ctx, cam)) return rc;
   if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
   if (int rc = raster_host_outputs(ctx, cam, nullptr, nullptr, nullptr, argb_out)) return rc;
-  if (int rc = rast_draw_device(ctx, cam, light, row_begin, row_end, nullptr, nullptr, nullptr,
-                                (uint32_t *)ctx->out_argb.p))
+  if (int rc = rast_check_frame_args(ctx, cam, light, row_begin, row_end)) return rc;
+  if (int rc = rast_frame(ctx, true, cam, light, row_begin, row_end, nullptr, nullptr, nullptr,
+                          (uint32_t *)ctx->out_argb.p, true))
     return rc;
+  if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;
   const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
   if (int rc = copy_out(ctx, argb_out, (uint32_t *)ctx->out_argb.p + off, cnt * sizeof(uint32_t))) return rc;
   return finish_stats(ctx);
@@ -462,7 +547,7 @@ int draw_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast
 
 int raster_read_clipped(b200_ctx *ctx, rast_triangle *out, int cap, int *n_out) {
   if (!ctx || !n_out) return B200_EINVAL;
-  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (int rc = finish_stats(ctx)) return rc;
   *n_out = ctx->rast_n_tris;
   const int n = ctx->rast_n_tris < cap ? ctx->rast_n_tris : cap;
   if (out && n > 0) CU_CHECK(ctx, cudaMemcpy(out, ctx->rast_src.p, sizeof(rast_triangle) * (size_t)n, cudaMemcpyDeviceToHost));
@@ -475,7 +560,7 @@ int raster_read_buffers(b200_ctx *ctx, float *screen_out, float *low_out, float 
     return ctx_fail(ctx, B200_EINVAL, "no intermediate buffers: nothing rendered yet, or the last frame took the "
                                       "scatter path (set B200_OPT_RAST_PATH to 1 to keep them)");
   const size_t npix = (size_t)ctx->rast_w * ctx->rast_h;
-  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (int rc = finish_stats(ctx)) return rc;
   if (screen_out) CU_CHECK(ctx, cudaMemcpy(screen_out, ctx->rast_screen.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost));
   if (low_out) CU_CHECK(ctx, cudaMemcpy(low_out, ctx->rast_low.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost));
   if (high_out) CU_CHECK(ctx, cudaMemcpy(high_out, ctx->rast_high.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost));

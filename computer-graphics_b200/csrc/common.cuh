@@ -102,6 +102,26 @@ struct b200_ctx {
   DevBuf rast_screen, rast_low, rast_high, rast_shadow, rast_depth, rast_index;
   int rast_w = 0, rast_h = 0;
 
+  // Pipelined raster frames (B200_OPT_RAST_PIPELINED): buffer sizes and grids come from
+  // the last verified frame of the same shape instead of two mid-frame read-backs; the
+  // frame's own counters are checked when it is waited for and a frame that outgrew the
+  // guess is re-rendered synchronously before anything is handed out.
+  int opt_rast_pipelined = 0;
+  struct RastSpec {
+    int valid = 0, has_shadow = 0, n_room = 0, n_boxes = 0, n_list = 0, W = 0, H = 0, row0 = 0, row1 = 0, fast = 0, ts = 0, whole_draw = 0;
+    unsigned long long tris = 0, chunks = 0, rows = 0, bins = 0;
+  } rast_spec;
+  struct RastInflight {
+    int active = 0, whole_draw = 0, fast = 0;
+    camera_t cam;
+    rast_light_t light;
+    int row0 = 0, row1 = 0;
+    float *rgb = nullptr, *depth = nullptr;
+    int32_t *index = nullptr;
+    uint32_t *argb = nullptr;
+    unsigned long long cap_tris = 0, cap_bins = 0;
+  } rast_inflight;
+
   // outputs / staging (device) used by the host-pointer entry points
   DevBuf out_rgb, out_depth, out_index, out_argb;
   DevBuf counters;    // unsigned long long[8]
@@ -129,9 +149,12 @@ struct RtFrame {
 };
 #define B200_MAX_LIGHTS 8
 
+// spec = true: pipelined (no host synchronisation; see b200_ctx::rast_spec)
 int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row0, int row1,
-                float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb);
-int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, rast_light_t *light_out);
+                float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb, bool spec);
+int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, rast_light_t *light_out,
+                  bool spec);
+static inline unsigned long long rast_spec_cap(unsigned long long seen) { return seen + seen / 8 + 1024; }
 int rt_prepare_scene(b200_ctx *ctx);
 int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int32_t *d_index,
               uint32_t *d_argb);

@@ -32,10 +32,10 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
   const unsigned chunk = gid >> RAST_CHUNK_LOG2, sub = gid & (RAST_CHUNK - 1);
   unsigned long long n_frag = 0;
   if (chunk < rast_count_chunks(p)) {
-    const int t = p.chunk_owner[chunk];
+    const int t = (int)min((unsigned)p.chunk_owner[chunk], (unsigned)(p.n_tris - 1));   // stale owner after an overflow
     const RastSetup &s = p.setup[t];
     const int r = (int)((chunk - s.chunk_off) << RAST_CHUNK_LOG2) + (int)sub;
-    if (r < s.nrows) {
+    if (r >= 0 && r < s.nrows) {
       const int y = s.row0 + r;
       float4 A, B;
       rast_row_record<true>(s, y, A, B);

@@ -370,7 +370,8 @@ int scan_exclusive(b200_ctx *ctx, const unsigned *counts, unsigned *offs, int n,
 // Host: runs the stage on the uploaded world-space scene; leaves the clipped list
 // in ctx->rast_src / ctx->rast_n_tris and the camera-space rotated light in
 // light_out (what the triangle loop's calculateIllumination reads, :675).
-int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, rast_light_t *light_out) {
+int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, rast_light_t *light_out,
+                  bool spec) {
   const int n_room = ctx->rast_n_room, n_boxes = ctx->rast_n_boxes;
   const int n_pre = n_room + 7 * n_boxes;
   GeomParams p;
@@ -404,14 +405,22 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
     CU_CHECK(ctx, cudaGetLastError());
     unsigned long long *dc = (unsigned long long *)ctx->counters.p;
     if (int rc = scan_exclusive(ctx, p.counts, p.offs, n_pre, p.offs + (n_pre + 1), dc + 8)) return rc;
-    // one small read-back into pinned memory: [7] validation flags, [8] clipped-list length
-    unsigned long long *hc = (unsigned long long *)ctx->pinned;
-    CU_CHECK(ctx, cudaMemcpyAsync(hc, dc, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    const unsigned long long flags = hc[7];
-    total = (unsigned)hc[8];
-    if (flags & 1ull) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
-    ctx->rast_has_shadow = (n_boxes > 0 || (flags & 2ull)) ? 1 : 0;
+    if (spec) {
+      // pipelined: the list length stays on the device ([8]); the write pass is bounded by
+      // the capacity guessed from the last verified frame and the guess is checked later
+      unsigned long long cap = rast_spec_cap(ctx->rast_spec.tris);
+      if (cap > 0x3fffffffull) cap = 0x3fffffffull;
+      total = (unsigned)cap;
+    } else {
+      // one small read-back into pinned memory: [7] validation flags, [8] clipped-list length
+      unsigned long long *hc = (unsigned long long *)ctx->pinned;
+      CU_CHECK(ctx, cudaMemcpyAsync(hc, dc, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      const unsigned long long flags = hc[7];
+      total = (unsigned)hc[8];
+      if (flags & 1ull) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+      ctx->rast_has_shadow = (n_boxes > 0 || (flags & 2ull)) ? 1 : 0;
+    }
   }
   if (int rc = ensure(ctx, ctx->rast_src, sizeof(rast_triangle) * (size_t)(total ? total : 1))) return rc;
   p.out = (rast_triangle *)ctx->rast_src.p;

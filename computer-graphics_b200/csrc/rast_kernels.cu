@@ -338,9 +338,10 @@ __global__ void rast_rows_kernel(const __grid_constant__ RastParams p) {
   const unsigned chunk = gid >> RAST_CHUNK_LOG2, sub = gid & (RAST_CHUNK - 1);
   if (chunk >= rast_count_chunks(p)) return;
   const int t = p.chunk_owner[chunk];
+  if ((unsigned)t >= (unsigned)p.n_tris) return;   // chunk of a triangle dropped on overflow (stale owner)
   const RastSetup &s = p.setup[t];
   const int r = (int)((chunk - s.chunk_off) << RAST_CHUNK_LOG2) + (int)sub;
-  if (r >= s.nrows) return;
+  if (r < 0 || r >= s.nrows) return;
   float4 A, B;
   rast_row_record(s, s.row0 + r, A, B);
   p.rowsA[s.row_off + r] = A;
@@ -395,7 +396,7 @@ __global__ void rast_spread_kernel(const __grid_constant__ RastParams p, int blo
   if (t < rast_count_tris(p)) {
     const RastSetup &s = p.setup[t];
     if (WHAT == 0) {
-      n = (p.fast && (s.flags & 2)) ? 0 : (s.nrows + RAST_CHUNK - 1) >> RAST_CHUNK_LOG2;
+      n = (s.nrows + RAST_CHUNK - 1) >> RAST_CHUNK_LOG2;
       a = (int)s.chunk_off;
     } else if (s.nrows > 0) {
       const int ts = p.ts_log2;
@@ -686,7 +687,8 @@ __global__ void rast_post_kernel(const __grid_constant__ RastParams p) {
 
 // ---- host side ---------------------------------------------------------------------------------
 int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row0, int row1,
-                float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
+                float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb, bool spec) {
+  // n is the list length, or in a pipelined whole-Draw frame the bound the geometry stage wrote under
   const int W = cam->width, H = cam->height, n = ctx->rast_n_tris;
   RastParams p;
   memset(&p, 0, sizeof p);
@@ -720,38 +722,54 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   size_t row_cap = (size_t)n * (size_t)(p.fb1 - p.fb0);
   const size_t row_budget = (size_t)64 << 20;   // 64 Mi rows = 2 GiB of row records
   if (row_cap < 1) row_cap = 1;
-  const size_t chunk_cap = (row_cap > row_budget ? row_budget : row_cap) / RAST_CHUNK + (size_t)n + 1;
+  size_t chunk_cap = (row_cap > row_budget ? row_budget : row_cap) / RAST_CHUNK + (size_t)n + 1;
+  size_t bin_cap = 0;
+  if (spec) {
+    // sizes guessed from the last verified frame; the setup / scan kernels flag any overflow
+    row_cap = (size_t)rast_spec_cap(ctx->rast_spec.rows);
+    chunk_cap = (size_t)rast_spec_cap(ctx->rast_spec.chunks);
+    bin_cap = (size_t)rast_spec_cap(ctx->rast_spec.bins);
+    p.n_tris_dev = ctx->rast_inflight.whole_draw ? p.counters + 8 : nullptr;
+    p.n_chunks_dev = p.counters + 6;
+    p.n_chunks = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
+    ctx->rast_inflight.cap_bins = bin_cap;
+    ctx->rast_inflight.fast = fast ? 1 : 0;
+  }
   if (int rc = ensure(ctx, ctx->rast_chunks, sizeof(int) * chunk_cap)) return rc;
   p.chunk_owner = (int *)ctx->rast_chunks.p;
   p.chunk_cap = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
+  unsigned long long *hc = (unsigned long long *)ctx->pinned;
 
   if (fast) {
     // ---- scatter / resolve (rast_fast.cuh) ----
     ctx->rast_w = 0; ctx->rast_h = 0;   // no intermediate buffers in this path
-    p.row_cap = 0xffffffffu;            // rows are never stored
+    p.row_cap = spec ? (unsigned)(row_cap > 0xffffffffull ? 0xffffffffull : row_cap) : 0xffffffffu;
     if (int rc = ensure(ctx, ctx->rast_keys, npix * sizeof(unsigned long long))) return rc;
     p.keys = (unsigned long long *)ctx->rast_keys.p;
     CU_CHECK(ctx, cudaMemsetAsync(p.keys + (size_t)p.fb0 * W, 0, (size_t)(p.fb1 - p.fb0) * W * sizeof(unsigned long long), ctx->stream));
-    unsigned long long c[8] = {0};
+    size_t n_rows = row_cap;
     if (n > 0) {
       rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
       rast_spread_launch(ctx, p, 0);
       CU_CHECK(ctx, cudaGetLastError());
-      CU_CHECK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
-      CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the chunk count sizes the next grid
-      memcpy(c, ctx->pinned, sizeof c);
-      if (c[5]) return ctx_fail(ctx, B200_ENOMEM, "row chunk budget exceeded");
     }
-    p.n_chunks = (unsigned)c[6];
-    {
-      const size_t n_rows = (size_t)c[4] ? (size_t)c[4] : 1;     // exact: the setup kernel counted them
-      if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(float4) * n_rows)) return rc;
-      if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * n_rows)) return rc;
-      p.rowsA = (float4 *)ctx->rast_rowsA.p;
-      p.rowsB = (float4 *)ctx->rast_rowsB.p;
+    if (!spec) {
+      p.n_chunks = 0;
+      n_rows = 1;
+      if (n > 0) {
+        CU_CHECK(ctx, cudaMemcpyAsync(hc, ctx->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the chunk count sizes the next grid
+        if (hc[5]) return ctx_fail(ctx, B200_ENOMEM, "row chunk budget exceeded");
+        p.n_chunks = (unsigned)hc[6];
+        if (hc[4]) n_rows = (size_t)hc[4];     // exact: the setup kernel counted them
+      }
     }
-    if (p.n_chunks > 0) {
+    if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(float4) * n_rows)) return rc;
+    if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * n_rows)) return rc;
+    p.rowsA = (float4 *)ctx->rast_rowsA.p;
+    p.rowsB = (float4 *)ctx->rast_rowsB.p;
+    if (p.n_chunks > 0 && n > 0) {
       rast_scatter_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
     }
@@ -799,24 +817,24 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
   ctx->stats.kernel_launches++;
   CU_CHECK(ctx, cudaGetLastError());
-  // the bin array is sized from the scanned total: read it back (tiny, one sync)
-  unsigned long long c[8];
-  CU_CHECK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  memcpy(c, ctx->pinned, sizeof c);
-  if (c[5]) return ctx_fail(ctx, B200_ENOMEM, "row table budget exceeded (triangles too tall for this band)");
-  const size_t bin_total = (size_t)c[3];
-  if (int rc = ensure(ctx, ctx->rast_bins, sizeof(int) * (bin_total ? bin_total : 1))) return rc;
-  if (int rc = ensure(ctx, ctx->rast_tmp, sizeof(int) * (bin_total ? bin_total : 1))) return rc;
+  if (!spec) {
+    // the bin array is sized from the scanned total: read it back (tiny, one sync)
+    CU_CHECK(ctx, cudaMemcpyAsync(hc, ctx->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hc[5]) return ctx_fail(ctx, B200_ENOMEM, "row table budget exceeded (triangles too tall for this band)");
+    bin_cap = (size_t)hc[3];
+    p.n_chunks = (unsigned)hc[6];
+  }
+  if (int rc = ensure(ctx, ctx->rast_bins, sizeof(int) * (bin_cap ? bin_cap : 1))) return rc;
+  if (int rc = ensure(ctx, ctx->rast_tmp, sizeof(int) * (bin_cap ? bin_cap : 1))) return rc;
   p.bins = (int *)ctx->rast_bins.p;
   p.bins_tmp = (int *)ctx->rast_tmp.p;
-  p.bin_cap = (unsigned)bin_total;
-  p.n_chunks = (unsigned)c[6];
-  if (p.n_chunks > 0) {
+  p.bin_cap = (unsigned)(bin_cap > 0xffffffffull ? 0xffffffffull : bin_cap);
+  if (p.n_chunks > 0 && n > 0) {
     rast_rows_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
   }
-  if (n > 0 && bin_total > 0) rast_spread_launch(ctx, p, 2);
+  if (n > 0 && bin_cap > 0) rast_spread_launch(ctx, p, 2);
   dim3 grid(p.tiles_x, p.tiles_y);
   switch (ts) {
     case 3: rast_fill_kernel<3><<<grid, 64, 0, ctx->stream>>>(p); break;

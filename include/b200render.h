@@ -120,6 +120,15 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
  * the intermediate buffers readable), 2 = atomic scatter + fused resolve
  * (lists without shadow-volume triangles only).  Results are identical. */
 #define B200_OPT_RAST_PATH 3
+/* Pipelined rasteriser frames for the device-pointer entries (rast_render_device,
+ * rast_draw_device): 0 (default) = every frame reads its list/table sizes back
+ * mid-frame (two short host waits); 1 = a frame of the same shape as the last
+ * verified one is enqueued without any host wait, sized from that frame plus a
+ * margin.  Its own counters are checked in b200_synchronize / b200_get_stats and a
+ * frame that outgrew the guess is rendered again there with exact sizes, so the
+ * output buffers are final only after one of those two calls returns.  The
+ * host-pointer entries always work this way internally.  Results are identical. */
+#define B200_OPT_RAST_PIPELINED 4
 int b200_set_option(b200_ctx *ctx, int option, int value);
 
 /* Counters of the last render on this context (b200_get_stats synchronises). */
@@ -131,6 +140,7 @@ typedef struct b200_stats {
   uint64_t kernel_launches;  /* kernels of this library launched by the call  */
   uint64_t fragments;        /* RAST: fragments shaded or depth-tested        */
   uint64_t bin_entries;      /* RAST: (tile, triangle) pairs                  */
+  uint64_t respeculated;     /* RAST: pipelined frames rendered twice (context lifetime) */
   float gpu_ms;              /* device time of the call, CUDA events          */
 } b200_stats;
 int b200_get_stats(b200_ctx *ctx, b200_stats *out);

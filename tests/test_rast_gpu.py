@@ -281,3 +281,77 @@ def test_invalid_arguments(b200, renderer):
     L = b200.make_rast_light((0, 0, 0, 1), (1, 1, 1), (0.2, 0.2, 0.2))
     with pytest.raises(b200.B200Error):
         renderer.render_raster_clipped(t, cam, L)
+
+
+def test_pipelined_frames_walk(b200, renderer):
+    """B200_OPT_RAST_PIPELINED: frames sized from the previous verified frame, no mid-frame
+    host waits.  A camera walk whose frames grow and shrink (including a jump from far away to
+    inside the room, which the guess cannot cover) must give the oracle's frame every time."""
+    import torch
+    room, boxes = b200.scene_cornell_rast()
+    W, H, f = 200, 160, 110.0
+    L = b200.make_rast_light(h.DEFAULT_RAST_LIGHT["pos"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
+    rgb = torch.zeros(H, W, 3, device="cuda")
+    depth = torch.zeros(H, W, device="cuda")
+    index = torch.zeros(H, W, dtype=torch.int32, device="cuda")
+    renderer.rast_upload_scene(room, boxes)
+    renderer.set_option(b200.OPT_RAST_PIPELINED, 1)
+    try:
+        before = renderer.stats()["respeculated"]
+        poses = [(0.0, 0.0, -12.0, 0.0), (0.0, 0.0, -11.9, 0.0), (0.0, 0.0, -3.001, 0.0), (0.02, 0.0, -3.0, 0.01),
+                 (0.1, 0.1, -0.4, 0.9), (0.1, 0.1, -0.41, 0.9), (0.0, 0.0, -12.0, 0.0), (0.0, 0.0, 1.5, 0.0)]
+        for i, (x, y, z, yaw) in enumerate(poses):
+            cam_pos, R = h.f32(x, y, z, 1), h.yaw_R(yaw)
+            cam = b200.make_camera(cam_pos, f, R, W, H)
+            renderer.rast_draw_device(cam, L, 0, H, rgb.data_ptr(), depth.data_ptr(), index.data_ptr())
+            renderer.synchronize()        # the frame is final (verified, or rendered again) from here on
+            want = h.oracle_rast_draw(W, H, f, cam_pos, R, h.DEFAULT_RAST_LIGHT, room, boxes)
+            assert np.array_equal(index.cpu().numpy(), want["index"]), f"pose {i}: owner"
+            assert np.array_equal(bits(depth.cpu().numpy()), bits(want["depth"])), f"pose {i}: depth"
+            assert np.array_equal(bits(rgb.cpu().numpy()), bits(want["rgb"])), f"pose {i}: colour"
+            assert h.clipped_equal(renderer.raster_read_clipped(), want["clipped"]), f"pose {i}: clipped list"
+            assert renderer.stats()["fragments"] == want["fragments"], f"pose {i}: fragments"
+        st = renderer.stats()
+        assert st["respeculated"] > before, "the jump into the room should have outgrown the guess"
+        assert st["respeculated"] - before < len(poses) - 2, "small camera moves must stay pipelined"
+    finally:
+        renderer.set_option(b200.OPT_RAST_PIPELINED, 0)
+
+
+def test_pipelined_clipped_lists_and_soup(b200, renderer):
+    """Pipelined frames on the scatter path (shadow-free lists) and through the clipped-list
+    entry: same-shape lists with very different row counts, back to back."""
+    import torch
+    W, H, f = 96, 80, 60.0
+    cam = b200.make_camera((0, 0, 0, 1), f, h.identity_R(), W, H)
+    light = dict(pos=(0.1, -0.3, 0.2, 1.0), power=(5.0, 4.0, 3.0), indirect=(0.3, 0.3, 0.3))
+    L = b200.make_rast_light(light["pos"], light["power"], light["indirect"])
+    rgb = torch.zeros(H, W, 3, device="cuda")
+    depth = torch.zeros(H, W, device="cuda")
+    renderer.set_option(b200.OPT_RAST_PIPELINED, 1)
+    try:
+        for shadow_frac in (0.0, 0.3):
+            for seed in range(4):
+                t = h.random_clipped_list(60, 50 + seed, W, H, f, shadow_frac=shadow_frac)
+                if seed % 2:      # shrink every other list towards its first vertex: far fewer rows
+                    for k in ("v1", "v2"):
+                        t[k][:, :2] = t["v0"][:, :2] + 0.05 * (t[k][:, :2] - t["v0"][:, :2])
+                renderer.rast_upload_clipped(t)
+                renderer.rast_render_device(cam, L, 0, H, rgb.data_ptr(), depth.data_ptr())
+                renderer.synchronize()
+                want = h.oracle_rast_draw_clipped(W, H, f, h.f32(*light["pos"]), light, t)
+                assert np.array_equal(bits(depth.cpu().numpy()), bits(want["depth"])), (shadow_frac, seed)
+                assert np.array_equal(bits(rgb.cpu().numpy()), bits(want["rgb"])), (shadow_frac, seed)
+        soup = b200.scene_soup_rast(30000, edge=0.03)
+        none = np.zeros(0, h.RAST_TRI)
+        renderer.rast_upload_scene(soup, none)
+        for z in (-3.001, -3.0, -2.9, -1.2):
+            cam_pos = h.f32(0, 0, z, 1)
+            cam = b200.make_camera(cam_pos, f, h.identity_R(), W, H)
+            renderer.rast_draw_device(cam, L, 0, H, rgb.data_ptr(), depth.data_ptr())
+            renderer.synchronize()
+            want = h.oracle_rast_draw(W, H, f, cam_pos, h.identity_R(), light, soup, none)
+            assert np.array_equal(bits(depth.cpu().numpy()), bits(want["depth"])), z
+            assert np.array_equal(bits(rgb.cpu().numpy()), bits(want["rgb"])), z
+    finally:
+        renderer.set_option(b200.OPT_RAST_PIPELINED, 0)
