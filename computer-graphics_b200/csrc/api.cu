@@ -69,7 +69,7 @@ void b200_destroy(b200_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rt_dtcam, &ctx->rast_src,
+  DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rt_dtcam, &ctx->rt_cells, &ctx->rt_cell_rec, &ctx->rt_cell_idx, &ctx->rast_src,
                     &ctx->rast_setup, &ctx->rast_rowsA, &ctx->rast_rowsB, &ctx->rast_bins, &ctx->rast_tile_count,
                     &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
                     &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
@@ -108,6 +108,10 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
     case B200_OPT_RAST_PATH:
       if (value < 0 || value > 2) return ctx_fail(ctx, B200_EINVAL, "raster path must be 0, 1 or 2");
       ctx->opt_rast_path = value;
+      return B200_OK;
+    case B200_OPT_RT_GRID:
+      if (value < 0 || value > 2) return ctx_fail(ctx, B200_EINVAL, "grid mode must be 0, 1 or 2");
+      ctx->opt_rt_grid = value;
       return B200_OK;
     case B200_OPT_RAST_PIPELINED:
       ctx->opt_rast_pipelined = value != 0;
@@ -608,5 +612,15 @@ extern "C" int b200_debug_counters(b200_ctx *ctx, unsigned long long *out8) {
   if (!ctx || !out8) return B200_EINVAL;
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   CU_CHECK(ctx, cudaMemcpy(out8, ctx->counters.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return B200_OK;
+}
+
+// List length of every direction-grid cell of the last gridded RT frame (diagnostics).
+extern "C" int b200_debug_rt_cells(b200_ctx *ctx, unsigned *out, int cap, int *n_cells, int *n_cam_cells) {
+  if (!ctx || !n_cells || !n_cam_cells) return B200_EINVAL;
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_cells = (int)ctx->rt_n_cells; *n_cam_cells = (int)ctx->rt_n_cam_cells;
+  const size_t n = ctx->rt_n_cells < (size_t)cap ? ctx->rt_n_cells : (size_t)cap;
+  if (out && n) CU_CHECK(ctx, cudaMemcpy(out, ctx->rt_cells.p, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
   return B200_OK;
 }

@@ -84,6 +84,10 @@ struct b200_ctx {
   DevBuf rt_spheres;  // rt_sphere[n]
   DevBuf rt_planes;   // float4[..]: per-origin edge-function planes for the filter
   DevBuf rt_dtcam;    // float[n]: per-frame numerator of t for primary rays
+  DevBuf rt_cells;    // direction grids: per-cell counts, cursors, padded counts, offsets, scan scratch
+  DevBuf rt_cell_rec, rt_cell_idx;   // the cells' lists: plane records and triangle indices
+  size_t rt_n_cells = 0, rt_n_cam_cells = 0;   // of the last gridded frame (diagnostics)
+  int opt_rt_grid = 0;               // 0 auto (scenes of RT_GRID_AUTO_TRIS triangles or more), 1 always, 2 never
   int rt_n_tris = 0, rt_n_spheres = 0;
   float rt_world_abs = 0.f;   // max |coordinate| over the uploaded scene
   int pending = 0;            // 1 = RT, 2 = RAST render whose counters are not read back yet
@@ -155,6 +159,8 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
 int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, rast_light_t *light_out,
                   bool spec);
 static inline unsigned long long rast_spec_cap(unsigned long long seen) { return seen + seen / 8 + 1024; }
+int scan_exclusive(b200_ctx *ctx, const unsigned *counts, unsigned *offs, int n, unsigned *tmp,
+                   unsigned long long *total_out);   // rast_geom.cu; tmp: n / 4096 + 2 words
 int rt_prepare_scene(b200_ctx *ctx);
 int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int32_t *d_index,
               uint32_t *d_argb);

@@ -17,6 +17,11 @@ struct RtKParams {
   const float4 *planes;      // see rt_filtered.cuh
   const float *dt_cam;       // per triangle: det(camera - v0, e1, e2)
   int tris_per_tile;
+  // direction grids (rt_grid.cuh), GRID kernels only
+  const unsigned *cell_off;  // first entry of each cell's list
+  const unsigned *cell_cnt;  // entries in it
+  const float4 *cell_rec;    // plane records, list by list
+  const int *cell_idx;       // triangle index of each entry
   // outputs: full-frame addressing (pixel (x, y) at y*W + x); any may be null
   float *rgb;
   float *depth;

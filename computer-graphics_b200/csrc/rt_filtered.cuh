@@ -34,6 +34,11 @@
 constexpr int RT_TILE = 256;      // triangles per shared-memory tile
 constexpr int RT_THREADS = 256;   // 8 warps: a 16x16 pixel block
 constexpr int RT_REC_F4 = 3;      // float4s per plane record (48 bytes)
+// direction grids (rt_grid.cuh)
+constexpr int RT_GRID_G = 64;              // light cube map: cells per face edge
+constexpr int RT_GRID_FACE = RT_GRID_G * RT_GRID_G;
+constexpr int RT_GRID_MAX_CELLS = 256;     // shadow phase: distinct cells one pixel block may walk, else it streams the scene
+constexpr int RT_GRID_TABLE_LOG2 = 9;      // hash set used to collect them
 
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+/sm_100a PTX) ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -174,6 +179,41 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- bundle-box tests shared by the render kernel (L0) and the grid builder -------
+// A triangle can matter to a ray only if all three edge values are >= -E there.  Over a
+// box of directions (centre c, half-widths h >= 0) each edge value is linear, so its
+// maximum is known exactly; the same holds for the sums of two and of all three, which
+// must then be >= -2E / -3E.  The sums catch what the single planes cannot: triangles
+// seen nearly edge-on, whose two long edge planes almost coincide and straddle the box.
+// (Coefficient sums are rounded once more; the factors leave room for that.)
+__device__ __forceinline__ bool rt_box_may_hit_light(const float4 q0, const float4 q1, const float4 q2, const float *c,
+                                                     const float *h, float Eg) {
+  const float U[3] = {q0.x, q0.y, q0.z}, V[3] = {q0.w, q1.x, q1.y}, W[3] = {q1.z, q1.w, q2.x};
+  auto hi = [&](float x, float y, float z) {
+    return fmaf(x, c[0], fmaf(y, c[1], z * c[2])) + fmaf(fabsf(x), h[0], fmaf(fabsf(y), h[1], fabsf(z) * h[2]));
+  };
+  if (fminf(fminf(hi(U[0], U[1], U[2]), hi(V[0], V[1], V[2])), hi(W[0], W[1], W[2])) < -Eg) return false;
+  const float uv = hi(U[0] + V[0], U[1] + V[1], U[2] + V[2]);
+  const float vw = hi(V[0] + W[0], V[1] + W[1], V[2] + W[2]);
+  const float uw = hi(U[0] + W[0], U[1] + W[1], U[2] + W[2]);
+  if (fminf(fminf(uv, vw), uw) < -2.1f * Eg) return false;
+  return true;
+}
+// camera: directions (dx, dy, f) with the z term folded into the constant; E absolute
+__device__ __forceinline__ bool rt_box_may_hit_cam(const float4 q0, const float4 q1, const float4 q2, float c0, float c1,
+                                                   float h0, float h1) {
+  auto hi = [&](float x, float y, float k) {
+    return fmaf(x, c0, fmaf(y, c1, k)) + fmaf(fabsf(x), h0, fabsf(y) * h1);
+  };
+  const float E = q2.y;
+  if (fminf(fminf(hi(q0.x, q0.y, q0.z), hi(q0.w, q1.x, q1.y)), hi(q1.z, q1.w, q2.x)) < -E) return false;
+  const float uv = hi(q0.x + q0.w, q0.y + q1.x, q0.z + q1.y);
+  const float vw = hi(q0.w + q1.z, q1.x + q1.w, q1.y + q2.x);
+  const float uw = hi(q0.x + q1.z, q0.y + q1.w, q0.z + q2.x);
+  if (fminf(fminf(uv, vw), uw) < -2.1f * E) return false;
+  return true;
 }
 
 #include "rt_filtered_kernel.cuh"

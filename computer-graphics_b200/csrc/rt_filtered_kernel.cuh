@@ -32,7 +32,11 @@ __device__ __noinline__ RtHit rt_ex_primary(const float4 *__restrict__ geom, con
   const float t = xdiv(__ldg(dt_cam + tri), D);   // numerator: the same for every primary ray (rt_prep_planes_kernel)
   const float distance = xmul(t, len);
   if (distance < 0.0f) return best;
-  if (distance >= best.dist || distance > FLT_MAX) return best;
+  // The reference walks the triangles in ascending order and replaces on a strict `<`
+  // (:313): the closest hit, lowest index on ties.  Written order-independently, because
+  // the direction-grid lists (rt_grid.cuh) are unordered.
+  if (distance > best.dist || distance > FLT_MAX) return best;
+  if (distance == best.dist && (best.dist == FLT_MAX || tri > best.idx)) return best;
   if (!inside) {
     const float sx = xsub(cx, g0.x), sy = xsub(cy, g0.y), sz = xsub(cz, g0.z);
     const float u = xdiv(xdet3(-dx, -dy, -dz, sx, sy, sz, e2x, e2y, e2z), D);
@@ -134,24 +138,112 @@ __device__ __noinline__ RtShade rt_ex_shade(const rt_triangle *__restrict__ src,
 // The TMA tile ring shared by the primary and the shadow passes.
 struct RtRing {
   float4 *smem;
+  int *smem_idx;     // GRID: triangle index of each record of the tile
   uint64_t *bars;
   uint32_t phase_bits;
   int issued;
 };
 
-__device__ __forceinline__ void rt_ring_issue(RtRing &ring, const float4 *src, int cnt) {
+// One tile of work: up to RT_TILE consecutive records of a list.
+struct RtItem {
+  const float4 *rec;
+  const int *idx;    // null: the list is the scene itself, record i is triangle base + i
+  int base, cnt;
+};
+
+__device__ __forceinline__ void rt_ring_issue(RtRing &ring, const RtItem &it) {
   const int buf = ring.issued & 1;
-  mbar_expect_tx(&ring.bars[buf], cnt * 48u);
-  tma_bulk_g2s(ring.smem + (size_t)buf * RT_TILE * RT_REC_F4, src, cnt * 48u, &ring.bars[buf]);
+  const uint32_t rec_bytes = (uint32_t)it.cnt * 48u, idx_bytes = it.idx ? (((uint32_t)it.cnt + 3u) & ~3u) * 4u : 0u;
+  mbar_expect_tx(&ring.bars[buf], rec_bytes + idx_bytes);
+  tma_bulk_g2s(ring.smem + (size_t)buf * RT_TILE * RT_REC_F4, it.rec, rec_bytes, &ring.bars[buf]);
+  if (it.idx) tma_bulk_g2s(ring.smem_idx + buf * RT_TILE, it.idx, idx_bytes, &ring.bars[buf]);
 }
 
-template <bool MULTI>
+// Walks the lists a pixel block has to stream, tile by tile: the whole scene, or
+// (GRID) the lists of the direction cells in cells[0 .. nc).  Uniform over the block.
+struct RtCursor {
+  const float4 *rec;
+  const int *idx;
+  int cnt, pos;
+  const int *cells;
+  int ci, nc;
+};
+
+__device__ __forceinline__ RtCursor rt_cursor_scene(const float4 *planes, int n_tris) {
+  RtCursor c;
+  c.rec = planes; c.idx = nullptr; c.cnt = n_tris; c.pos = 0; c.cells = nullptr; c.ci = 0; c.nc = 0;
+  return c;
+}
+__device__ __forceinline__ RtCursor rt_cursor_cells(const int *cells, int nc) {
+  RtCursor c;
+  c.rec = nullptr; c.idx = nullptr; c.cnt = 0; c.pos = 0; c.cells = cells; c.ci = 0; c.nc = nc;
+  return c;
+}
+
+template <bool GRID>
+__device__ __forceinline__ bool rt_cursor_next(const RtKParams &p, RtCursor &c, RtItem &it) {
+  while (c.pos >= c.cnt) {
+    if (!GRID || c.ci >= c.nc) return false;
+    const int cell = c.cells[c.ci++];
+    const unsigned off = __ldg(p.cell_off + cell);
+    c.cnt = (int)__ldg(p.cell_cnt + cell);
+    c.rec = p.cell_rec + (size_t)off * RT_REC_F4;
+    c.idx = p.cell_idx + off;
+    c.pos = 0;
+  }
+  it.rec = c.rec + (size_t)c.pos * RT_REC_F4;
+  it.idx = c.idx ? c.idx + c.pos : nullptr;
+  it.base = c.pos;
+  it.cnt = min(RT_TILE, c.cnt - c.pos);
+  c.pos += RT_TILE;
+  return true;
+}
+
+// Shadow phase, GRID: the cube-map cell (around the light) that g = hit - light falls
+// into: face * RT_GRID_FACE + j * RT_GRID_G + i, or -1 for a vector that has no direction.
+// The division's rounding moves a direction by far less than the 2 % of a cell by
+// which rt_grid_test_light widens every cell.
+__device__ __forceinline__ int rt_grid_cell_of(float gx, float gy, float gz) {
+  const float ax = fabsf(gx), ay = fabsf(gy), az = fabsf(gz);
+  const int a = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+  const float ga = a == 0 ? gx : (a == 1 ? gy : gz);
+  const float gb = a == 0 ? gy : (a == 1 ? gz : gx);
+  const float gc = a == 0 ? gz : (a == 1 ? gx : gy);
+  const float m = fabsf(ga);
+  if (!(m > 1e-30f && m < 1e30f)) return -1;
+  const float G = (float)RT_GRID_G;
+  const int i = min(max((int)floorf((gb / m + 1.0f) * 0.5f * G), 0), RT_GRID_G - 1);
+  const int j = min(max((int)floorf((gc / m + 1.0f) * 0.5f * G), 0), RT_GRID_G - 1);
+  return (2 * a + (ga < 0.0f ? 1 : 0)) * RT_GRID_FACE + j * RT_GRID_G + i;
+}
+
+// Adds `cell` to the block's set (open addressing in shared memory; the list keeps
+// the distinct cells).  *n_cells may run past RT_GRID_MAX_CELLS: the caller checks.
+__device__ __forceinline__ void rt_grid_mark(int cell, int *table, int *cells, int *n_cells) {
+  unsigned hsh = ((unsigned)cell * 2654435761u) >> (32 - RT_GRID_TABLE_LOG2);
+  for (int probe = 0; probe < (1 << RT_GRID_TABLE_LOG2); ++probe) {
+    const int old = atomicCAS(table + hsh, -1, cell);
+    if (old == cell) return;
+    if (old == -1) {
+      const int pos = atomicAdd(n_cells, 1);
+      if (pos < RT_GRID_MAX_CELLS) cells[pos] = cell;
+      return;
+    }
+    hsh = (hsh + 1) & ((1u << RT_GRID_TABLE_LOG2) - 1);
+  }
+  atomicAdd(n_cells, RT_GRID_MAX_CELLS + 1);   // table full: stream the scene
+}
+
+template <bool MULTI, bool GRID>
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(const __grid_constant__ RtKParams p) {
-  extern __shared__ __align__(128) float4 tile_smem[];  // 2 x RT_TILE x 3 float4
+  extern __shared__ __align__(128) float4 tile_smem[];  // 2 x RT_TILE x 3 float4 (+ GRID: 2 x RT_TILE int)
   __shared__ __align__(8) uint64_t bars[2];
+  __shared__ int s_cells[GRID ? RT_GRID_MAX_CELLS : 1];
+  __shared__ int s_table[GRID ? (1 << RT_GRID_TABLE_LOG2) : 1];
+  __shared__ int s_ncells;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // warp = 8x4 pixel patch; 8 warps tile a 16x16 block as 2 columns x 4 rows
@@ -159,8 +251,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
   const int v = p.row0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
   const bool live = (u < p.W) && (v < p.row1);
   const size_t pid = (size_t)v * p.W + u;
-  const int n_tiles = (p.n_tris + RT_TILE - 1) / RT_TILE;
-  const size_t origin_stride = (size_t)n_tiles * RT_TILE * RT_REC_F4;
+  const size_t origin_stride = (size_t)((p.n_tris + RT_TILE - 1) / RT_TILE) * RT_TILE * RT_REC_F4;
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
@@ -170,6 +261,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
   __syncthreads();
   RtRing ring;
   ring.smem = tile_smem; ring.bars = bars; ring.phase_bits = 0; ring.issued = 0;
+  ring.smem_idx = reinterpret_cast<int *>(tile_smem + 2 * RT_TILE * RT_REC_F4);
 
   // dir = R * vec4(u - W/2, v - H/2, f, 1)   (skeleton.cpp:126-128)
   const float x = (float)(u - p.W / 2), y = (float)(v - p.H / 2);
@@ -206,45 +298,64 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
     const float wh0 = (0.5f * (hi0 - lo0) + 0.5f) * 1.0001f + 1e-3f;
     const float wh1 = (0.5f * (hi1 - lo1) + 0.5f) * 1.0001f + 1e-3f;
 
-    const float4 *src = p.planes;  // origin 0
-    if (threadIdx.x == 0 && n_tiles > 0) rt_ring_issue(ring, src, min(RT_TILE, p.n_tris));
-    for (int tile = 0; tile < n_tiles; ++tile) {
+    RtCursor cursor = rt_cursor_scene(p.planes, p.n_tris);   // origin 0
+    if (GRID) {
+      if (threadIdx.x == 0) s_cells[0] = blockIdx.y * gridDim.x + blockIdx.x;   // this block's own cell
+      __syncthreads();
+      cursor = rt_cursor_cells(s_cells, 1);
+    }
+    RtItem item;
+    bool have = rt_cursor_next<GRID>(p, cursor, item);
+    if (threadIdx.x == 0 && have) rt_ring_issue(ring, item);
+    while (have) {
       const int buf = ring.issued & 1;
       ++ring.issued;
-      __syncthreads();   // everyone is done with the other buffer (it held tile-1): refill it
-      if (threadIdx.x == 0 && tile + 1 < n_tiles)
-        rt_ring_issue(ring, src + (size_t)(tile + 1) * RT_TILE * RT_REC_F4, min(RT_TILE, p.n_tris - (tile + 1) * RT_TILE));
+      __syncthreads();   // everyone is done with the other buffer (it held the previous tile): refill it
+      RtItem next_item;
+      const bool have_next = rt_cursor_next<GRID>(p, cursor, next_item);
+      if (threadIdx.x == 0 && have_next) rt_ring_issue(ring, next_item);
       mbar_wait(&bars[buf], (ring.phase_bits >> buf) & 1u);
       ring.phase_bits ^= 1u << buf;
       const float4 *T = tile_smem + (size_t)buf * RT_TILE * RT_REC_F4;
-      const int base = tile * RT_TILE;
-      const int cnt = min(RT_TILE, p.n_tris - base);
-      if (!warp_live) continue;
+      const int *Tidx = ring.smem_idx + buf * RT_TILE;
+      const bool listed = GRID && item.idx != nullptr;
+      const int base = item.base;
+      const int cnt = warp_live ? item.cnt : 0;
+#ifdef RT_PROFILE_COUNTERS
+      if (threadIdx.x == 0) atomicAdd(p.counters + 12, (unsigned long long)item.cnt);
+#endif
+      item = next_item;
+      have = have_next;
       for (int r0 = 0; r0 < cnt; r0 += 32) {
         // ---- L0: one triangle per lane vs the warp's bundle box ----
         bool pass = false;
         if (r0 + lane < cnt) {
           const float4 q0 = T[(r0 + lane) * 3], q1 = T[(r0 + lane) * 3 + 1], q2 = T[(r0 + lane) * 3 + 2];
-          const float bu = fmaf(q0.x, wc0, fmaf(q0.y, wc1, q0.z)) + fmaf(fabsf(q0.x), wh0, fabsf(q0.y) * wh1);
-          const float bv = fmaf(q0.w, wc0, fmaf(q1.x, wc1, q1.y)) + fmaf(fabsf(q0.w), wh0, fabsf(q1.x) * wh1);
-          const float bw = fmaf(q1.z, wc0, fmaf(q1.w, wc1, q2.x)) + fmaf(fabsf(q1.z), wh0, fabsf(q1.w) * wh1);
           // E already covers the rounding of the centre evaluation (|wc| <= dmax);
           // the half-width terms are sums of non-negative products, inflated above
-          pass = !(fminf(fminf(bu, bv), bw) < -q2.y);
+          pass = rt_box_may_hit_cam(q0, q1, q2, wc0, wc1, wh0, wh1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, pass);
+        // ---- L1: every lane tests its pixel (centre, margin widened by the +-0.5 jitter)
+        //      against every survivor and remembers the ones it needs ----
+        unsigned mine = 0;
         while (mask) {
           const int j = __ffs(mask) - 1;
           mask &= mask - 1;
-          const int tri = base + r0 + j;
           const float4 q0 = T[(r0 + j) * 3], q1 = T[(r0 + j) * 3 + 1], q2 = T[(r0 + j) * 3 + 2];
-          if (!live) continue;
-          // ---- L1: pixel centre, margin widened by the +-0.5 jitter ----
           const float cu = fmaf(q0.x, dir0, fmaf(q0.y, dir1, q0.z));
           const float cv = fmaf(q0.w, dir0, fmaf(q1.x, dir1, q1.y));
           const float cw = fmaf(q1.z, dir0, fmaf(q1.w, dir1, q2.x));
-          RT_PC(0);
-          if (fminf(fminf(cu, cv), cw) < -q2.w) continue;
+          if (live) RT_PC(0);
+          if (live && !(fminf(fminf(cu, cv), cw) < -q2.w)) mine |= 1u << j;
+        }
+        // ---- L2 / EX: each lane walks ITS OWN candidates, in ascending order; lanes are on
+        //      different triangles here, so small triangles do not serialise the warp ----
+        while (mine) {
+          const int j = __ffs(mine) - 1;
+          mine &= mine - 1;
+          const int tri = listed ? Tidx[r0 + j] : base + r0 + j;
+          const float4 q0 = T[(r0 + j) * 3], q1 = T[(r0 + j) * 3 + 1], q2 = T[(r0 + j) * 3 + 2];
           RT_PC(1);
           const float E = q2.y, dt_lo = q2.z;
           // ---- L2 / EX: per ray ----
@@ -259,7 +370,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
               RT_PC(2);
               const float mN = mU + mV + mW;
               // reference distance >= dt_lo*len/(mN+E): cannot beat the current closest
-              const bool farther = (mN > E) && (dt_lo * len[k] >= best[k].dist * (mN + E));
+              const bool farther = (mN > E) && (dt_lo * len[k] > best[k].dist * (mN + E));
               if (!farther) {
                 ++n_exact;
                 best[k] = rt_ex_primary(p.geom, p.dt_cam, cx, cy, cz, tri, m3 >= E ? 1 : 0, dx, dy, dz, len[k], best[k]);
@@ -338,58 +449,97 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
     // the buffer about to be refilled last held the tile before the previous
     // phase's final one; every thread left it at that phase's last barrier
     __syncthreads();
-    if (threadIdx.x == 0 && n_tiles > 0) rt_ring_issue(ring, src, min(RT_TILE, p.n_tris));
-    for (int tile = 0; tile < n_tiles; ++tile) {
+    RtCursor cursor = rt_cursor_scene(src, p.n_tris);
+    if (GRID) {
+      // the cube-map cells around this light that the block's shadow rays fall into
+      for (int i = threadIdx.x; i < (1 << RT_GRID_TABLE_LOG2); i += RT_THREADS) s_table[i] = -1;
+      if (threadIdx.x == 0) s_ncells = 0;
+      __syncthreads();
+      const int cell_base = (int)(gridDim.x * gridDim.y) + l * 6 * RT_GRID_FACE;
+      int last = -2;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        if (!((active >> k) & 1u)) continue;
+        const float gx = -xsub(Lx, xadd(cx, xmul(ht[k], dxs[k / 3])));
+        const float gy = -xsub(Ly, xadd(cy, xmul(ht[k], dys[k % 3])));
+        const float gz = -xsub(Lz, xadd(cz, xmul(ht[k], dz)));
+        const int cell = rt_grid_cell_of(gx, gy, gz);
+        if (cell == last) continue;
+        last = cell;
+        if (cell < 0) atomicAdd(&s_ncells, RT_GRID_MAX_CELLS + 1);   // no direction: stream the scene
+        else rt_grid_mark(cell_base + cell, s_table, s_cells, &s_ncells);
+      }
+      __syncthreads();
+      if (s_ncells <= RT_GRID_MAX_CELLS) cursor = rt_cursor_cells(s_cells, s_ncells);
+#ifdef RT_PROFILE_COUNTERS
+      if (threadIdx.x == 0) {
+        if (s_ncells > RT_GRID_MAX_CELLS) atomicAdd(p.counters + 10, 1ull);
+        else atomicAdd(p.counters + 11, (unsigned long long)s_ncells);
+      }
+#endif
+    }
+    RtItem item;
+    bool have = rt_cursor_next<GRID>(p, cursor, item);
+    if (threadIdx.x == 0 && have) rt_ring_issue(ring, item);
+    while (have) {
       const int buf = ring.issued & 1;
       ++ring.issued;
       __syncthreads();
-      if (threadIdx.x == 0 && tile + 1 < n_tiles)
-        rt_ring_issue(ring, src + (size_t)(tile + 1) * RT_TILE * RT_REC_F4, min(RT_TILE, p.n_tris - (tile + 1) * RT_TILE));
+      RtItem next_item;
+      const bool have_next = rt_cursor_next<GRID>(p, cursor, next_item);
+      if (threadIdx.x == 0 && have_next) rt_ring_issue(ring, next_item);
       mbar_wait(&bars[buf], (ring.phase_bits >> buf) & 1u);
       ring.phase_bits ^= 1u << buf;
       const float4 *T = tile_smem + (size_t)buf * RT_TILE * RT_REC_F4;
-      const int base = tile * RT_TILE;
-      const int cnt = min(RT_TILE, p.n_tris - base);
-      if (!warp_active) continue;
+      const int *Tidx = ring.smem_idx + buf * RT_TILE;
+      const bool listed = GRID && item.idx != nullptr;
+      const int base = item.base;
+      const int cnt = warp_active ? item.cnt : 0;
+#ifdef RT_PROFILE_COUNTERS
+      if (threadIdx.x == 0) atomicAdd(p.counters + 13, (unsigned long long)item.cnt);
+#endif
+      item = next_item;
+      have = have_next;
       for (int r0 = 0; r0 < cnt; r0 += 32) {
         // ---- L0: one triangle per lane vs the warp's shadow-bundle box ----
         bool pass = false;
         if (r0 + lane < cnt) {
           const float4 q0 = T[(r0 + lane) * 3], q1 = T[(r0 + lane) * 3 + 1], q2 = T[(r0 + lane) * 3 + 2];
           const float Eg = q2.y * wnorm;
-          const float cu = fmaf(q0.x, wc[0], fmaf(q0.y, wc[1], q0.z * wc[2]));
-          const float cv = fmaf(q0.w, wc[0], fmaf(q1.x, wc[1], q1.y * wc[2]));
-          const float cw = fmaf(q1.z, wc[0], fmaf(q1.w, wc[1], q2.x * wc[2]));
-          const float hu = fmaf(fabsf(q0.x), wh[0], fmaf(fabsf(q0.y), wh[1], fabsf(q0.z) * wh[2]));
-          const float hv = fmaf(fabsf(q0.w), wh[0], fmaf(fabsf(q1.x), wh[1], fabsf(q1.y) * wh[2]));
-          const float hw = fmaf(fabsf(q1.z), wh[0], fmaf(fabsf(q1.w), wh[1], fabsf(q2.x) * wh[2]));
-          const float m3 = fminf(fminf(cu + hu, cv + hv), cw + hw);
-          const float mN = (cu + cv + cw) + (hu + hv + hw);
-          pass = !(m3 < -Eg) && !(mN + Eg < q2.z);
+          const float nx = q0.x + q0.w + q1.z, ny = q0.y + q1.x + q1.w, nz = q0.z + q1.y + q2.x;
+          const float mN = fmaf(nx, wc[0], fmaf(ny, wc[1], nz * wc[2])) +
+                           fmaf(fabsf(nx), wh[0], fmaf(fabsf(ny), wh[1], fabsf(nz) * wh[2]));
+          pass = rt_box_may_hit_light(q0, q1, q2, wc, wh, Eg) && !(mN + 1.1f * Eg < q2.z);
         }
         unsigned mask = __ballot_sync(0xffffffffu, pass);
+        // ---- L1: the pixel's own bundle box against every survivor ----
+        unsigned mine = 0;
         while (mask) {
           const int j = __ffs(mask) - 1;
           mask &= mask - 1;
-          const int tri = base + r0 + j;
           const float4 q0 = T[(r0 + j) * 3], q1 = T[(r0 + j) * 3 + 1], q2 = T[(r0 + j) * 3 + 2];
-          const unsigned todo = active & ~occluded;
-          if (!todo) continue;
           const float Eg = q2.y * pnorm;
-          {
-            // ---- L1: the pixel's own bundle box ----
-            const float cu = fmaf(q0.x, pc[0], fmaf(q0.y, pc[1], q0.z * pc[2]));
-            const float cv = fmaf(q0.w, pc[0], fmaf(q1.x, pc[1], q1.y * pc[2]));
-            const float cw = fmaf(q1.z, pc[0], fmaf(q1.w, pc[1], q2.x * pc[2]));
-            const float hu = fmaf(fabsf(q0.x), ph[0], fmaf(fabsf(q0.y), ph[1], fabsf(q0.z) * ph[2]));
-            const float hv = fmaf(fabsf(q0.w), ph[0], fmaf(fabsf(q1.x), ph[1], fabsf(q1.y) * ph[2]));
-            const float hw = fmaf(fabsf(q1.z), ph[0], fmaf(fabsf(q1.w), ph[1], fabsf(q2.x) * ph[2]));
-            const float m3 = fminf(fminf(cu + hu, cv + hv), cw + hw);
-            const float mN = (cu + cv + cw) + (hu + hv + hw);
-            RT_PC(3);
-            if ((m3 < -Eg) || (mN + Eg < q2.z)) continue;
-            RT_PC(4);
-          }
+          const float cu = fmaf(q0.x, pc[0], fmaf(q0.y, pc[1], q0.z * pc[2]));
+          const float cv = fmaf(q0.w, pc[0], fmaf(q1.x, pc[1], q1.y * pc[2]));
+          const float cw = fmaf(q1.z, pc[0], fmaf(q1.w, pc[1], q2.x * pc[2]));
+          const float hu = fmaf(fabsf(q0.x), ph[0], fmaf(fabsf(q0.y), ph[1], fabsf(q0.z) * ph[2]));
+          const float hv = fmaf(fabsf(q0.w), ph[0], fmaf(fabsf(q1.x), ph[1], fabsf(q1.y) * ph[2]));
+          const float hw = fmaf(fabsf(q1.z), ph[0], fmaf(fabsf(q1.w), ph[1], fabsf(q2.x) * ph[2]));
+          const float m3 = fminf(fminf(cu + hu, cv + hv), cw + hw);
+          const float mN = (cu + cv + cw) + (hu + hv + hw);
+          if (active) RT_PC(3);
+          if ((active & ~occluded) && !((m3 < -Eg) || (mN + Eg < q2.z))) mine |= 1u << j;
+        }
+        // ---- L2 / EX: each lane walks its own candidates ----
+        while (mine) {
+          const int j = __ffs(mine) - 1;
+          mine &= mine - 1;
+          const unsigned todo = active & ~occluded;
+          if (!todo) break;
+          const int tri = listed ? Tidx[r0 + j] : base + r0 + j;
+          const float4 q0 = T[(r0 + j) * 3], q1 = T[(r0 + j) * 3 + 1], q2 = T[(r0 + j) * 3 + 2];
+          const float Eg = q2.y * pnorm;
+          RT_PC(4);
           // ---- L2 / EX: per shadow ray ----
 #pragma unroll
           for (int k = 0; k < 9; ++k) {
@@ -461,6 +611,9 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
   rt_count(p.counters + 1, (unsigned long long)n_exact);
 #ifdef RT_PROFILE_COUNTERS
   if (live) for (int i = 0; i < 6; ++i) atomicAdd(p.counters + 2 + i, (unsigned long long)prof_cnt[i + (i >= 2 ? 1 : 0)]);
+  // diagnostic build only: the depth plane carries this pixel's shadow L1 test count, the index plane its exact evaluations
+  if (live && p.depth) p.depth[pid] = (float)prof_cnt[3];
+  if (live && p.index) p.index[pid] = (int)n_exact;
 #endif
 }
 

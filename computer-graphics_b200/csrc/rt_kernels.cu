@@ -9,6 +9,7 @@
 //                         reference arithmetic runs only where it can matter.
 #include "rt_exact.cuh"
 #include "rt_filtered.cuh"
+#include "rt_grid.cuh"
 
 // ------------------------------------------------------------------------------
 // scene preparation: v0 / e1 / e2 per triangle (skeleton.cpp:283-284)
@@ -122,6 +123,7 @@ int rt_prepare_scene(b200_ctx *ctx) {
 int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int32_t *d_index,
               uint32_t *d_argb) {
   RtKParams p;
+  memset(&p, 0, sizeof p);
   memcpy(p.cam, f.cam, sizeof p.cam);
   p.focal = f.focal;
   memcpy(p.R, f.R, sizeof p.R);
@@ -145,6 +147,9 @@ int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int
   }
   return rt_launch_filtered(ctx, f, p);
 }
+
+constexpr int RT_GRID_AUTO_TRIS = 2048;                       // scenes this large get direction grids
+constexpr unsigned long long RT_GRID_MAX_ENTRIES = 1ull << 26;   // 64 Mi list entries = 3.25 GiB
 
 int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
   const int n = ctx->rt_n_tris;
@@ -194,10 +199,68 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
   const int rows = f.row1 - f.row0;
   dim3 grid((f.W + 15) / 16, (rows + 15) / 16);
   const size_t smem = 2 * (size_t)RT_TILE * RT_REC_F4 * sizeof(float4);
-  if (f.n_lights > 1)
-    rt_filtered_kernel<true><<<grid, RT_THREADS, smem, ctx->stream>>>(p);
-  else
-    rt_filtered_kernel<false><<<grid, RT_THREADS, smem, ctx->stream>>>(p);
+
+  // ---- large scenes: per-frame direction grids, then the kernel streams cell lists ----
+  bool use_grid = n > 0 && (ctx->opt_rt_grid == 1 || (ctx->opt_rt_grid == 0 && n >= RT_GRID_AUTO_TRIS));
+  if (use_grid) {
+    const size_t cells = (size_t)grid.x * grid.y + (size_t)f.n_lights * 6 * RT_GRID_FACE;
+    const size_t scan_tmp = cells / 4096 + 2;
+    ctx->rt_n_cells = cells; ctx->rt_n_cam_cells = (size_t)grid.x * grid.y;
+    if (int rc = ensure(ctx, ctx->rt_cells, sizeof(unsigned) * (4 * cells + 1 + scan_tmp))) return rc;
+    unsigned *cnt = (unsigned *)ctx->rt_cells.p, *cursor = cnt + cells, *padded = cursor + cells,
+             *off = padded + cells, *tmp = off + cells + 1;
+    RtGridParams g;
+    g.planes = (const float4 *)ctx->rt_planes.p;
+    g.origin_stride_f4 = origin_stride;
+    g.n_tris = n;
+    memcpy(g.R, f.R, sizeof g.R);
+    g.focal = f.focal;
+    g.W = f.W; g.H = f.H; g.row0 = f.row0; g.row1 = f.row1;
+    g.gx = (int)grid.x; g.gy = (int)grid.y;
+    g.n_lights = f.n_lights;
+    g.cell_cnt = cnt; g.cell_cursor = cursor; g.cell_off = off;
+    g.cell_rec = nullptr; g.cell_idx = nullptr; g.cap = 0;
+    CU_CHECK(ctx, cudaMemsetAsync(cnt, 0, sizeof(unsigned) * 2 * cells, ctx->stream));   // counts and cursors
+    const dim3 bgrid((n + 7) / 8, 1 + f.n_lights);
+    rt_grid_bin_kernel<false><<<bgrid, 256, 0, ctx->stream>>>(g);
+    rt_grid_pad_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(cnt, padded, (int)cells);
+    ctx->stats.kernel_launches += 2;
+    CU_CHECK(ctx, cudaGetLastError());
+    unsigned long long *dc = (unsigned long long *)ctx->counters.p;
+    if (int rc = scan_exclusive(ctx, padded, off, (int)cells, tmp, dc + 9)) return rc;
+    // the lists are sized from the scanned total: one small read-back
+    unsigned long long *hc = (unsigned long long *)ctx->pinned;
+    CU_CHECK(ctx, cudaMemcpyAsync(hc, dc + 9, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned long long total = hc[0];
+    if (total > RT_GRID_MAX_ENTRIES) {
+      use_grid = false;   // lists larger than the budget (huge triangles everywhere): stream the scene instead
+    } else {
+      if (int rc = ensure(ctx, ctx->rt_cell_rec, sizeof(float4) * RT_REC_F4 * (size_t)(total + 4))) return rc;
+      if (int rc = ensure(ctx, ctx->rt_cell_idx, sizeof(int) * (size_t)(total + 4))) return rc;
+      g.cell_rec = (float4 *)ctx->rt_cell_rec.p;
+      g.cell_idx = (int *)ctx->rt_cell_idx.p;
+      g.cap = total;
+      rt_grid_bin_kernel<true><<<bgrid, 256, 0, ctx->stream>>>(g);
+      ctx->stats.kernel_launches++;
+      CU_CHECK(ctx, cudaGetLastError());
+      p.cell_off = off; p.cell_cnt = cnt;
+      p.cell_rec = g.cell_rec; p.cell_idx = g.cell_idx;
+    }
+  }
+
+  if (use_grid) {
+    const size_t gsmem = smem + 2 * (size_t)RT_TILE * sizeof(int);
+    if (f.n_lights > 1)
+      rt_filtered_kernel<true, true><<<grid, RT_THREADS, gsmem, ctx->stream>>>(p);
+    else
+      rt_filtered_kernel<false, true><<<grid, RT_THREADS, gsmem, ctx->stream>>>(p);
+  } else {
+    if (f.n_lights > 1)
+      rt_filtered_kernel<true, false><<<grid, RT_THREADS, smem, ctx->stream>>>(p);
+    else
+      rt_filtered_kernel<false, false><<<grid, RT_THREADS, smem, ctx->stream>>>(p);
+  }
   ctx->stats.kernel_launches++;
   CU_CHECK(ctx, cudaGetLastError());
   return B200_OK;

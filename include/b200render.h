@@ -129,6 +129,10 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
  * output buffers are final only after one of those two calls returns.  The
  * host-pointer entries always work this way internally.  Results are identical. */
 #define B200_OPT_RAST_PIPELINED 4
+/* Raytracer direction grids (per-frame lists of the triangles each 16x16 pixel
+ * block and each cube-map cell around a light can see): 0 = automatic (scenes of
+ * 2048 triangles or more), 1 = always, 2 = never.  Results are identical. */
+#define B200_OPT_RT_GRID 5
 int b200_set_option(b200_ctx *ctx, int option, int value);
 
 /* Counters of the last render on this context (b200_get_stats synchronises). */

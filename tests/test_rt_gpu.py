@@ -29,6 +29,15 @@ def run_both(b200, renderer, tris, sph, W, H, focal, cam, R, lights, what, brute
     st = renderer.stats()
     check_equal(got, want, what + " [filtered]")
     assert st["primary_rays"] == want["primary"] and st["shadow_rays"] == want["shadow"]
+    # the same frame through the direction grids (automatic only for large scenes)
+    renderer.set_option(b200.OPT_RT_GRID, 1)
+    try:
+        got_g = renderer.render_raytrace(tris, sph, c, lights)
+        st_g = renderer.stats()
+    finally:
+        renderer.set_option(b200.OPT_RT_GRID, 0)
+    check_equal(got_g, want, what + " [filtered, grids]")
+    assert st_g["shadow_rays"] == want["shadow"]
     if brute:
         renderer.set_option(b200.OPT_RT_BRUTEFORCE, 1)
         got2 = renderer.render_raytrace(tris, sph, c, lights)
@@ -145,3 +154,47 @@ def test_invalid_arguments(b200, renderer, cornell_rt):
         renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS, 5, 40)
     with pytest.raises(b200.B200Error):
         renderer.render_raytrace(tris, sph, c, [((0, 0, 0, 1), (1, 1, 1))] * 9)
+
+
+def test_grid_tessellated_scene(b200, renderer):
+    """BASELINE config 5's generator at a size the oracle finishes in seconds: large enough
+    for the direction grids to switch on by themselves."""
+    tris, sph = b200.scene_cornell_rt_tessellated(10)        # 2800 triangles
+    assert len(tris) == 2800
+    _, _, st = run_both(b200, renderer, tris, sph, 150, 110, 75.0, h.f32(0, 0, -3, 1), h.identity_R(),
+                        h.DEFAULT_RT_LIGHTS, "tessellated 2800", brute=False)
+    # with the lists the kernel launches next to the binning kernels; without them only prep + render
+    assert st["kernel_launches"] >= 7
+    run_both(b200, renderer, tris, sph, 97, 61, 50.0, h.f32(0.2, -0.1, -0.7, 1), h.yaw_R(-0.6),
+             [((0.3, -0.6, -0.2, 1), (9, 9, 9)), ((-0.4, 0.5, -0.9, 1), (4, 5, 6))], "tessellated, inside, 2 lights",
+             brute=False)
+
+
+def test_grid_distance_ties_go_to_the_lowest_index(b200, renderer, cornell_rt):
+    """Coincident copies of every triangle with different colours: equal distances, and the
+    reference keeps the first (strict `<`, skeleton.cpp:313).  The grid lists are unordered."""
+    tris, sph = cornell_rt
+    dup = np.concatenate([tris, tris, tris]).copy()
+    dup["color"][len(tris):2 * len(tris)] = (0.9, 0.1, 0.9)
+    dup["color"][2 * len(tris):] = (0.1, 0.9, 0.1)
+    got, want, _ = run_both(b200, renderer, dup, sph, 90, 70, 60.0, h.f32(0, 0, -3, 1), h.identity_R(),
+                            h.DEFAULT_RT_LIGHTS, "coincident triangles")
+    assert got["index"].max() < len(tris)
+
+
+def test_grid_full_size_matches_streaming_kernel(b200, renderer):
+    """BASELINE config 5 geometry (100 800 triangles) on a 480x270 frame: the grid kernel
+    against the scene-streaming kernel (itself checked against the oracle above)."""
+    tris, sph = b200.scene_cornell_rt_tessellated(60)
+    c = b200.make_camera(h.f32(0, 0, -3, 1), 192.0, h.identity_R(), 480, 270)
+    renderer.set_option(b200.OPT_RT_GRID, 2)
+    try:
+        a = renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
+        sa = renderer.stats()
+    finally:
+        renderer.set_option(b200.OPT_RT_GRID, 0)
+    b = renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
+    sb = renderer.stats()
+    for k in ("rgb", "depth", "index"):
+        assert np.array_equal(a[k], b[k]), k
+    assert sa["shadow_rays"] == sb["shadow_rays"] and sb["kernel_launches"] > sa["kernel_launches"]
