@@ -442,8 +442,54 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
       wh[c] = 0.5f * (wu - wl) * 1.0001f + 1e-7f * fmaxf(fabsf(wl), fabsf(wu));
     }
     if (!active) { pnorm = 0.f; pc[0] = pc[1] = pc[2] = 0.f; ph[0] = ph[1] = ph[2] = 0.f; }
-    const float wnorm = warp_max(pnorm) * 1.0001f;
+    float wnorm = warp_max(pnorm) * 1.0001f;
     pnorm *= 1.0001f;
+    // GRID (large scenes): a patch that straddles a silhouette has hits on two surfaces and
+    // one box around both sweeps everything in between.  Split the bundle across the middle
+    // of the box's longest axis and keep a tight box around each half.
+    float wc2[3] = {0.f, 0.f, 0.f}, wh2[3] = {0.f, 0.f, 0.f}, wnorm2 = 0.f;
+    bool two = false;
+    if (GRID && warp_active) {
+      const int ax = (wh[0] >= wh[1] && wh[0] >= wh[2]) ? 0 : (wh[1] >= wh[2] ? 1 : 2);
+      const float mid = ax == 0 ? wc[0] : (ax == 1 ? wc[1] : wc[2]);
+      float alo[3] = {INFINITY, INFINITY, INFINITY}, ahi[3] = {-INFINITY, -INFINITY, -INFINITY};
+      float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        if ((active >> k) & 1u) {
+          const float g[3] = {-xsub(Lx, xadd(cx, xmul(ht[k], dxs[k / 3]))), -xsub(Ly, xadd(cy, xmul(ht[k], dys[k % 3]))),
+                              -xsub(Lz, xadd(cz, xmul(ht[k], dz)))};
+          const bool in_a = (ax == 0 ? g[0] : (ax == 1 ? g[1] : g[2])) < mid;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (in_a) { alo[c] = fminf(alo[c], g[c]); ahi[c] = fmaxf(ahi[c], g[c]); }
+            else { blo[c] = fminf(blo[c], g[c]); bhi[c] = fmaxf(bhi[c], g[c]); }
+          }
+        }
+      }
+      float na = 0.f, nb = 0.f;
+      bool has_a = true, has_b = true;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float al = warp_min(alo[c]), au = warp_max(ahi[c]), bl = warp_min(blo[c]), bu = warp_max(bhi[c]);
+        has_a = has_a && au >= al; has_b = has_b && bu >= bl;
+        alo[c] = al; ahi[c] = au; blo[c] = bl; bhi[c] = bu;
+      }
+      if (has_a && has_b) {
+        two = true;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          wc[c] = 0.5f * (alo[c] + ahi[c]);
+          wh[c] = 0.5f * (ahi[c] - alo[c]) * 1.0001f + 1e-7f * fmaxf(fabsf(alo[c]), fabsf(ahi[c]));
+          na = fmaxf(na, fmaxf(fabsf(alo[c]), fabsf(ahi[c])));
+          wc2[c] = 0.5f * (blo[c] + bhi[c]);
+          wh2[c] = 0.5f * (bhi[c] - blo[c]) * 1.0001f + 1e-7f * fmaxf(fabsf(blo[c]), fabsf(bhi[c]));
+          nb = fmaxf(nb, fmaxf(fabsf(blo[c]), fabsf(bhi[c])));
+        }
+        wnorm = na * 1.0001f;
+        wnorm2 = nb * 1.0001f;
+      }
+    }
 
     const float4 *src = p.planes + (size_t)(1 + l) * origin_stride;
     // the buffer about to be refilled last held the tile before the previous
@@ -510,6 +556,12 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
           const float mN = fmaf(nx, wc[0], fmaf(ny, wc[1], nz * wc[2])) +
                            fmaf(fabsf(nx), wh[0], fmaf(fabsf(ny), wh[1], fabsf(nz) * wh[2]));
           pass = rt_box_may_hit_light(q0, q1, q2, wc, wh, Eg) && !(mN + 1.1f * Eg < q2.z);
+          if (GRID && two && !pass) {
+            const float Eg2 = q2.y * wnorm2;
+            const float mN2 = fmaf(nx, wc2[0], fmaf(ny, wc2[1], nz * wc2[2])) +
+                              fmaf(fabsf(nx), wh2[0], fmaf(fabsf(ny), wh2[1], fabsf(nz) * wh2[2]));
+            pass = rt_box_may_hit_light(q0, q1, q2, wc2, wh2, Eg2) && !(mN2 + 1.1f * Eg2 < q2.z);
+          }
         }
         unsigned mask = __ballot_sync(0xffffffffu, pass);
         // ---- L1: the pixel's own bundle box against every survivor ----
