@@ -38,6 +38,17 @@ static int ensure_pinned(b200_ctx *ctx, size_t bytes) {
   return B200_OK;
 }
 
+int band_slice_done(b200_ctx *ctx, int a, int b) {
+  if (!ctx->slice_host || b <= a) return B200_OK;
+  cudaEvent_t ev = ctx->ev_slice[ctx->slice_n++ % B200_SLICES];
+  CU_CHECK(ctx, cudaEventRecord(ev, ctx->stream));
+  CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->slice_host + (size_t)(a - ctx->slice_row0) * ctx->slice_w,
+                                ctx->slice_dev + (size_t)a * ctx->slice_w, (size_t)(b - a) * ctx->slice_w * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, ctx->copy_stream));
+  return B200_OK;
+}
+
 extern "C" {
 
 int b200_init(int device, b200_ctx **out) {
@@ -52,6 +63,12 @@ int b200_init(int device, b200_ctx **out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_slice[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_slice[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_slice[2], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_slice[3], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     delete ctx;
     return B200_ECUDA;
@@ -78,6 +95,9 @@ void b200_destroy(b200_ctx *ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->ev_copied);
+  for (int i = 0; i < B200_SLICES; ++i) cudaEventDestroy(ctx->ev_slice[i]);
+  cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -118,7 +138,7 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
       ctx->rast_spec.valid = 0;
       return B200_OK;
     case B200_OPT_RAST_TILE_LOG2:
-      if (value < 3 || value > 6) return ctx_fail(ctx, B200_EINVAL, "tile log2 must be 3..6");
+      if (value < 3 || value > 5) return ctx_fail(ctx, B200_EINVAL, "tile log2 must be 3..5");
       ctx->opt_rast_tile_log2 = value;
       return B200_OK;
   }
@@ -266,6 +286,19 @@ static int finish_stats(b200_ctx *ctx) {
   return B200_OK;
 }
 
+// ---- sliced return of the packed framebuffer (see b200_ctx::copy_stream) ------------------
+static void band_slices_begin(b200_ctx *ctx, uint32_t *host_row0, const uint32_t *dev_frame, int row0, int width) {
+  ctx->slice_host = host_row0; ctx->slice_dev = dev_frame; ctx->slice_row0 = row0; ctx->slice_w = width;
+  ctx->slice_n = 0;
+}
+// every slice copy is ordered before whatever is enqueued on ctx->stream next
+static int band_slices_end(b200_ctx *ctx) {
+  ctx->slice_host = nullptr;
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+  CU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+  return B200_OK;
+}
+
 static int copy_out(b200_ctx *ctx, void *host, const void *dev, size_t bytes) {
   if (!host) return B200_OK;
   CU_CHECK(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -313,11 +346,33 @@ int draw_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const
   if (int rc = rt_upload_scene(ctx, tris, n_tris, spheres, n_spheres)) return rc;
   const size_t npix = (size_t)cam->width * cam->height;
   if (int rc = ensure(ctx, ctx->out_argb, npix * sizeof(uint32_t))) return rc;
-  if (int rc = rt_render_device(ctx, cam, lights, n_lights, row_begin, row_end, nullptr, nullptr, nullptr,
-                                (uint32_t *)ctx->out_argb.p))
-    return rc;
-  const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
-  if (int rc = copy_out(ctx, argb_out, (uint32_t *)ctx->out_argb.p + off, cnt * sizeof(uint32_t))) return rc;
+  RtFrame f;
+  if (int rc = fill_frame(ctx, cam, lights, n_lights, row_begin, row_end, f)) return rc;
+  if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // the counters are shared
+  ctx->stats.kernel_launches = 0;
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  // Large frames are rendered in slices of whole 16-row blocks so that the copy of one slice to
+  // the host overlaps the rendering of the next (scenes with per-frame grids: one slice, the
+  // grids are built per launch).
+  const int rows = row_end - row_begin;
+  const bool gridded = ctx->opt_rt_grid == 1 || (ctx->opt_rt_grid == 0 && n_tris >= 2048);
+  const int k = (!gridded && (size_t)rows * cam->width >= ((size_t)1 << 20)) ? B200_SLICES : 1;
+  band_slices_begin(ctx, argb_out, (const uint32_t *)ctx->out_argb.p, row_begin, cam->width);
+  for (int i = 0; i < k; ++i) {
+    RtFrame fi = f;
+    fi.row0 = band_slice_edge(row_begin, rows, i, k, 16);
+    fi.row1 = band_slice_edge(row_begin, rows, i + 1, k, 16);
+    if (fi.row1 <= fi.row0) continue;
+    if (int rc = rt_launch(ctx, fi, nullptr, nullptr, nullptr, (uint32_t *)ctx->out_argb.p)) { ctx->slice_host = nullptr; return rc; }
+    if (i + 1 == k) CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if (int rc = band_slice_done(ctx, fi.row0, fi.row1)) { ctx->slice_host = nullptr; return rc; }
+  }
+  if (rows <= 0) CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  if (int rc = band_slices_end(ctx)) return rc;
+  ctx->stats.primary_rays = (uint64_t)f.W * (uint64_t)rows * 9u;
+  if (int rc = enqueue_counter_readback(ctx)) return rc;
+  ctx->pending = 1;
   return finish_stats(ctx);
 }
 
@@ -533,13 +588,20 @@ int draw_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room, const
   if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
   if (int rc = raster_host_outputs(ctx, cam, nullptr, nullptr, nullptr, argb_out)) return rc;
   if (int rc = rast_check_frame_args(ctx, cam, light, row_begin, row_end)) return rc;
-  if (int rc = rast_frame(ctx, true, cam, light, row_begin, row_end, nullptr, nullptr, nullptr,
-                          (uint32_t *)ctx->out_argb.p, true))
-    return rc;
-  if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;
-  const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
-  if (int rc = copy_out(ctx, argb_out, (uint32_t *)ctx->out_argb.p + off, cnt * sizeof(uint32_t))) return rc;
-  return finish_stats(ctx);
+  // the packed rows leave for the host slice by slice while the next slice is resolved
+  band_slices_begin(ctx, argb_out, (const uint32_t *)ctx->out_argb.p, row_begin, cam->width);
+  const int rc_frame = rast_frame(ctx, true, cam, light, row_begin, row_end, nullptr, nullptr, nullptr,
+                                  (uint32_t *)ctx->out_argb.p, true);
+  if (int rc = band_slices_end(ctx)) return rc;
+  if (rc_frame) return rc_frame;
+  const uint64_t twice = ctx->stats.respeculated;
+  if (int rc = finish_stats(ctx)) return rc;     // verifies a pipelined frame; renders it again if it outgrew its guess
+  if (ctx->stats.respeculated != twice) {        // ... in which case the rows copied so far were not final
+    const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
+    if (int rc = copy_out(ctx, argb_out, (uint32_t *)ctx->out_argb.p + off, cnt * sizeof(uint32_t))) return rc;
+    return finish_stats(ctx);
+  }
+  return B200_OK;
 }
 
 int draw_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes, int n_boxes,

@@ -62,6 +62,7 @@ __host__ __device__ __forceinline__ uint32_t put_pixel_argb(float r, float g, fl
 }
 
 // ---- context -------------------------------------------------------------------
+#define B200_SLICES 4
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
@@ -72,6 +73,13 @@ struct b200_ctx {
   cudaStream_t stream = nullptr;      // where work is enqueued (own_stream unless overridden)
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // Host-pointer entries return the packed framebuffer in slices: while the kernels render
+  // slice i + 1, slice i travels to the host on a second stream (band_begin .. band_slice_done).
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_slice[B200_SLICES] = {}, ev_copied = nullptr;
+  uint32_t *slice_host = nullptr;       // destination of row `slice_row0`; null = no sliced copy in progress
+  const uint32_t *slice_dev = nullptr;  // device frame (full-frame addressing)
+  int slice_row0 = 0, slice_w = 0, slice_n = 0;
   std::string err;
   b200_stats stats{};
   int opt_rt_bruteforce = 0;
@@ -162,5 +170,13 @@ static inline unsigned long long rast_spec_cap(unsigned long long seen) { return
 int scan_exclusive(b200_ctx *ctx, const unsigned *counts, unsigned *offs, int n, unsigned *tmp,
                    unsigned long long *total_out);   // rast_geom.cu; tmp: n / 4096 + 2 words
 int rt_prepare_scene(b200_ctx *ctx);
+// rows [a, b) of the packed frame are final on ctx->stream: start their copy to the host (no-op unless sliced)
+int band_slice_done(b200_ctx *ctx, int a, int b);
+// slice boundaries of a band of `rows` rows split k ways on multiples of `align` rows
+static inline int band_slice_edge(int row0, int rows, int i, int k, int align) {
+  if (i >= k) return row0 + rows;
+  const int e = (int)((long long)rows * i / k) / align * align;
+  return row0 + e;
+}
 int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int32_t *d_index,
               uint32_t *d_argb);

@@ -773,12 +773,19 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
       rast_scatter_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
     }
-    if (row1 > row0) {
-      dim3 rg((W + RS_W - 1) / RS_W, (row1 - row0 + RS_H - 1) / RS_H);
+    // host-pointer entries: resolve in slices, each slice's packed rows leave for the host
+    // while the next one is resolved (band_slice_done is a no-op otherwise)
+    const int k = (ctx->slice_host && (size_t)(row1 - row0) * W >= ((size_t)1 << 20)) ? B200_SLICES : 1;
+    for (int i = 0; i < k; ++i) {
+      p.row0 = band_slice_edge(row0, row1 - row0, i, k, RS_H);
+      p.row1 = band_slice_edge(row0, row1 - row0, i + 1, k, RS_H);
+      if (p.row1 <= p.row0) continue;
+      dim3 rg((W + RS_W - 1) / RS_W, (p.row1 - p.row0 + RS_H - 1) / RS_H);
       rast_resolve_kernel<<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
+      CU_CHECK(ctx, cudaGetLastError());
+      if (int rc = band_slice_done(ctx, p.row0, p.row1)) return rc;
     }
-    CU_CHECK(ctx, cudaGetLastError());
     return B200_OK;
   }
 
@@ -843,11 +850,16 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   }
   ctx->stats.kernel_launches++;
   CU_CHECK(ctx, cudaGetLastError());
-  if (row1 > row0) {
-    dim3 pb(32, 8), pg((W + 31) / 32, (row1 - row0 + 7) / 8);
+  const int k = (ctx->slice_host && (size_t)(row1 - row0) * W >= ((size_t)1 << 20)) ? B200_SLICES : 1;
+  for (int i = 0; i < k; ++i) {
+    p.row0 = band_slice_edge(row0, row1 - row0, i, k, 8);
+    p.row1 = band_slice_edge(row0, row1 - row0, i + 1, k, 8);
+    if (p.row1 <= p.row0) continue;
+    dim3 pb(32, 8), pg((W + 31) / 32, (p.row1 - p.row0 + 7) / 8);
     rast_post_kernel<<<pg, pb, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     CU_CHECK(ctx, cudaGetLastError());
+    if (int rc = band_slice_done(ctx, p.row0, p.row1)) return rc;
   }
   return B200_OK;
 }

@@ -115,7 +115,7 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
  * unfiltered kernel that runs the reference arithmetic on every ray/triangle
  * pair (on-device cross-check of the filtered kernel; results are identical). */
 #define B200_OPT_RT_BRUTEFORCE 1
-#define B200_OPT_RAST_TILE_LOG2 2
+#define B200_OPT_RAST_TILE_LOG2 2   /* ordered-tile path: log2 of the screen-tile edge, 3..5 (default 5) */
 /* Rasteriser strategy: 0 = automatic, 1 = ordered screen tiles (any list; keeps
  * the intermediate buffers readable), 2 = atomic scatter + fused resolve
  * (lists without shadow-volume triangles only).  Results are identical. */

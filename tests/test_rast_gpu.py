@@ -41,7 +41,7 @@ def compare(b200, renderer, W, H, focal, light_cam, light, clipped, what, tiles=
             assert np.array_equal(bits(buf[key]), bits(want[key])), f"{tag}: {key}"
         assert np.array_equal(bits(got["rgb"]), bits(want["rgb"])), f"{tag}: final colour"
         assert st["fragments"] == want["fragments"], f"{tag}: fragments {st['fragments']} vs {want['fragments']}"
-    renderer.set_option(b200.OPT_RAST_TILE_LOG2, 4)
+    renderer.set_option(b200.OPT_RAST_TILE_LOG2, 5)
     renderer.set_option(b200.OPT_RAST_PATH, 0)
     return want
 
@@ -355,3 +355,23 @@ def test_pipelined_clipped_lists_and_soup(b200, renderer):
             assert np.array_equal(bits(rgb.cpu().numpy()), bits(want["rgb"])), z
     finally:
         renderer.set_option(b200.OPT_RAST_PIPELINED, 0)
+
+
+def test_sliced_framebuffer_return(b200, renderer):
+    """draw_raster(_band) returns megapixel frames in slices that overlap the resolve / post pass:
+    both strategies, against the quantised float frame of the plain path."""
+    room, boxes = b200.scene_cornell_rast()
+    W, H, f = 1296, 1000, 700.0
+    cam = b200.make_camera(h.DEFAULT_RAST_CAM, f, h.identity_R(), W, H)
+    L = b200.make_rast_light(h.DEFAULT_RAST_LIGHT["pos"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
+    for scene in ((room, boxes), (room, np.zeros(0, h.RAST_TRI))):     # ordered tiles / scatter-resolve
+        want = b200.quantise(renderer.render_raster(scene[0], scene[1], cam, L, want=("rgb",))["rgb"])
+        want[0] = want[-1] = 0      # the post pass never reaches the one-pixel border (:283): the cleared
+        want[:, 0] = want[:, -1] = 0  # surface's 0 stays, not PutPixelSDL's 0x80000000
+        for frame in range(2):                                          # second frame: pipelined
+            got = renderer.draw_raster(scene[0], scene[1], cam, L)
+            bad = np.argwhere(got != want)
+            assert len(bad) == 0, f"boxes={len(scene[1])} frame {frame}: {len(bad)} px differ, rows {bad[:, 0].min()}..{bad[:, 0].max()}, first {bad[0]}: {got[tuple(bad[0])]:#x} vs {want[tuple(bad[0])]:#x}"
+        band = np.zeros((H - 203, W), np.uint32)
+        renderer.draw_raster_band(scene[0], scene[1], cam, L, 3, H - 200, band.ctypes.data)
+        assert np.array_equal(band, want[3:H - 200])

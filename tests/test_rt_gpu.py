@@ -198,3 +198,17 @@ def test_grid_full_size_matches_streaming_kernel(b200, renderer):
     for k in ("rgb", "depth", "index"):
         assert np.array_equal(a[k], b[k]), k
     assert sa["shadow_rays"] == sb["shadow_rays"] and sb["kernel_launches"] > sa["kernel_launches"]
+
+
+def test_sliced_framebuffer_return(b200, renderer, cornell_rt):
+    """Frames of a megapixel or more come back from draw_raytrace(_band) in slices that overlap
+    the rendering; the packed frame must equal the quantised float frame of the plain path."""
+    tris, sph = cornell_rt
+    W, H = 1296, 1000       # not a multiple of the 16-row blocks
+    c = b200.make_camera(h.f32(0, 0, -3, 1), 640.0, h.identity_R(), W, H)
+    want = b200.quantise(renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS, want=("rgb",))["rgb"])
+    got = renderer.draw_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
+    assert np.array_equal(got, want)
+    band = np.zeros((H - 37 - 100, W), np.uint32)
+    renderer.draw_raytrace_band(tris, sph, c, h.DEFAULT_RT_LIGHTS, 37, H - 100, band.ctypes.data)
+    assert np.array_equal(band, want[37:H - 100])
