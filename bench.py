@@ -385,8 +385,18 @@ def run_b200_one(args, workload):
         cam = b200.make_camera(RT_CAM, focal, h.identity_R(), W, H)
         r.rt_upload_scene(tris, sph)
 
+        # N > 1 with the peer-mapped frame: the ranks share the frame by interleaved 16-row blocks
+        # (better balanced than contiguous bands); each stores its blocks straight into rank 0's frame
+        interleaved = world > 1 and gather == "p2p_store"
+        if interleaved:
+            r.set_option(b200.OPT_RT_INTERLEAVE_N, world)
+            r.set_option(b200.OPT_RT_INTERLEAVE_R, rank)
+
         def step():
-            r.rt_render_device(cam, RT_LIGHTS, row0, row1, p_rgb, p_depth)
+            if interleaved:
+                r.rt_render_device(cam, RT_LIGHTS, 0, H, p_rgb, p_depth)
+            else:
+                r.rt_render_device(cam, RT_LIGHTS, row0, row1, p_rgb, p_depth)
             exchange()
 
         tris_pin = torch.from_numpy(tris.view(np.uint8).copy()).pin_memory()
@@ -479,7 +489,9 @@ def run_b200_one(args, workload):
                     "exact_evals": st["exact_evals"]}
         config = {"workload": workload, "width": W, "height": H, "focal": focal, "spp": 9,
                   "triangles": int(len(tris)), "spheres": int(len(sph)), "lights": len(RT_LIGHTS),
-                  "rays_per_frame": rays, "parallelism": f"row bands x{world}", "gather": gather, "gather_note": gather_note,
+                  "rays_per_frame": rays,
+                  "parallelism": (f"interleaved 16-row blocks x{world}" if world > 1 and gather == "p2p_store" else f"row bands x{world}"),
+                  "gather": gather, "gather_note": gather_note,
                   "l2": "flushed between timed steps (256 MiB write); outputs 133 MB > L2"}
     else:
         frames = 1.0

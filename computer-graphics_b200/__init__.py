@@ -26,6 +26,8 @@ OPT_RAST_TILE_LOG2 = 2
 OPT_RAST_PATH = 3
 OPT_RAST_PIPELINED = 4
 OPT_RT_GRID = 5
+OPT_RT_INTERLEAVE_N = 6
+OPT_RT_INTERLEAVE_R = 7
 
 RT_TRI = np.dtype([("v0", "<f4", 4), ("v1", "<f4", 4), ("v2", "<f4", 4),
                    ("normal", "<f4", 4), ("color", "<f4", 3)])

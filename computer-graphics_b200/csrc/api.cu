@@ -129,6 +129,15 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
       if (value < 0 || value > 2) return ctx_fail(ctx, B200_EINVAL, "raster path must be 0, 1 or 2");
       ctx->opt_rast_path = value;
       return B200_OK;
+    case B200_OPT_RT_INTERLEAVE_N:
+      if (value < 1 || value > 4096) return ctx_fail(ctx, B200_EINVAL, "interleave count must be 1..4096");
+      ctx->opt_rt_il_n = value;
+      if (ctx->opt_rt_il_r >= value) ctx->opt_rt_il_r = 0;
+      return B200_OK;
+    case B200_OPT_RT_INTERLEAVE_R:
+      if (value < 0 || value >= ctx->opt_rt_il_n) return ctx_fail(ctx, B200_EINVAL, "interleave index must be below the count");
+      ctx->opt_rt_il_r = value;
+      return B200_OK;
     case B200_OPT_RT_GRID:
       if (value < 0 || value > 2) return ctx_fail(ctx, B200_EINVAL, "grid mode must be 0, 1 or 2");
       ctx->opt_rt_grid = value;
@@ -206,6 +215,7 @@ static int fill_frame(b200_ctx *ctx, const camera_t *cam, const light_t *lights,
   f.focal = cam->focal;
   memcpy(f.R, cam->R, sizeof f.R);
   f.W = cam->width; f.H = cam->height; f.row0 = row0; f.row1 = row1;
+  f.il_n = 1; f.il_r = 0;
   f.n_lights = n_lights;
   memset(f.lights, 0, sizeof f.lights);
   for (int l = 0; l < n_lights; ++l) {
@@ -223,12 +233,16 @@ int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, 
   if (int rc = fill_frame(ctx, cam, lights, n_lights, row_begin, row_end, f)) return rc;
   cudaSetDevice(ctx->device);
   if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // the counters are shared
+  f.il_n = ctx->opt_rt_il_n; f.il_r = ctx->opt_rt_il_r;
   ctx->stats.kernel_launches = 0;
   CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (int rc = rt_launch(ctx, f, d_rgb, d_depth, d_index, d_argb)) return rc;
   CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->stats.primary_rays = (uint64_t)f.W * (uint64_t)(row_end - row_begin) * 9u;
+  uint64_t my_rows = 0;   // rows of this context's 16-row blocks
+  for (int b = f.il_r; b * 16 < row_end - row_begin; b += f.il_n)
+    my_rows += (uint64_t)((row_end - row_begin - b * 16) < 16 ? (row_end - row_begin - b * 16) : 16);
+  ctx->stats.primary_rays = (uint64_t)f.W * my_rows * 9u;
   if (int rc = enqueue_counter_readback(ctx)) return rc;
   ctx->pending = 1;
   return B200_OK;

@@ -95,6 +95,7 @@ struct b200_ctx {
   DevBuf rt_cells;    // direction grids: per-cell counts, cursors, padded counts, offsets, scan scratch
   DevBuf rt_cell_rec, rt_cell_idx;   // the cells' lists: plane records and triangle indices
   size_t rt_n_cells = 0, rt_n_cam_cells = 0;   // of the last gridded frame (diagnostics)
+  int opt_rt_il_n = 1, opt_rt_il_r = 0;        // row-block interleave of rt_render_device (see the header)
   int opt_rt_grid = 0;               // 0 auto (scenes of RT_GRID_AUTO_TRIS triangles or more), 1 always, 2 never
   int rt_n_tris = 0, rt_n_spheres = 0;
   float rt_world_abs = 0.f;   // max |coordinate| over the uploaded scene
@@ -156,6 +157,7 @@ struct RtFrame {
   float focal;
   float R[16];
   int W, H, row0, row1;
+  int il_n, il_r;      // this launch renders the 16-row blocks b of [row0, row1) with b % il_n == il_r
   int n_lights;
   float lights[8][7];  // pos[4], colour[3]
 };

@@ -7,6 +7,8 @@ struct RtKParams {
   float focal;
   float R[16];
   int W, H, row0, row1;
+  int il_n, il_r;            // 16-row block b of the range is rendered by the launch with b % il_n == il_r
+  int blocks_y;              // 16-row blocks in [row0, row1) (all of them, not only this launch's)
   int n_lights;
   float lights[B200_MAX_LIGHTS][7];
   const float4 *geom;        // 3 x float4 per triangle: v0, e1, e2

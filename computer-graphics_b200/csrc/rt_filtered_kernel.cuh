@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // warp = 8x4 pixel patch; 8 warps tile a 16x16 block as 2 columns x 4 rows
   const int u = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-  const int v = p.row0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+  const int block_y = blockIdx.y * p.il_n + p.il_r;     // 16-row block of the range (interleaved launches)
+  const int v = p.row0 + block_y * 16 + (warp >> 1) * 4 + (lane >> 3);
   const bool live = (u < p.W) && (v < p.row1);
   const size_t pid = (size_t)v * p.W + u;
   const size_t origin_stride = (size_t)((p.n_tris + RT_TILE - 1) / RT_TILE) * RT_TILE * RT_REC_F4;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
 
     RtCursor cursor = rt_cursor_scene(p.planes, p.n_tris);   // origin 0
     if (GRID) {
-      if (threadIdx.x == 0) s_cells[0] = blockIdx.y * gridDim.x + blockIdx.x;   // this block's own cell
+      if (threadIdx.x == 0) s_cells[0] = block_y * gridDim.x + blockIdx.x;   // this block's own cell
       __syncthreads();
       cursor = rt_cursor_cells(s_cells, 1);
     }
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
       for (int i = threadIdx.x; i < (1 << RT_GRID_TABLE_LOG2); i += RT_THREADS) s_table[i] = -1;
       if (threadIdx.x == 0) s_ncells = 0;
       __syncthreads();
-      const int cell_base = (int)(gridDim.x * gridDim.y) + l * 6 * RT_GRID_FACE;
+      const int cell_base = (int)gridDim.x * p.blocks_y + l * 6 * RT_GRID_FACE;
       int last = -2;
 #pragma unroll
       for (int k = 0; k < 9; ++k) {

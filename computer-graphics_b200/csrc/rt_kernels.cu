@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) rt_bruteforce_kernel(const __grid_constan
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // each warp owns an 8x4 pixel patch; a 128-thread block covers 16x8 pixels
   const int u = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-  const int v = p.row0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+  const int v = p.row0 + ((blockIdx.y >> 1) * p.il_n + p.il_r) * 16 + (blockIdx.y & 1) * 8 + (warp >> 1) * 4 + (lane >> 3);
   unsigned long long n_shadow = 0;
   if (u < p.W && v < p.row1) {
     // dir = R * vec4(u - W/2, v - H/2, f, 1)   (skeleton.cpp:126-128)
@@ -128,6 +128,7 @@ int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int
   p.focal = f.focal;
   memcpy(p.R, f.R, sizeof p.R);
   p.W = f.W; p.H = f.H; p.row0 = f.row0; p.row1 = f.row1;
+  p.il_n = f.il_n > 1 ? f.il_n : 1; p.il_r = f.il_n > 1 ? f.il_r : 0;
   p.n_lights = f.n_lights;
   memcpy(p.lights, f.lights, sizeof p.lights);
   p.geom = (const float4 *)ctx->rt_geom.p;
@@ -138,8 +139,11 @@ int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int
   p.counters = (unsigned long long *)ctx->counters.p;
   const int rows = f.row1 - f.row0;
   if (rows <= 0 || f.W <= 0) return B200_OK;
+  p.blocks_y = (rows + 15) / 16;
+  const int my_blocks = p.blocks_y > p.il_r ? (p.blocks_y - p.il_r + p.il_n - 1) / p.il_n : 0;   // this launch's 16-row blocks
+  if (my_blocks == 0) return B200_OK;
   if (ctx->opt_rt_bruteforce) {
-    dim3 grid((f.W + 15) / 16, (rows + 7) / 8);
+    dim3 grid((f.W + 15) / 16, 2 * my_blocks);
     rt_bruteforce_kernel<<<grid, 128, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     CU_CHECK(ctx, cudaGetLastError());
@@ -196,16 +200,16 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
     CU_CHECK(ctx, cudaGetLastError());
   }
 
-  const int rows = f.row1 - f.row0;
-  dim3 grid((f.W + 15) / 16, (rows + 15) / 16);
+  const int my_blocks = (p.blocks_y - p.il_r + p.il_n - 1) / p.il_n;
+  dim3 grid((f.W + 15) / 16, my_blocks);
   const size_t smem = 2 * (size_t)RT_TILE * RT_REC_F4 * sizeof(float4);
 
   // ---- large scenes: per-frame direction grids, then the kernel streams cell lists ----
   bool use_grid = n > 0 && (ctx->opt_rt_grid == 1 || (ctx->opt_rt_grid == 0 && n >= RT_GRID_AUTO_TRIS));
   if (use_grid) {
-    const size_t cells = (size_t)grid.x * grid.y + (size_t)f.n_lights * 6 * RT_GRID_FACE;
+    const size_t cells = (size_t)grid.x * p.blocks_y + (size_t)f.n_lights * 6 * RT_GRID_FACE;   // camera cells: every block of the range
     const size_t scan_tmp = cells / 4096 + 2;
-    ctx->rt_n_cells = cells; ctx->rt_n_cam_cells = (size_t)grid.x * grid.y;
+    ctx->rt_n_cells = cells; ctx->rt_n_cam_cells = (size_t)grid.x * p.blocks_y;
     if (int rc = ensure(ctx, ctx->rt_cells, sizeof(unsigned) * (4 * cells + 1 + scan_tmp))) return rc;
     unsigned *cnt = (unsigned *)ctx->rt_cells.p, *cursor = cnt + cells, *padded = cursor + cells,
              *off = padded + cells, *tmp = off + cells + 1;
@@ -216,7 +220,7 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
     memcpy(g.R, f.R, sizeof g.R);
     g.focal = f.focal;
     g.W = f.W; g.H = f.H; g.row0 = f.row0; g.row1 = f.row1;
-    g.gx = (int)grid.x; g.gy = (int)grid.y;
+    g.gx = (int)grid.x; g.gy = p.blocks_y;
     g.n_lights = f.n_lights;
     g.cell_cnt = cnt; g.cell_cursor = cursor; g.cell_off = off;
     g.cell_rec = nullptr; g.cell_idx = nullptr; g.cap = 0;

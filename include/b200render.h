@@ -133,6 +133,13 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
  * block and each cube-map cell around a light can see): 0 = automatic (scenes of
  * 2048 triangles or more), 1 = always, 2 = never.  Results are identical. */
 #define B200_OPT_RT_GRID 5
+/* Raytracer work split for N cooperating contexts (one per GPU) that render the SAME row
+ * range into one full-frame buffer: with INTERLEAVE_N = n > 1 and INTERLEAVE_R = r this
+ * context renders the 16-row blocks b of the range with b % n == r and leaves the others
+ * untouched, which balances the GPUs better than contiguous bands.  Device-pointer entry
+ * (rt_render_device) only; the default (1, 0) renders every row of the range. */
+#define B200_OPT_RT_INTERLEAVE_N 6
+#define B200_OPT_RT_INTERLEAVE_R 7
 int b200_set_option(b200_ctx *ctx, int option, int value);
 
 /* Counters of the last render on this context (b200_get_stats synchronises). */

@@ -212,3 +212,41 @@ def test_sliced_framebuffer_return(b200, renderer, cornell_rt):
     band = np.zeros((H - 37 - 100, W), np.uint32)
     renderer.draw_raytrace_band(tris, sph, c, h.DEFAULT_RT_LIGHTS, 37, H - 100, band.ctypes.data)
     assert np.array_equal(band, want[37:H - 100])
+
+
+@pytest.mark.parametrize("mode", ["filtered", "grids", "bruteforce"])
+def test_interleaved_blocks_tile_the_frame(b200, renderer, cornell_rt, mode):
+    """B200_OPT_RT_INTERLEAVE_N/R: n contexts (here one, three times) render the 16-row blocks
+    b % n == r of the same row range into one full-frame buffer; together they give the frame."""
+    import torch
+    tris, sph = cornell_rt
+    W, H = 150, 117                    # 8 blocks of 16 rows, the last one partial
+    c = b200.make_camera(h.f32(0, 0, -3, 1), 100.0, h.identity_R(), W, H)
+    renderer.set_option(b200.OPT_RT_BRUTEFORCE, 1 if mode == "bruteforce" else 0)
+    renderer.set_option(b200.OPT_RT_GRID, 1 if mode == "grids" else 2)
+    try:
+        full = renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
+        rays = renderer.stats()
+        renderer.rt_upload_scene(tris, sph)
+        for row0, row1 in ((0, H), (5, 101)):
+            rgb = torch.full((H, W, 3), float("nan"), device="cuda")
+            depth = torch.full((H, W), float("nan"), device="cuda")
+            index = torch.full((H, W), 12345, dtype=torch.int32, device="cuda")
+            primary = shadow = 0
+            for r in range(3):
+                renderer.set_option(b200.OPT_RT_INTERLEAVE_N, 3)
+                renderer.set_option(b200.OPT_RT_INTERLEAVE_R, r)
+                renderer.rt_render_device(c, h.DEFAULT_RT_LIGHTS, row0, row1, rgb.data_ptr(), depth.data_ptr(), index.data_ptr())
+                st = renderer.stats()
+                primary += st["primary_rays"]; shadow += st["shadow_rays"]
+            assert np.array_equal(bits(rgb.cpu().numpy()[row0:row1]), bits(full["rgb"][row0:row1]))
+            assert np.array_equal(bits(depth.cpu().numpy()[row0:row1]), bits(full["depth"][row0:row1]))
+            assert np.array_equal(index.cpu().numpy()[row0:row1], full["index"][row0:row1])
+            assert (index.cpu().numpy()[:row0] == 12345).all() and (index.cpu().numpy()[row1:] == 12345).all()
+            assert primary == W * (row1 - row0) * 9
+            if (row0, row1) == (0, H):
+                assert shadow == rays["shadow_rays"]
+    finally:
+        renderer.set_option(b200.OPT_RT_INTERLEAVE_N, 1)
+        renderer.set_option(b200.OPT_RT_BRUTEFORCE, 0)
+        renderer.set_option(b200.OPT_RT_GRID, 0)
