@@ -62,6 +62,7 @@ int b200_init(int device, b200_ctx **out) {
   ctx->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  ctx->timeline = getenv("B200_TIMELINE") != nullptr;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) != cudaSuccess ||
@@ -281,6 +282,14 @@ static int finish_stats(b200_ctx *ctx) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->stats.gpu_ms = ms;
+  if (ctx->timeline && ctx->pending == 2 && ctx->tl_n > 1) {
+    for (int i = 1; i < ctx->tl_n; ++i) {
+      float d = 0.f;
+      cudaEventElapsedTime(&d, ctx->tl_ev[i - 1], ctx->tl_ev[i]);
+      fprintf(stderr, "[b200 timeline] %-28s %8.1f us\n", ctx->tl_name[i], d * 1000.f);
+    }
+    fprintf(stderr, "[b200 timeline] frame %.1f us\n", ms * 1000.f);
+  }
   if (ctx->pending == 1) {
     ctx->stats.shadow_rays = c[0];
     ctx->stats.exact_evals = c[1];
@@ -483,6 +492,8 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
   ctx->stats.kernel_launches = 0;
   CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  ctx->tl_n = 0;
+  tl_mark(ctx, "frame start");
   rast_light_t lc = *light;
   if (whole_draw) {
     if (int rc = rast_geometry(ctx, cam, light, &lc, spec)) return rc;

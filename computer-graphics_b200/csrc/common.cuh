@@ -137,6 +137,10 @@ struct b200_ctx {
 
   // outputs / staging (device) used by the host-pointer entry points
   DevBuf out_rgb, out_depth, out_index, out_argb;
+  // diagnostics (environment B200_TIMELINE=1): an event after every launch, printed by finish_stats
+  int timeline = 0, tl_n = 0;
+  cudaEvent_t tl_ev[64] = {};
+  const char *tl_name[64] = {};
   DevBuf counters;    // unsigned long long[8]
   void *pinned = nullptr;
   size_t pinned_cap = 0;
@@ -172,6 +176,12 @@ static inline unsigned long long rast_spec_cap(unsigned long long seen) { return
 int scan_exclusive(b200_ctx *ctx, const unsigned *counts, unsigned *offs, int n, unsigned *tmp,
                    unsigned long long *total_out);   // rast_geom.cu; tmp: n / 4096 + 2 words
 int rt_prepare_scene(b200_ctx *ctx);
+static inline void tl_mark(b200_ctx *ctx, const char *name) {
+  if (!ctx->timeline || ctx->tl_n >= 64) return;
+  if (!ctx->tl_ev[ctx->tl_n]) cudaEventCreate(&ctx->tl_ev[ctx->tl_n]);
+  cudaEventRecord(ctx->tl_ev[ctx->tl_n], ctx->stream);
+  ctx->tl_name[ctx->tl_n++] = name;
+}
 // rows [a, b) of the packed frame are final on ctx->stream: start their copy to the host (no-op unless sliced)
 int band_slice_done(b200_ctx *ctx, int a, int b);
 // slice boundaries of a band of `rows` rows split k ways on multiples of `align` rows

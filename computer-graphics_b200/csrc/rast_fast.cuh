@@ -39,8 +39,8 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
       const int y = s.row0 + r;
       float4 A, B;
       rast_row_record<true>(s, y, A, B);
-      p.rowsA[s.row_off + r] = A;      // kept for the resolve pass: the winner's fragment is
-      p.rowsB[s.row_off + r] = B;      // re-derived from its row record
+      __stcs(p.rowsA + s.row_off + r, A);   // kept for the resolve pass (the winner's fragment is re-derived
+      __stcs(p.rowsB + s.row_off + r, B);   // from its row record); streaming stores: the keys should stay in L2
       const int lx = __float_as_int(A.x), rx = __float_as_int(A.y);
       const int x0 = max(lx, 0), x1 = min(rx, p.W);      // right end excluded (:504); bounds (:573)
       unsigned long long *row = p.keys + (size_t)y * p.W;

@@ -363,6 +363,7 @@ int scan_exclusive(b200_ctx *ctx, const unsigned *counts, unsigned *offs, int n,
   scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(tmp, nb);
   scan_apply_kernel<<<nb, SCAN_THREADS, 0, ctx->stream>>>(counts, n, tmp, nb, offs, total_out);
   ctx->stats.kernel_launches += 3;
+  tl_mark(ctx, "scan_apply_kernel");
   CU_CHECK(ctx, cudaGetLastError());
   return B200_OK;
 }
@@ -402,6 +403,7 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
   if (n_pre > 0) {
     rast_geom_kernel<false><<<(n_pre + 127) / 128, 128, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
+    tl_mark(ctx, "rast_geom_kernel");
     CU_CHECK(ctx, cudaGetLastError());
     unsigned long long *dc = (unsigned long long *)ctx->counters.p;
     if (int rc = scan_exclusive(ctx, p.counts, p.offs, n_pre, p.offs + (n_pre + 1), dc + 8)) return rc;
@@ -428,6 +430,7 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
   if (total > 0) {
     rast_geom_kernel<true><<<(n_pre + 127) / 128, 128, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
+    tl_mark(ctx, "rast_geom_kernel");
     CU_CHECK(ctx, cudaGetLastError());
   }
   ctx->rast_n_tris = (int)total;

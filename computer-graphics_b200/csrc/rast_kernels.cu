@@ -241,7 +241,11 @@ __device__ __forceinline__ int edge_py(const RastEdge &e, int i) {
 
 // Smallest i in [0, n] with (up ? y(i) >= Y : y(i) <= Y); y(i) is monotone in i.
 __device__ __forceinline__ int edge_first(const RastEdge &e, int Y, bool up) {
-  float est = ceilf(__fdividef((float)(Y - e.ay), e.sy));   // an estimate: the loops below make it exact
+  // An estimate from the real-number condition; the loops below make it exact in the
+  // reference's float arithmetic.  up: a + s*i >= Y  <=>  i >= (Y - a)/s.
+  // down (s < 0): floor(a + s*i) <= Y  <=>  a + s*i < Y + 1  <=>  i > (Y + 1 - a)/s.
+  const float est = up ? ceilf(__fdividef((float)(Y - e.ay), e.sy))
+                       : floorf(__fdividef((float)(Y + 1 - e.ay), e.sy)) + 1.0f;
   int i = est >= 0.f ? (est <= (float)e.n ? (int)est : e.n) : 0;   // NaN -> 0
   if (up) {
     while (i > 0 && edge_py(e, i - 1) >= Y) --i;
@@ -432,6 +436,7 @@ static void rast_spread_launch(b200_ctx *ctx, const RastParams &p, int what) {
   else if (what == 1) rast_spread_kernel<1><<<grid, 256, 0, ctx->stream>>>(p, per_block);
   else rast_spread_kernel<2><<<grid, 256, 0, ctx->stream>>>(p, per_block);
   ctx->stats.kernel_launches++;
+  tl_mark(ctx, "rast_spread_kernel");
 }
 
 // ---- calculateIllumination (:674-688) without the final "+ indirect" -----------------------
@@ -746,11 +751,11 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     p.row_cap = spec ? (unsigned)(row_cap > 0xffffffffull ? 0xffffffffull : row_cap) : 0xffffffffu;
     if (int rc = ensure(ctx, ctx->rast_keys, npix * sizeof(unsigned long long))) return rc;
     p.keys = (unsigned long long *)ctx->rast_keys.p;
-    CU_CHECK(ctx, cudaMemsetAsync(p.keys + (size_t)p.fb0 * W, 0, (size_t)(p.fb1 - p.fb0) * W * sizeof(unsigned long long), ctx->stream));
     size_t n_rows = row_cap;
     if (n > 0) {
       rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
+      tl_mark(ctx, "rast_setup_kernel");
       rast_spread_launch(ctx, p, 0);
       CU_CHECK(ctx, cudaGetLastError());
     }
@@ -769,9 +774,14 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * n_rows)) return rc;
     p.rowsA = (float4 *)ctx->rast_rowsA.p;
     p.rowsB = (float4 *)ctx->rast_rowsB.p;
+    // cleared right before the scatter so that the 64-bit keys (66 MB at 4K, less than the L2)
+    // are still cache-resident when the atomics arrive
+    CU_CHECK(ctx, cudaMemsetAsync(p.keys + (size_t)p.fb0 * W, 0, (size_t)(p.fb1 - p.fb0) * W * sizeof(unsigned long long), ctx->stream));
+    tl_mark(ctx, "memset keys");
     if (p.n_chunks > 0 && n > 0) {
       rast_scatter_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
+      tl_mark(ctx, "rast_scatter_kernel");
     }
     // host-pointer entries: resolve in slices, each slice's packed rows leave for the host
     // while the next one is resolved (band_slice_done is a no-op otherwise)
@@ -783,6 +793,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
       dim3 rg((W + RS_W - 1) / RS_W, (p.row1 - p.row0 + RS_H - 1) / RS_H);
       rast_resolve_kernel<<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
+      tl_mark(ctx, "rast_resolve_kernel");
       CU_CHECK(ctx, cudaGetLastError());
       if (int rc = band_slice_done(ctx, p.row0, p.row1)) return rc;
     }
@@ -818,11 +829,13 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (n > 0) {
     rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
+    tl_mark(ctx, "rast_setup_kernel");
     rast_spread_launch(ctx, p, 0);
     rast_spread_launch(ctx, p, 1);
   }
   rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
   ctx->stats.kernel_launches++;
+  tl_mark(ctx, "rast_scan_kernel");
   CU_CHECK(ctx, cudaGetLastError());
   if (!spec) {
     // the bin array is sized from the scanned total: read it back (tiny, one sync)
@@ -840,6 +853,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (p.n_chunks > 0 && n > 0) {
     rast_rows_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
+    tl_mark(ctx, "rast_rows_kernel");
   }
   if (n > 0 && bin_cap > 0) rast_spread_launch(ctx, p, 2);
   dim3 grid(p.tiles_x, p.tiles_y);
@@ -849,6 +863,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     default: rast_fill_kernel<5><<<grid, 1024, 0, ctx->stream>>>(p); break;
   }
   ctx->stats.kernel_launches++;
+  tl_mark(ctx, "rast_fill_kernel");
   CU_CHECK(ctx, cudaGetLastError());
   const int k = (ctx->slice_host && (size_t)(row1 - row0) * W >= ((size_t)1 << 20)) ? B200_SLICES : 1;
   for (int i = 0; i < k; ++i) {
@@ -858,6 +873,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     dim3 pb(32, 8), pg((W + 31) / 32, (p.row1 - p.row0 + 7) / 8);
     rast_post_kernel<<<pg, pb, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
+    tl_mark(ctx, "rast_post_kernel");
     CU_CHECK(ctx, cudaGetLastError());
     if (int rc = band_slice_done(ctx, p.row0, p.row1)) return rc;
   }

@@ -1,0 +1,17 @@
+import sys, os, importlib
+sys.path.insert(0,"/root/repo"); sys.path.insert(0,"/root/repo/tests")
+import torch, numpy as np
+import helpers as h, bench
+b=importlib.import_module("computer-graphics_b200")
+w=sys.argv[1]
+kind,W,H,f=bench.WORKLOADS[w]
+r=b.Renderer(0)
+rgb=torch.empty((H,W,3),device="cuda"); depth=torch.empty((H,W),device="cuda")
+room,boxes=bench.rast_scene(b,w)
+cam=b.make_camera(bench.RAST_CAM,f,h.identity_R(),W,H)
+L=b.make_rast_light(bench.RAST_LIGHT["pos"],bench.RAST_LIGHT["power"],bench.RAST_LIGHT["indirect"])
+r.rast_upload_scene(room,boxes)
+r.set_option(b.OPT_RAST_PIPELINED,1)
+for i in range(4):
+    if i==3: sys.stderr.write("---- last frame\n")
+    r.rast_draw_device(cam,L,0,H,rgb.data_ptr(),depth.data_ptr()); r.synchronize()
