@@ -75,7 +75,7 @@ int b200_init(int device, b200_ctx **out) {
     return B200_ECUDA;
   }
   ctx->stream = ctx->own_stream;
-  if (ensure(ctx, ctx->counters, 16 * sizeof(unsigned long long)) != B200_OK || ensure_pinned(ctx, 256) != B200_OK) {
+  if (ensure(ctx, ctx->counters, 32 * sizeof(unsigned long long)) != B200_OK || ensure_pinned(ctx, 512) != B200_OK) {
     delete ctx;
     return B200_ENOMEM;
   }
@@ -162,9 +162,10 @@ int b200_get_stats(b200_ctx *ctx, b200_stats *out) {
   return B200_OK;
 }
 
-// Every render ends by copying its counters into the second half of the pinned scratch.
+// Every render ends by copying its counters into the second half of the pinned scratch
+// (the first half takes the mid-frame read-backs).
 static int enqueue_counter_readback(b200_ctx *ctx) {
-  CU_CHECK(ctx, cudaMemcpyAsync((unsigned long long *)ctx->pinned + 16, ctx->counters.p, 16 * sizeof(unsigned long long),
+  CU_CHECK(ctx, cudaMemcpyAsync((unsigned long long *)ctx->pinned + 32, ctx->counters.p, 32 * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, ctx->stream));
   return B200_OK;
 }
@@ -236,7 +237,7 @@ int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, 
   if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // the counters are shared
   f.il_n = ctx->opt_rt_il_n; f.il_r = ctx->opt_rt_il_r;
   ctx->stats.kernel_launches = 0;
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (int rc = rt_launch(ctx, f, d_rgb, d_depth, d_index, d_argb)) return rc;
   CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -257,14 +258,14 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
 static int finish_stats(b200_ctx *ctx) {
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   if (!ctx->pending) return B200_OK;
-  const unsigned long long *c = (const unsigned long long *)ctx->pinned + 16;
+  const unsigned long long *c = (const unsigned long long *)ctx->pinned + 32;
   if (ctx->pending == 2 && ctx->rast_inflight.active) {
     b200_ctx::RastInflight &f = ctx->rast_inflight;
     f.active = 0;
     bool ok = c[5] == 0 && (f.fast || c[3] <= f.cap_bins);
     if (f.whole_draw) {
       const int has_shadow = (ctx->rast_n_boxes > 0 || (c[7] & 2ull)) ? 1 : 0;
-      ok = ok && c[8] <= f.cap_tris && !(c[7] & 1ull) && has_shadow == ctx->rast_has_shadow;
+      ok = ok && c[24] <= f.cap_tris && !(c[7] & 1ull) && has_shadow == ctx->rast_has_shadow;
     }
     if (!ok) {
       // the frame outgrew the guess: render it again with exact sizes
@@ -276,7 +277,7 @@ static int finish_stats(b200_ctx *ctx) {
         return rc;
       CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     } else if (f.whole_draw) {
-      ctx->rast_n_tris = (int)c[8];
+      ctx->rast_n_tris = (int)c[24];
     }
   }
   float ms = 0.f;
@@ -296,7 +297,7 @@ static int finish_stats(b200_ctx *ctx) {
     ctx->stats.prim_tests = (ctx->stats.primary_rays + ctx->stats.shadow_rays) *
                             (uint64_t)(ctx->rt_n_tris + ctx->rt_n_spheres);
   } else {
-    ctx->stats.fragments = c[2];
+    ctx->stats.fragments = c[16];
     ctx->stats.bin_entries = c[3];
     // what this frame needed sizes the next pipelined frame of the same shape
     b200_ctx::RastSpec &sp = ctx->rast_spec;
@@ -373,7 +374,7 @@ int draw_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const
   if (int rc = fill_frame(ctx, cam, lights, n_lights, row_begin, row_end, f)) return rc;
   if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // the counters are shared
   ctx->stats.kernel_launches = 0;
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   // Large frames are rendered in slices of whole 16-row blocks so that the copy of one slice to
   // the host overlaps the rendering of the next (scenes with per-frame grids: one slice, the
@@ -490,7 +491,7 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
     f.cap_tris = 0; f.cap_bins = 0;
   }
   ctx->stats.kernel_launches = 0;
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   ctx->tl_n = 0;
   tl_mark(ctx, "frame start");

@@ -141,7 +141,7 @@ struct b200_ctx {
   int timeline = 0, tl_n = 0;
   cudaEvent_t tl_ev[64] = {};
   const char *tl_name[64] = {};
-  DevBuf counters;    // unsigned long long[8]
+  DevBuf counters;    // unsigned long long[32]
   void *pinned = nullptr;
   size_t pinned_cap = 0;
 };
@@ -172,7 +172,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
                 float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb, bool spec);
 int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, rast_light_t *light_out,
                   bool spec);
-static inline unsigned long long rast_spec_cap(unsigned long long seen) { return seen + seen / 8 + 1024; }
+static inline unsigned long long rast_spec_cap(unsigned long long seen) { return seen + seen / 32 + 1024; }   // +3 %
 int scan_exclusive(b200_ctx *ctx, const unsigned *counts, unsigned *offs, int n, unsigned *tmp,
                    unsigned long long *total_out);   // rast_geom.cu; tmp: n / 4096 + 2 words
 int rt_prepare_scene(b200_ctx *ctx);

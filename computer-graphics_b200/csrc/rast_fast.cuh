@@ -53,7 +53,7 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_frag += __shfl_xor_sync(0xffffffffu, n_frag, o);
-  if ((threadIdx.x & 31) == 0 && n_frag) atomicAdd(p.counters + 2, n_frag);
+  if ((threadIdx.x & 31) == 0 && n_frag) atomicAdd(p.counters + 16, n_frag);
 }
 
 constexpr int RS_W = 32, RS_H = 8, RS_HW = RS_W + 2, RS_HH = RS_H + 2, RS_N = RS_HW * RS_HH;   // 34 x 10 = 340

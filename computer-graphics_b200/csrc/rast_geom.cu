@@ -406,7 +406,7 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
     tl_mark(ctx, "rast_geom_kernel");
     CU_CHECK(ctx, cudaGetLastError());
     unsigned long long *dc = (unsigned long long *)ctx->counters.p;
-    if (int rc = scan_exclusive(ctx, p.counts, p.offs, n_pre, p.offs + (n_pre + 1), dc + 8)) return rc;
+    if (int rc = scan_exclusive(ctx, p.counts, p.offs, n_pre, p.offs + (n_pre + 1), dc + 24)) return rc;
     if (spec) {
       // pipelined: the list length stays on the device ([8]); the write pass is bounded by
       // the capacity guessed from the last verified frame and the guess is checked later
@@ -414,12 +414,12 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
       if (cap > 0x3fffffffull) cap = 0x3fffffffull;
       total = (unsigned)cap;
     } else {
-      // one small read-back into pinned memory: [7] validation flags, [8] clipped-list length
+      // one small read-back into pinned memory: [7] validation flags, [24] clipped-list length
       unsigned long long *hc = (unsigned long long *)ctx->pinned;
-      CU_CHECK(ctx, cudaMemcpyAsync(hc, dc, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_CHECK(ctx, cudaMemcpyAsync(hc, dc, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
       CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
       const unsigned long long flags = hc[7];
-      total = (unsigned)hc[8];
+      total = (unsigned)hc[24];
       if (flags & 1ull) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
       ctx->rast_has_shadow = (n_boxes > 0 || (flags & 2ull)) ? 1 : 0;
     }

@@ -86,7 +86,7 @@ struct RastParams {
   float *out_depth;
   int *out_index;
   uint32_t *out_argb;
-  unsigned long long *counters;  // [2] fragments, [3] bin entries, [4] rows, [5] overflow flag, [6] row chunks
+  unsigned long long *counters;  // [3] bin entries, [4] rows, [5] overflow flag, [6] row chunks, second cache line: [16] fragments (updated while [6] is read), [24] list length (read while [4]/[6] are updated)
 };
 
 __device__ __forceinline__ int rast_count_tris(const RastParams &p) {
@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) rast_setup_kernel(const __grid_
   const int t = t0 + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int n_tris = rast_count_tris(p);
-  const int n_here = max(0, min(SETUP_THREADS, n_tris - t0));
+  if (t0 >= n_tris) return;   // pipelined launches are sized by a bound on the list length
+  const int n_here = min(SETUP_THREADS, n_tris - t0);
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.src + t0);
     for (int i = threadIdx.x; i < n_here * TRI_WORDS; i += SETUP_THREADS) stage[i] = __ldg(src + i);
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
   unsigned long long nf = (on_screen && y >= p.fb0 && y < p.fb1) ? n_frag : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
-  if (lane == 0 && nf) atomicAdd(p.counters + 2, nf);
+  if (lane == 0 && nf) atomicAdd(p.counters + 16, nf);
 }
 
 // ---- post pass (:283-307) --------------------------------------------------------------------
@@ -734,7 +735,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     row_cap = (size_t)rast_spec_cap(ctx->rast_spec.rows);
     chunk_cap = (size_t)rast_spec_cap(ctx->rast_spec.chunks);
     bin_cap = (size_t)rast_spec_cap(ctx->rast_spec.bins);
-    p.n_tris_dev = ctx->rast_inflight.whole_draw ? p.counters + 8 : nullptr;
+    p.n_tris_dev = ctx->rast_inflight.whole_draw ? p.counters + 24 : nullptr;
     p.n_chunks_dev = p.counters + 6;
     p.n_chunks = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
     ctx->rast_inflight.cap_bins = bin_cap;

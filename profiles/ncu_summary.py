@@ -42,18 +42,22 @@ def report(path):
 
 
 def launches(path):
+    """Summarises the last frame of bench.py's TIMED region: frames start at rt_prep_planes_kernel /
+    rast_geom_kernel<0>; the end-to-end frames that follow (sliced, smaller grids) and the FFMA peak
+    microbenchmark are not part of it."""
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
-    # the last frame of the run: walk back to the first kernel of the frame
-    frame, seen = [], set()
-    for r in reversed(rows):
-        key = r[4]
-        if key in seen and key.startswith(("rast_resolve", "rast_post", "void rt_filtered")):
-            break
-        seen.add(key)
-        frame.append(r)
-    frame.reverse()
+    rows = [r for r in rows if not r[4].startswith(("b200_ffma_peak_kernel", "void at::"))]
+    starts = [i for i, r in enumerate(rows) if r[4].startswith(("rt_prep_planes_kernel", "void rast_geom_kernel<0>",
+                                                                 "void rast_geom_kernel<(bool)0>"))]
+    frames = [rows[a:b] for a, b in zip(starts, starts[1:] + [len(rows)])]
+
+    def blocks(fr):   # thread blocks of the frame's final kernel: the sliced end-to-end frames have fewer
+        g = [int(v) for v in fr[-1][8].strip("()").split(",")]
+        return g[0] * g[1] * g[2]
+    full = max(blocks(fr) for fr in frames)
+    frame = [fr for fr in frames if blocks(fr) == full][-1]
     total = sum(float(r[-1]) for r in frame)
-    print(f"### {path}: last frame, {len(frame)} launches, {total / 1e3:.1f} us in kernels")
+    print(f"### {path}: last timed frame, {len(frame)} launches, {total / 1e3:.1f} us in kernels")
     print("| kernel | grid | block | us | share |")
     print("|---|---|---|---|---|")
     for r in frame:

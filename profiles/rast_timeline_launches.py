@@ -11,7 +11,7 @@ room,boxes=bench.rast_scene(b,w)
 cam=b.make_camera(bench.RAST_CAM,f,h.identity_R(),W,H)
 L=b.make_rast_light(bench.RAST_LIGHT["pos"],bench.RAST_LIGHT["power"],bench.RAST_LIGHT["indirect"])
 r.rast_upload_scene(room,boxes)
-r.set_option(b.OPT_RAST_PIPELINED,1)
+r.set_option(b.OPT_RAST_PIPELINED,int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 for i in range(4):
     if i==3: sys.stderr.write("---- last frame\n")
     r.rast_draw_device(cam,L,0,H,rgb.data_ptr(),depth.data_ptr()); r.synchronize()
