@@ -279,6 +279,19 @@ __device__ __forceinline__ bool edge_run(const RastSetup &s, int ei, int Y, Rast
     i0 = i1 = i;
     return true;
   }
+  if (e.n <= 8) {
+    // |step_y| < 1, short edge (every edge of a small triangle): look at all samples, branch-free;
+    // y(i) is monotone, so the samples with y == Y are the run the searches below would find
+    int lo = 8, hi = -1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool in = i < e.n && edge_py(e, i) == Y;
+      lo = in ? min(lo, i) : lo;
+      hi = in ? i : hi;
+    }
+    i0 = lo; i1 = hi;
+    return hi >= 0;
+  }
   const bool up = b.y > a.y;         // |step_y| < 1: a run of samples per row
   i0 = edge_first(e, Y, up);
   i1 = edge_first(e, up ? Y + 1 : Y - 1, up) - 1;
