@@ -188,6 +188,9 @@ __device__ __forceinline__ float warp_max(float v) {
 // must then be >= -2E / -3E.  The sums catch what the single planes cannot: triangles
 // seen nearly edge-on, whose two long edge planes almost coincide and straddle the box.
 // (Coefficient sums are rounded once more; the factors leave room for that.)
+// PAIRS = false (small scenes streamed whole, where a few extra L0 survivors cost less than
+// the test) checks the single planes only.
+template <bool PAIRS = true>
 __device__ __forceinline__ bool rt_box_may_hit_light(const float4 q0, const float4 q1, const float4 q2, const float *c,
                                                      const float *h, float Eg) {
   const float U[3] = {q0.x, q0.y, q0.z}, V[3] = {q0.w, q1.x, q1.y}, W[3] = {q1.z, q1.w, q2.x};
@@ -195,6 +198,7 @@ __device__ __forceinline__ bool rt_box_may_hit_light(const float4 q0, const floa
     return fmaf(x, c[0], fmaf(y, c[1], z * c[2])) + fmaf(fabsf(x), h[0], fmaf(fabsf(y), h[1], fabsf(z) * h[2]));
   };
   if (fminf(fminf(hi(U[0], U[1], U[2]), hi(V[0], V[1], V[2])), hi(W[0], W[1], W[2])) < -Eg) return false;
+  if (!PAIRS) return true;
   const float uv = hi(U[0] + V[0], U[1] + V[1], U[2] + V[2]);
   const float vw = hi(V[0] + W[0], V[1] + W[1], V[2] + W[2]);
   const float uw = hi(U[0] + W[0], U[1] + W[1], U[2] + W[2]);
@@ -202,6 +206,7 @@ __device__ __forceinline__ bool rt_box_may_hit_light(const float4 q0, const floa
   return true;
 }
 // camera: directions (dx, dy, f) with the z term folded into the constant; E absolute
+template <bool PAIRS = true>
 __device__ __forceinline__ bool rt_box_may_hit_cam(const float4 q0, const float4 q1, const float4 q2, float c0, float c1,
                                                    float h0, float h1) {
   auto hi = [&](float x, float y, float k) {
@@ -209,6 +214,7 @@ __device__ __forceinline__ bool rt_box_may_hit_cam(const float4 q0, const float4
   };
   const float E = q2.y;
   if (fminf(fminf(hi(q0.x, q0.y, q0.z), hi(q0.w, q1.x, q1.y)), hi(q1.z, q1.w, q2.x)) < -E) return false;
+  if (!PAIRS) return true;
   const float uv = hi(q0.x + q0.w, q0.y + q1.x, q0.z + q1.y);
   const float vw = hi(q0.w + q1.z, q1.x + q1.w, q1.y + q2.x);
   const float uw = hi(q0.x + q1.z, q0.y + q1.w, q0.z + q2.x);

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
           const float4 q0 = T[(r0 + lane) * 3], q1 = T[(r0 + lane) * 3 + 1], q2 = T[(r0 + lane) * 3 + 2];
           // E already covers the rounding of the centre evaluation (|wc| <= dmax);
           // the half-width terms are sums of non-negative products, inflated above
-          pass = rt_box_may_hit_cam(q0, q1, q2, wc0, wc1, wh0, wh1);
+          pass = rt_box_may_hit_cam<GRID>(q0, q1, q2, wc0, wc1, wh0, wh1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, pass);
         // ---- L1: every lane tests its pixel (centre, margin widened by the +-0.5 jitter)
@@ -556,12 +556,12 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
           const float nx = q0.x + q0.w + q1.z, ny = q0.y + q1.x + q1.w, nz = q0.z + q1.y + q2.x;
           const float mN = fmaf(nx, wc[0], fmaf(ny, wc[1], nz * wc[2])) +
                            fmaf(fabsf(nx), wh[0], fmaf(fabsf(ny), wh[1], fabsf(nz) * wh[2]));
-          pass = rt_box_may_hit_light(q0, q1, q2, wc, wh, Eg) && !(mN + 1.1f * Eg < q2.z);
+          pass = rt_box_may_hit_light<GRID>(q0, q1, q2, wc, wh, Eg) && !(mN + 1.1f * Eg < q2.z);
           if (GRID && two && !pass) {
             const float Eg2 = q2.y * wnorm2;
             const float mN2 = fmaf(nx, wc2[0], fmaf(ny, wc2[1], nz * wc2[2])) +
                               fmaf(fabsf(nx), wh2[0], fmaf(fabsf(ny), wh2[1], fabsf(nz) * wh2[2]));
-            pass = rt_box_may_hit_light(q0, q1, q2, wc2, wh2, Eg2) && !(mN2 + 1.1f * Eg2 < q2.z);
+            pass = rt_box_may_hit_light<GRID>(q0, q1, q2, wc2, wh2, Eg2) && !(mN2 + 1.1f * Eg2 < q2.z);
           }
         }
         unsigned mask = __ballot_sync(0xffffffffu, pass);
