@@ -31,6 +31,10 @@ struct GeomParams {
   rast_triangle *out;
   unsigned out_cap;
   unsigned long long *flags;   // bit0: a triangle with texture != 0, bit1: a shadow-coloured input triangle
+  // single-pass mode (pipelined frames): chained scan over the blocks
+  unsigned *ticket;            // hands out block ids in scheduling order (forward progress of the look-back)
+  unsigned long long *desc;    // per block: state << 62 | value; state 1 = block sum, 2 = inclusive prefix
+  unsigned long long *total;   // list length
 };
 
 struct GV { float x, y, z, w; };
@@ -150,11 +154,22 @@ __device__ __noinline__ int clip_six_planes(int W, int H, float focal, GTri *cur
   return n_cur;
 }
 
-template <bool WRITE>
+// MODE 0: count the triangles each pre-clip triangle turns into; MODE 1: write them at the
+// offsets a scan of the counts gave (exact sizes: two passes and a host read-back in between);
+// MODE 2: one pass -- count, block scan, decoupled look-back over the preceding blocks'
+// published sums, write -- into a list whose capacity was guessed (pipelined frames).
+template <int MODE>
 __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ GeomParams p) {
+  constexpr bool WRITE = MODE != 0;
   constexpr int GT = 128, TW = sizeof(rast_triangle) / 4;
   __shared__ uint32_t stage[GT * TW];   // coalesced word streams in and out of the 84-byte records
-  const int j0 = blockIdx.x * GT;
+  __shared__ unsigned s_bid, s_warp[4], s_prefix;
+  if (MODE == 2) {
+    if (threadIdx.x == 0) s_bid = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+  }
+  const int bid = MODE == 2 ? (int)s_bid : (int)blockIdx.x;
+  const int j0 = bid * GT;
   const int j = j0 + threadIdx.x;
   const int n_pre = p.n_room + 7 * p.n_boxes;
   // a block whose triangles all come from `room` reads them through shared memory
@@ -232,13 +247,59 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
   }
   cur[0] = t;
   if (!all_in) n_cur = clip_six_planes(p.W, p.H, p.focal, cur);
-  if (!WRITE) {
-    if (j < n_pre) {
-      p.counts[j] = (unsigned)n_cur;
-      if (__float_as_int(attr[7]) != 0) atomicOr(p.flags, 1ull);
-      if (s == 0 && !(attr[4] >= 0.0f)) atomicOr(p.flags, 2ull);
-    }
+  if (MODE != 1 && j < n_pre) {
+    if (__float_as_int(attr[7]) != 0) atomicOr(p.flags, 1ull);
+    if (s == 0 && !(attr[4] >= 0.0f)) atomicOr(p.flags, 2ull);
+  }
+  if (MODE == 0) {
+    if (j < n_pre) p.counts[j] = (unsigned)n_cur;
     return;
+  }
+  unsigned my_off = 0;   // where this thread's first output goes
+  if (MODE == 2) {
+    const unsigned cnt = j < n_pre ? (unsigned)n_cur : 0u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned before = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { before += w < warp ? s_warp[w] : 0u; block_sum += s_warp[w]; }
+    if (warp == 0) {
+      // Decoupled look-back by the whole warp: lane l inspects the block l places back; the
+      // window moves 32 blocks at a time until it contains a block whose inclusive prefix is known.
+      // Every block before this one already holds its ticket, so it will publish.
+      const unsigned long long VAL = (1ull << 62) - 1;
+      if (lane == 0 && bid > 0) atomicExch(p.desc + bid, (1ull << 62) | block_sum);
+      unsigned long long prefix = 0;
+      for (int base = bid - 1;;) {
+        const int k = base - lane;
+        const unsigned long long v = k >= 0 ? atomicAdd(p.desc + k, 0ull) : (2ull << 62);   // "block -1": prefix 0
+        const unsigned state = (unsigned)(v >> 62);
+        const unsigned ready = __ballot_sync(0xffffffffu, state != 0), done = __ballot_sync(0xffffffffu, state == 2);
+        const int first = done ? __ffs(done) - 1 : 31;                 // nearest block with an inclusive prefix
+        const unsigned need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+        if ((ready & need) != need) continue;                            // someone in the window has not published yet
+        unsigned long long part = lane <= first ? (v & VAL) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        prefix += part;
+        if (done) break;
+        base -= 32;
+      }
+      if (lane == 0) {
+        atomicExch(p.desc + bid, (2ull << 62) | (prefix + block_sum));
+        if (bid == (int)gridDim.x - 1) *p.total = prefix + block_sum;
+        s_prefix = (unsigned)prefix;
+      }
+    }
+    __syncthreads();
+    my_off = s_prefix + before + incl - cnt;
   }
   // Common case: the whole block is unclipped (one output each, contiguous in the
   // list): write the records through shared memory as one coalesced stream.
@@ -251,14 +312,14 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
 #pragma unroll
     for (int k = 0; k < 9; ++k) o[12 + k] = attr[k];
     __syncthreads();
-    const unsigned off0 = p.offs[j0];
+    const unsigned off0 = MODE == 2 ? s_prefix : p.offs[j0];
     uint32_t *dst = reinterpret_cast<uint32_t *>(p.out + off0);
     if (off0 + GT <= p.out_cap)
       for (int i = threadIdx.x; i < GT * TW; i += GT) dst[i] = stage[i];
     return;
   }
   if (j >= n_pre) return;
-  const unsigned off = p.offs[j];
+  const unsigned off = MODE == 2 ? my_off : p.offs[j];
   for (int i = 0; i < n_cur; ++i) {
     if (off + i >= p.out_cap) break;
     rast_triangle *o = p.out + off + i;
@@ -395,25 +456,41 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
   p.boxes = p.room + n_room;
   p.n_boxes = n_boxes;
   const int n_scan_blocks = (n_pre + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  if (int rc = ensure(ctx, ctx->rast_geom_tmp, sizeof(unsigned) * (2 * (size_t)(n_pre + 1) + n_scan_blocks + 2))) return rc;
+  const int n_blocks = (n_pre + 127) / 128;
+  const size_t tmp_words = 2 * (size_t)(n_pre + 1) + n_scan_blocks + 2;          // counts, offsets, scan scratch
+  const size_t chain_off = (tmp_words * sizeof(unsigned) + 15) / 16 * 16;        // then: ticket (16 B), block descriptors
+  if (int rc = ensure(ctx, ctx->rast_geom_tmp, chain_off + 16 + sizeof(unsigned long long) * (size_t)(n_blocks + 1))) return rc;
   p.flags = (unsigned long long *)ctx->counters.p + 7;
   p.counts = (unsigned *)ctx->rast_geom_tmp.p;
   p.offs = p.counts + (n_pre + 1);
+  p.ticket = (unsigned *)((char *)ctx->rast_geom_tmp.p + chain_off);
+  p.desc = (unsigned long long *)((char *)ctx->rast_geom_tmp.p + chain_off + 16);
+  p.total = (unsigned long long *)ctx->counters.p + 24;
+  if (spec && n_pre > 0) {
+    // pipelined: one pass into a list whose capacity comes from the last verified frame; the
+    // list length stays on the device ([24]) and the guess is checked when the frame is waited for
+    unsigned long long cap = rast_spec_cap(ctx->rast_spec.tris);
+    if (cap > 0x3fffffffull) cap = 0x3fffffffull;
+    if (int rc = ensure(ctx, ctx->rast_src, sizeof(rast_triangle) * (size_t)cap)) return rc;
+    p.out = (rast_triangle *)ctx->rast_src.p;
+    p.out_cap = (unsigned)cap;
+    CU_CHECK(ctx, cudaMemsetAsync(p.ticket, 0, 16 + sizeof(unsigned long long) * (size_t)n_blocks, ctx->stream));
+    rast_geom_kernel<2><<<n_blocks, 128, 0, ctx->stream>>>(p);
+    ctx->stats.kernel_launches++;
+    tl_mark(ctx, "rast_geom_kernel<2>");
+    CU_CHECK(ctx, cudaGetLastError());
+    ctx->rast_n_tris = (int)cap;
+    return B200_OK;
+  }
   unsigned total = 0;
   if (n_pre > 0) {
-    rast_geom_kernel<false><<<(n_pre + 127) / 128, 128, 0, ctx->stream>>>(p);
+    rast_geom_kernel<0><<<(n_pre + 127) / 128, 128, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     tl_mark(ctx, "rast_geom_kernel");
     CU_CHECK(ctx, cudaGetLastError());
     unsigned long long *dc = (unsigned long long *)ctx->counters.p;
     if (int rc = scan_exclusive(ctx, p.counts, p.offs, n_pre, p.offs + (n_pre + 1), dc + 24)) return rc;
-    if (spec) {
-      // pipelined: the list length stays on the device ([8]); the write pass is bounded by
-      // the capacity guessed from the last verified frame and the guess is checked later
-      unsigned long long cap = rast_spec_cap(ctx->rast_spec.tris);
-      if (cap > 0x3fffffffull) cap = 0x3fffffffull;
-      total = (unsigned)cap;
-    } else {
+    {
       // one small read-back into pinned memory: [7] validation flags, [24] clipped-list length
       unsigned long long *hc = (unsigned long long *)ctx->pinned;
       CU_CHECK(ctx, cudaMemcpyAsync(hc, dc, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -428,7 +505,7 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
   p.out = (rast_triangle *)ctx->rast_src.p;
   p.out_cap = total;
   if (total > 0) {
-    rast_geom_kernel<true><<<(n_pre + 127) / 128, 128, 0, ctx->stream>>>(p);
+    rast_geom_kernel<1><<<(n_pre + 127) / 128, 128, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     tl_mark(ctx, "rast_geom_kernel");
     CU_CHECK(ctx, cudaGetLastError());
