@@ -77,6 +77,7 @@ struct RastParams {
   // pipelined mode: the list length / chunk count are not known on the host yet; n_tris and
   // n_chunks above are then launch bounds and the kernels clamp to these device values
   const unsigned long long *n_tris_dev, *n_chunks_dev;
+  int spread_in_setup;   // long lists: rast_setup_kernel hands the row chunks out itself (no rast_spread_kernel<0>)
   unsigned *tile_count, *tile_off, *tile_cursor;
   int *bins, *bins_tmp;
   unsigned bin_cap;
@@ -213,6 +214,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) rast_setup_kernel(const __grid_
     s.nrows = 0; nrows = 0; nch = 0;
     atomicExch(p.counters + 5, 1ull);
   }
+  if (p.spread_in_setup)   // the triangle's row chunks, the work items of the per-row kernels
+    warp_spread((int)nch, (int)s.chunk_off, 0, 0, t, [&](int k, int x0, int, int, int tri) { p.chunk_owner[(unsigned)x0 + k] = tri; });
   __syncthreads();   // every thread has read its triangle: the buffer now carries the records out
   if (t < n_tris) {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(&s);
@@ -727,6 +730,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   memcpy(p.indirect, light->indirect, sizeof p.indirect);
   p.src = (const rast_triangle *)ctx->rast_src.p;
   p.n_tris = n;
+  p.spread_in_setup = n > 8192 ? 1 : 0;   // short lists of big triangles: one block per triangle spreads better
 
   const size_t npix = (size_t)W * H;
   if (ctx->opt_rast_path == 2 && ctx->rast_has_shadow)
@@ -770,7 +774,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
       rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
       tl_mark(ctx, "rast_setup_kernel");
-      rast_spread_launch(ctx, p, 0);
+      if (!p.spread_in_setup) rast_spread_launch(ctx, p, 0);
       CU_CHECK(ctx, cudaGetLastError());
     }
     if (!spec) {
@@ -844,7 +848,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     tl_mark(ctx, "rast_setup_kernel");
-    rast_spread_launch(ctx, p, 0);
+    if (!p.spread_in_setup) rast_spread_launch(ctx, p, 0);
     rast_spread_launch(ctx, p, 1);
   }
   rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
