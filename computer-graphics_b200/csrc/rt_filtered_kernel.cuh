@@ -385,10 +385,28 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
 
   // spheres (skeleton.cpp:341-355)
   if (live) {
+    for (int s = 0; s < p.n_sph; ++s) {     // per ray the spheres still come in ascending order
+      // Bundle pre-test: an upper bound of q + tolerance (see rt_sphere_may_hit) over the pixel's
+      // nine directions d = (dxs[1] +- 0.5, dys[1] +- 0.5, f).  Negative: no sample can report a root.
+      {
+        const float Lx = cx - __ldg(&p.sph[s].centre[0]), Ly = cy - __ldg(&p.sph[s].centre[1]),
+                    Lz = cz - __ldg(&p.sph[s].centre[2]);
+        const float r2 = __ldg(&p.sph[s].radius_squared);
+        const float LL = fmaf(Lx, Lx, fmaf(Ly, Ly, Lz * Lz)), c = LL - r2;
+        if (c > 0.0f) {                        // camera outside the sphere
+          const float hw = 0.5002f;            // half-width of the bundle, with the rounding of the +-0.5 offsets
+          const float dL = fabsf(fmaf(dxs[1], Lx, fmaf(dys[1], Ly, dz * Lz))) + hw * (fabsf(Lx) + fabsf(Ly));
+          const float a_max = dL * dL * 1.00001f;
+          const float ax0 = fmaxf(fabsf(dxs[1]) - hw, 0.0f), ay0 = fmaxf(fabsf(dys[1]) - hw, 0.0f);
+          const float ax1 = fabsf(dxs[1]) + hw, ay1 = fabsf(dys[1]) + hw;
+          const float dd_min = fmaf(ax0, ax0, fmaf(ay0, ay0, dz * dz)) * 0.99999f;
+          const float dd_max = fmaf(ax1, ax1, fmaf(ay1, ay1, dz * dz)) * 1.00001f;
+          if (a_max - dd_min * c < -1.001e-4f * (a_max + dd_max * (LL + r2))) continue;
+        }
+      }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float dx = dxs[k / 3], dy = dys[k % 3];
-      for (int s = 0; s < p.n_sph; ++s) {
+      for (int k = 0; k < 9; ++k) {
+        const float dx = dxs[k / 3], dy = dys[k % 3];
         if (!rt_sphere_may_hit(p.sph[s], cx, cy, cz, dx, dy, dz)) continue;
         const RtSphT h = rt_ex_sphere(p.sph + s, cx, cy, cz, dx, dy, dz);
         if (h.hit && h.t < best[k].dist) { best[k].t = h.t; best[k].dist = h.t; best[k].idx = -1 - s; }
