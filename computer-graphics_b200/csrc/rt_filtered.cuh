@@ -37,8 +37,9 @@ constexpr int RT_REC_F4 = 3;      // float4s per plane record (48 bytes)
 // direction grids (rt_grid.cuh)
 constexpr int RT_GRID_G = 64;              // light cube map: cells per face edge
 constexpr int RT_GRID_FACE = RT_GRID_G * RT_GRID_G;
-constexpr int RT_GRID_MAX_CELLS = 256;     // shadow phase: distinct cells one pixel block may walk, else it streams the scene
-constexpr int RT_GRID_TABLE_LOG2 = 9;      // hash set used to collect them
+constexpr int RT_WTILE = 64;               // records per tile of a warp's private ring (grid kernels)
+constexpr int RT_GRID_MAX_CELLS = 96;      // shadow phase: distinct cells one warp (8x4 pixels, 288 rays) may walk, else it streams the scene
+constexpr int RT_GRID_TABLE_LOG2 = 8;      // hash set used to collect them
 
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+/sm_100a PTX) ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

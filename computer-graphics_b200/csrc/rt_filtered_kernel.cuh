@@ -144,19 +144,20 @@ struct RtRing {
   int issued;
 };
 
-// One tile of work: up to RT_TILE consecutive records of a list.
+// One tile of work: up to TILE consecutive records of a list.
 struct RtItem {
   const float4 *rec;
   const int *idx;    // null: the list is the scene itself, record i is triangle base + i
   int base, cnt;
 };
 
+template <int TILE>
 __device__ __forceinline__ void rt_ring_issue(RtRing &ring, const RtItem &it) {
   const int buf = ring.issued & 1;
   const uint32_t rec_bytes = (uint32_t)it.cnt * 48u, idx_bytes = it.idx ? (((uint32_t)it.cnt + 3u) & ~3u) * 4u : 0u;
   mbar_expect_tx(&ring.bars[buf], rec_bytes + idx_bytes);
-  tma_bulk_g2s(ring.smem + (size_t)buf * RT_TILE * RT_REC_F4, it.rec, rec_bytes, &ring.bars[buf]);
-  if (it.idx) tma_bulk_g2s(ring.smem_idx + buf * RT_TILE, it.idx, idx_bytes, &ring.bars[buf]);
+  tma_bulk_g2s(ring.smem + (size_t)buf * TILE * RT_REC_F4, it.rec, rec_bytes, &ring.bars[buf]);
+  if (it.idx) tma_bulk_g2s(ring.smem_idx + buf * TILE, it.idx, idx_bytes, &ring.bars[buf]);
 }
 
 // Walks the lists a pixel block has to stream, tile by tile: the whole scene, or
@@ -180,7 +181,7 @@ __device__ __forceinline__ RtCursor rt_cursor_cells(const int *cells, int nc) {
   return c;
 }
 
-template <bool GRID>
+template <bool GRID, int TILE>
 __device__ __forceinline__ bool rt_cursor_next(const RtKParams &p, RtCursor &c, RtItem &it) {
   while (c.pos >= c.cnt) {
     if (!GRID || c.ci >= c.nc) return false;
@@ -194,8 +195,8 @@ __device__ __forceinline__ bool rt_cursor_next(const RtKParams &p, RtCursor &c, 
   it.rec = c.rec + (size_t)c.pos * RT_REC_F4;
   it.idx = c.idx ? c.idx + c.pos : nullptr;
   it.base = c.pos;
-  it.cnt = min(RT_TILE, c.cnt - c.pos);
-  c.pos += RT_TILE;
+  it.cnt = min(TILE, c.cnt - c.pos);
+  c.pos += TILE;
   return true;
 }
 
@@ -239,11 +240,17 @@ template <bool MULTI, bool GRID>
 #define RT_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(const __grid_constant__ RtKParams p) {
-  extern __shared__ __align__(128) float4 tile_smem[];  // 2 x RT_TILE x 3 float4 (+ GRID: 2 x RT_TILE int)
-  __shared__ __align__(8) uint64_t bars[2];
-  __shared__ int s_cells[GRID ? RT_GRID_MAX_CELLS : 1];
-  __shared__ int s_table[GRID ? (1 << RT_GRID_TABLE_LOG2) : 1];
-  __shared__ int s_ncells;
+  // Scene streaming (GRID = false): the block shares one double-buffered ring of RT_TILE-record
+  // tiles, refilled under __syncthreads.  Cell lists (GRID = true): every WARP has its own ring of
+  // RT_WTILE-record tiles, its own cell set and no block barrier at all -- the lists are short,
+  // and a warp on a dense or silhouette patch no longer holds the other seven back.
+  constexpr int TILE = GRID ? RT_WTILE : RT_TILE;
+  constexpr int NRING = GRID ? RT_THREADS / 32 : 1;
+  extern __shared__ __align__(128) float4 tile_smem[];  // NRING x 2 x TILE x 3 float4 (+ GRID: NRING x 2 x TILE int)
+  __shared__ __align__(8) uint64_t bars_all[2 * NRING];
+  __shared__ int s_cells_all[GRID ? NRING * RT_GRID_MAX_CELLS : 1];
+  __shared__ int s_table_all[GRID ? NRING * (1 << RT_GRID_TABLE_LOG2) : 1];
+  __shared__ int s_ncells_all[NRING];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // warp = 8x4 pixel patch; 8 warps tile a 16x16 block as 2 columns x 4 rows
@@ -255,14 +262,20 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
   const size_t origin_stride = (size_t)((p.n_tris + RT_TILE - 1) / RT_TILE) * RT_TILE * RT_REC_F4;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int i = 0; i < 2 * NRING; ++i) mbar_init(&bars_all[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
+  const int ring_id = GRID ? warp : 0;
+  uint64_t *bars = bars_all + 2 * ring_id;
+  int *s_cells = s_cells_all + (GRID ? ring_id * RT_GRID_MAX_CELLS : 0);
+  int *s_table = s_table_all + (GRID ? ring_id * (1 << RT_GRID_TABLE_LOG2) : 0);
+  int &s_ncells = s_ncells_all[ring_id];
+  const bool issuer = GRID ? lane == 0 : threadIdx.x == 0;     // who issues the ring's TMA copies
+  auto ring_sync = [] { if (GRID) __syncwarp(); else __syncthreads(); };
   RtRing ring;
-  ring.smem = tile_smem; ring.bars = bars; ring.phase_bits = 0; ring.issued = 0;
-  ring.smem_idx = reinterpret_cast<int *>(tile_smem + 2 * RT_TILE * RT_REC_F4);
+  ring.smem = tile_smem + (size_t)ring_id * 2 * TILE * RT_REC_F4; ring.bars = bars; ring.phase_bits = 0; ring.issued = 0;
+  ring.smem_idx = reinterpret_cast<int *>(tile_smem + (size_t)NRING * 2 * TILE * RT_REC_F4) + ring_id * 2 * TILE;
 
   // dir = R * vec4(u - W/2, v - H/2, f, 1)   (skeleton.cpp:126-128)
   const float x = (float)(u - p.W / 2), y = (float)(v - p.H / 2);
@@ -301,29 +314,29 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
 
     RtCursor cursor = rt_cursor_scene(p.planes, p.n_tris);   // origin 0
     if (GRID) {
-      if (threadIdx.x == 0) s_cells[0] = block_y * gridDim.x + blockIdx.x;   // this block's own cell
-      __syncthreads();
-      cursor = rt_cursor_cells(s_cells, 1);
+      if (issuer) s_cells[0] = block_y * gridDim.x + blockIdx.x;   // this block's own cell
+      ring_sync();
+      cursor = rt_cursor_cells(s_cells, warp_live ? 1 : 0);
     }
     RtItem item;
-    bool have = rt_cursor_next<GRID>(p, cursor, item);
-    if (threadIdx.x == 0 && have) rt_ring_issue(ring, item);
+    bool have = rt_cursor_next<GRID, TILE>(p, cursor, item);
+    if (issuer && have) rt_ring_issue<TILE>(ring, item);
     while (have) {
       const int buf = ring.issued & 1;
       ++ring.issued;
-      __syncthreads();   // everyone is done with the other buffer (it held the previous tile): refill it
+      ring_sync();   // everyone is done with the other buffer (it held the previous tile): refill it
       RtItem next_item;
-      const bool have_next = rt_cursor_next<GRID>(p, cursor, next_item);
-      if (threadIdx.x == 0 && have_next) rt_ring_issue(ring, next_item);
+      const bool have_next = rt_cursor_next<GRID, TILE>(p, cursor, next_item);
+      if (issuer && have_next) rt_ring_issue<TILE>(ring, next_item);
       mbar_wait(&bars[buf], (ring.phase_bits >> buf) & 1u);
       ring.phase_bits ^= 1u << buf;
-      const float4 *T = tile_smem + (size_t)buf * RT_TILE * RT_REC_F4;
-      const int *Tidx = ring.smem_idx + buf * RT_TILE;
+      const float4 *T = ring.smem + (size_t)buf * TILE * RT_REC_F4;
+      const int *Tidx = ring.smem_idx + buf * TILE;
       const bool listed = GRID && item.idx != nullptr;
       const int base = item.base;
       const int cnt = warp_live ? item.cnt : 0;
 #ifdef RT_PROFILE_COUNTERS
-      if (threadIdx.x == 0) atomicAdd(p.counters + 12, (unsigned long long)item.cnt);
+      if (issuer) atomicAdd(p.counters + 12, (unsigned long long)item.cnt);
 #endif
       item = next_item;
       have = have_next;
@@ -513,13 +526,13 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
     const float4 *src = p.planes + (size_t)(1 + l) * origin_stride;
     // the buffer about to be refilled last held the tile before the previous
     // phase's final one; every thread left it at that phase's last barrier
-    __syncthreads();
+    ring_sync();
     RtCursor cursor = rt_cursor_scene(src, p.n_tris);
     if (GRID) {
       // the cube-map cells around this light that the block's shadow rays fall into
-      for (int i = threadIdx.x; i < (1 << RT_GRID_TABLE_LOG2); i += RT_THREADS) s_table[i] = -1;
-      if (threadIdx.x == 0) s_ncells = 0;
-      __syncthreads();
+      for (int i = lane; i < (1 << RT_GRID_TABLE_LOG2); i += 32) s_table[i] = -1;
+      if (lane == 0) s_ncells = 0;
+      __syncwarp();
       const int cell_base = (int)gridDim.x * p.blocks_y + l * 6 * RT_GRID_FACE;
       int last = -2;
 #pragma unroll
@@ -534,34 +547,35 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MIN_BLOCKS) rt_filtered_kernel(
         if (cell < 0) atomicAdd(&s_ncells, RT_GRID_MAX_CELLS + 1);   // no direction: stream the scene
         else rt_grid_mark(cell_base + cell, s_table, s_cells, &s_ncells);
       }
-      __syncthreads();
+      __syncwarp();
       if (s_ncells <= RT_GRID_MAX_CELLS) cursor = rt_cursor_cells(s_cells, s_ncells);
+      else if (!warp_active) cursor = rt_cursor_cells(s_cells, 0);
 #ifdef RT_PROFILE_COUNTERS
-      if (threadIdx.x == 0) {
+      if (lane == 0) {
         if (s_ncells > RT_GRID_MAX_CELLS) atomicAdd(p.counters + 10, 1ull);
         else atomicAdd(p.counters + 11, (unsigned long long)s_ncells);
       }
 #endif
     }
     RtItem item;
-    bool have = rt_cursor_next<GRID>(p, cursor, item);
-    if (threadIdx.x == 0 && have) rt_ring_issue(ring, item);
+    bool have = rt_cursor_next<GRID, TILE>(p, cursor, item);
+    if (issuer && have) rt_ring_issue<TILE>(ring, item);
     while (have) {
       const int buf = ring.issued & 1;
       ++ring.issued;
-      __syncthreads();
+      ring_sync();
       RtItem next_item;
-      const bool have_next = rt_cursor_next<GRID>(p, cursor, next_item);
-      if (threadIdx.x == 0 && have_next) rt_ring_issue(ring, next_item);
+      const bool have_next = rt_cursor_next<GRID, TILE>(p, cursor, next_item);
+      if (issuer && have_next) rt_ring_issue<TILE>(ring, next_item);
       mbar_wait(&bars[buf], (ring.phase_bits >> buf) & 1u);
       ring.phase_bits ^= 1u << buf;
-      const float4 *T = tile_smem + (size_t)buf * RT_TILE * RT_REC_F4;
-      const int *Tidx = ring.smem_idx + buf * RT_TILE;
+      const float4 *T = ring.smem + (size_t)buf * TILE * RT_REC_F4;
+      const int *Tidx = ring.smem_idx + buf * TILE;
       const bool listed = GRID && item.idx != nullptr;
       const int base = item.base;
       const int cnt = warp_active ? item.cnt : 0;
 #ifdef RT_PROFILE_COUNTERS
-      if (threadIdx.x == 0) atomicAdd(p.counters + 13, (unsigned long long)item.cnt);
+      if (issuer) atomicAdd(p.counters + 13, (unsigned long long)item.cnt);
 #endif
       item = next_item;
       have = have_next;
