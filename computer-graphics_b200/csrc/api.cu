@@ -192,9 +192,10 @@ int rt_upload_scene(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt
   ctx->rt_n_tris = n_tris;
   ctx->rt_n_spheres = n_spheres;
   // bound of |coordinate| over the scene, for the shadow filter's error budget
-  float m = 0.f;
+  float m = 0.f, nm = 1.f;
   for (int i = 0; i < n_tris; ++i)
     for (int k = 0; k < 3; ++k) {
+      nm = fabsf(tris[i].normal[k]) <= 1e30f ? fmaxf(nm, fabsf(tris[i].normal[k])) : 1e30f;   // NaN / inf: widest margins
       m = fmaxf(m, fabsf(tris[i].v0[k]));
       m = fmaxf(m, fabsf(tris[i].v1[k]));
       m = fmaxf(m, fabsf(tris[i].v2[k]));
@@ -202,6 +203,7 @@ int rt_upload_scene(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt
   for (int i = 0; i < n_spheres; ++i)
     for (int k = 0; k < 3; ++k) m = fmaxf(m, fabsf(spheres[i].centre[k]) + fabsf(spheres[i].radius));
   ctx->rt_world_abs = m;
+  ctx->rt_normal_abs = nm;
   return rt_prepare_scene(ctx);
 }
 

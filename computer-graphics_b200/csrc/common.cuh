@@ -99,6 +99,7 @@ struct b200_ctx {
   int opt_rt_grid = 0;               // 0 auto (scenes of RT_GRID_AUTO_TRIS triangles or more), 1 always, 2 never
   int rt_n_tris = 0, rt_n_spheres = 0;
   float rt_world_abs = 0.f;   // max |coordinate| over the uploaded scene
+  float rt_normal_abs = 1.f;  // max(1, max |normal component|): scales the 1e-5 * normal shadow-ray offset (:394)
   int pending = 0;            // 1 = RT, 2 = RAST render whose counters are not read back yet
 
   // RAST scene (device)

@@ -89,6 +89,7 @@ struct RtPrepParams {
   float focal;
   float dmax;        // upper bound of |d|_inf over the frame's primary rays
   float world_S;     // upper bound of |start - v0|_inf for any ray start in the scene
+  float n_scale;     // max(1, max |normal component|): the shadow-ray start is hit + 1e-5 * normal (:394)
   int n_lights;
   float lights[B200_MAX_LIGHTS][3];
   float4 *planes;    // [(1 + n_lights)][n_tiles * RT_TILE][3]
@@ -145,8 +146,9 @@ __global__ void rt_prep_planes_kernel(const __grid_constant__ RtPrepParams p) {
                      __double2float_ru((E + h) * (1.0 + 1e-6)));
   } else {
     const double S = (double)p.world_S;
-    const double E = 256.0 * eps * (a1 * a2 + S * (a1 + a2)) + 6.2e-5 * (a1 + a2);
-    const double slackT = 256.0 * eps * S * a1 * a2 + 1.01e-5 * N1 + 1e-6 * fabs(Dt);
+    const double ns = (double)p.n_scale;
+    const double E = 256.0 * eps * (a1 * a2 + S * (a1 + a2)) + 6.2e-5 * ns * (a1 + a2);
+    const double slackT = 256.0 * eps * S * a1 * a2 + 1.01e-5 * ns * N1 + 1e-6 * fabs(Dt);
     // light closer than 1e-3 S to the plane: the "beyond the light" argument
     // loses its margin, leave the triangle to the reference arithmetic
     if (!(fabs(Dt) > 1e-3 * S * N2) || !(fabs(Dt) - slackT > 0.0)) degenerate = true;

@@ -191,6 +191,7 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
         m = fmaxf(m, fabsf(f.lights[l][k]));
       }
     q.world_S = 2.0f * m * 1.001f + 1e-4f;
+    q.n_scale = ctx->rt_normal_abs;
     q.planes = (float4 *)ctx->rt_planes.p;
     q.origin_stride_f4 = origin_stride;
     q.dt_cam = (float *)ctx->rt_dtcam.p;

@@ -250,3 +250,13 @@ def test_interleaved_blocks_tile_the_frame(b200, renderer, cornell_rt, mode):
         renderer.set_option(b200.OPT_RT_INTERLEAVE_N, 1)
         renderer.set_option(b200.OPT_RT_BRUTEFORCE, 0)
         renderer.set_option(b200.OPT_RT_GRID, 0)
+
+
+def test_unnormalised_normals(b200, renderer):
+    """The shadow ray starts at hit + 1e-5 * normal (:394) with whatever normal the caller
+    supplies; the filter margins scale with the largest normal component."""
+    tris, sph = h.random_rt_scene(120, 77, size=0.5, n_spheres=1)
+    tris["normal"][:, :3] *= np.float32(43.0)
+    tris["normal"][::7, :3] *= np.float32(0.01)
+    run_both(b200, renderer, tris, sph, 80, 60, 60.0, h.f32(0.1, -0.1, -2.5, 1), h.yaw_R(0.2),
+             h.DEFAULT_RT_LIGHTS, "unnormalised normals")
