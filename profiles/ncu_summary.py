@@ -31,7 +31,10 @@ def report(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
+    last = {}                                   # a capture spans several frames: keep each kernel's last launch
     for r in rows[2:]:
+        last[(r[hdr.index("Kernel Name")], r[hdr.index("Grid Size")])] = r
+    for r in last.values():
         name = r[hdr.index("Kernel Name")]
         print(f"### {name}  (grid {r[hdr.index('Grid Size')]}, block {r[hdr.index('Block Size')]})")
         for k, label in KEYS.items():
@@ -43,12 +46,12 @@ def report(path):
 
 def launches(path):
     """Summarises the last frame of bench.py's TIMED region: frames start at rt_prep_planes_kernel /
-    rast_geom_kernel<0>; the end-to-end frames that follow (sliced, smaller grids) and the FFMA peak
+    rast_geom_kernel<0> (two-pass geometry) or <2> (single pass, pipelined frames); the end-to-end frames that follow (sliced, smaller grids) and the FFMA peak
     microbenchmark are not part of it."""
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
     rows = [r for r in rows if not r[4].startswith(("b200_ffma_peak_kernel", "void at::"))]
     starts = [i for i, r in enumerate(rows) if r[4].startswith(("rt_prep_planes_kernel", "void rast_geom_kernel<0>",
-                                                                 "void rast_geom_kernel<(bool)0>"))]
+                                                                 "void rast_geom_kernel<2>"))]
     frames = [rows[a:b] for a, b in zip(starts, starts[1:] + [len(rows)])]
 
     def blocks(fr):   # thread blocks of the frame's final kernel: the sliced end-to-end frames have fewer

@@ -31,7 +31,9 @@ else:
     cam = b200.make_camera(bench.RAST_CAM, focal, h.identity_R(), W, H)
     L = b200.make_rast_light(bench.RAST_LIGHT["pos"], bench.RAST_LIGHT["power"], bench.RAST_LIGHT["indirect"])
     r.rast_upload_scene(room, boxes)
+    r.set_option(b200.OPT_RAST_PIPELINED, 1)      # as bench.py runs it
     for _ in range(frames):
         r.rast_draw_device(cam, L, 0, H, rgb.data_ptr(), depth.data_ptr())
+        r.synchronize()
         st = r.stats()
 print(workload, st)
