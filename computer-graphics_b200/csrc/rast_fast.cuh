@@ -27,6 +27,18 @@ __device__ __forceinline__ unsigned long long rast_key(float zinv, int tri) {
   return ((unsigned long long)hi << 32) | (unsigned)(tri + 1);
 }
 
+// red.max on a key with an L2 evict-last policy: the 64-bit keys (66 MB at 4K) are what the
+// scatter revisits at random, while the setup records it reads and the row records it writes
+// stream through once -- the policy keeps the keys resident while those pass.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void red_max_u64_keep(unsigned long long *addr, unsigned long long v, uint64_t pol) {
+  asm volatile("red.relaxed.gpu.global.max.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(addr), "l"(v), "l"(pol) : "memory");
+}
+
 __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned chunk = gid >> RAST_CHUNK_LOG2, sub = gid & (RAST_CHUNK - 1);
@@ -44,9 +56,10 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
       const int lx = __float_as_int(A.x), rx = __float_as_int(A.y);
       const int x0 = max(lx, 0), x1 = min(rx, p.W);      // right end excluded (:504); bounds (:573)
       unsigned long long *row = p.keys + (size_t)y * p.W;
+      const uint64_t keep = l2_policy_evict_last();
       for (int x = x0; x < x1; ++x) {
         const float zinv = xadd(A.z, xmul(A.w, (float)(x - lx)));   // :543
-        if (zinv >= 0.0f) atomicMax(row + x, rast_key(zinv, t));   // :574 against the cleared buffer
+        if (zinv >= 0.0f) red_max_u64_keep(row + x, rast_key(zinv, t), keep);   // :574 against the cleared buffer
       }
       n_frag = x1 > x0 ? (unsigned long long)(x1 - x0) : 0ull;
     }
