@@ -96,6 +96,7 @@ void b200_destroy(b200_ctx *ctx) {
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->ev_copied);
   for (int i = 0; i < B200_SLICES; ++i) cudaEventDestroy(ctx->ev_slice[i]);
+  for (int i = 0; i < 64; ++i) if (ctx->tl_ev[i]) cudaEventDestroy(ctx->tl_ev[i]);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;

@@ -95,6 +95,7 @@ struct b200_ctx {
   DevBuf rt_cells;    // direction grids: per-cell counts, cursors, padded counts, offsets, scan scratch
   DevBuf rt_cell_rec, rt_cell_idx;   // the cells' lists: plane records and triangle indices
   size_t rt_n_cells = 0, rt_n_cam_cells = 0;   // of the last gridded frame (diagnostics)
+  int rt_grid_smem_set = 0;                    // the grid kernels' dynamic shared-memory limit has been raised
   int opt_rt_il_n = 1, opt_rt_il_r = 0;        // row-block interleave of rt_render_device (see the header)
   int opt_rt_grid = 0;               // 0 auto (scenes of RT_GRID_AUTO_TRIS triangles or more), 1 always, 2 never
   int rt_n_tris = 0, rt_n_spheres = 0;

@@ -257,11 +257,10 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
   if (use_grid) {
     // one private double-buffered ring per warp: records + triangle indices
     const size_t gsmem = (size_t)(RT_THREADS / 32) * 2 * RT_WTILE * (RT_REC_F4 * sizeof(float4) + sizeof(int));
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->rt_grid_smem_set) {      // per context: function attributes are per device
       CU_CHECK(ctx, cudaFuncSetAttribute(rt_filtered_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
       CU_CHECK(ctx, cudaFuncSetAttribute(rt_filtered_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-      attr_set = true;
+      ctx->rt_grid_smem_set = 1;
     }
     if (f.n_lights > 1)
       rt_filtered_kernel<true, true><<<grid, RT_THREADS, gsmem, ctx->stream>>>(p);
