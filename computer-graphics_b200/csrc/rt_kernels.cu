@@ -203,7 +203,8 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
 
   const int my_blocks = (p.blocks_y - p.il_r + p.il_n - 1) / p.il_n;
   dim3 grid((f.W + 15) / 16, my_blocks);
-  const size_t smem = 2 * (size_t)RT_TILE * RT_REC_F4 * sizeof(float4);
+  const size_t hit_smem = 27 * (size_t)RT_THREADS * sizeof(float);   // t, distance, index of the nine samples per thread
+  const size_t smem = 2 * (size_t)RT_TILE * RT_REC_F4 * sizeof(float4) + hit_smem;
 
   // ---- large scenes: per-frame direction grids, then the kernel streams cell lists ----
   bool use_grid = n > 0 && (ctx->opt_rt_grid == 1 || (ctx->opt_rt_grid == 0 && n >= RT_GRID_AUTO_TRIS));
@@ -254,14 +255,17 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
     }
   }
 
+  if (!ctx->rt_grid_smem_set) {      // per context: function attributes are per device
+    const size_t most = (size_t)(RT_THREADS / 32) * 2 * RT_WTILE * (RT_REC_F4 * sizeof(float4) + sizeof(int)) + hit_smem;
+    CU_CHECK(ctx, cudaFuncSetAttribute(rt_filtered_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+    CU_CHECK(ctx, cudaFuncSetAttribute(rt_filtered_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+    CU_CHECK(ctx, cudaFuncSetAttribute(rt_filtered_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_CHECK(ctx, cudaFuncSetAttribute(rt_filtered_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->rt_grid_smem_set = 1;
+  }
   if (use_grid) {
     // one private double-buffered ring per warp: records + triangle indices
-    const size_t gsmem = (size_t)(RT_THREADS / 32) * 2 * RT_WTILE * (RT_REC_F4 * sizeof(float4) + sizeof(int));
-    if (!ctx->rt_grid_smem_set) {      // per context: function attributes are per device
-      CU_CHECK(ctx, cudaFuncSetAttribute(rt_filtered_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-      CU_CHECK(ctx, cudaFuncSetAttribute(rt_filtered_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-      ctx->rt_grid_smem_set = 1;
-    }
+    const size_t gsmem = (size_t)(RT_THREADS / 32) * 2 * RT_WTILE * (RT_REC_F4 * sizeof(float4) + sizeof(int)) + hit_smem;
     if (f.n_lights > 1)
       rt_filtered_kernel<true, true><<<grid, RT_THREADS, gsmem, ctx->stream>>>(p);
     else
