@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
     unsigned occluded = 0;
     // g = hit - light per ray; boxes of the pixel's and the warp's bundles
     float glo[3] = {INFINITY, INFINITY, INFINITY}, ghi[3] = {-INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
+#pragma unroll(GRID ? 1 : 9)   // grid kernels: smaller code (their warps run out of step and miss in the instruction cache)
     for (int k = 0; k < 9; ++k) {
       if ((active >> k) & 1u) {
         const float gx = -xsub(Lx, xadd(cx, xmul(HT(k), dxs[k / 3])));
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
       const float mid = ax == 0 ? wc[0] : (ax == 1 ? wc[1] : wc[2]);
       float alo[3] = {INFINITY, INFINITY, INFINITY}, ahi[3] = {-INFINITY, -INFINITY, -INFINITY};
       float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
+#pragma unroll(GRID ? 1 : 9)   // grid kernels: smaller code (their warps run out of step and miss in the instruction cache)
       for (int k = 0; k < 9; ++k) {
         if ((active >> k) & 1u) {
           const float g[3] = {-xsub(Lx, xadd(cx, xmul(HT(k), dxs[k / 3]))), -xsub(Ly, xadd(cy, xmul(HT(k), dys[k % 3]))),
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
       __syncwarp();
       const int cell_base = (int)gridDim.x * p.blocks_y + l * 6 * RT_GRID_FACE;
       int last = -2;
-#pragma unroll
+#pragma unroll(GRID ? 1 : 9)   // grid kernels: smaller code (their warps run out of step and miss in the instruction cache)
       for (int k = 0; k < 9; ++k) {
         if (!((active >> k) & 1u)) continue;
         const float gx = -xsub(Lx, xadd(cx, xmul(HT(k), dxs[k / 3])));
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
 
     // sphere occluders + the lighting tail of DirectLight, then (single light)
     // the pixelColour accumulation in the reference's order (:151-156)
-#pragma unroll
+#pragma unroll(GRID ? 1 : 9)   // grid kernels: smaller code (their warps run out of step and miss in the instruction cache)
     for (int k = 0; k < 9; ++k) {
       if (!((active >> k) & 1u)) continue;
       const float px = xadd(cx, xmul(HT(k), dxs[k / 3])), py = xadd(cy, xmul(HT(k), dys[k % 3])),
