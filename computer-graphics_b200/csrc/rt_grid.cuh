@@ -153,8 +153,11 @@ __global__ void __launch_bounds__(256) rt_grid_bin_kernel(const __grid_constant_
     const unsigned base = (unsigned)(p.gx * p.gy) + (unsigned)(o - 1) * 6u * RT_GRID_FACE;
     constexpr int G1 = RT_GRID_G / 8;      // coarse cells per face edge
     static_assert(G1 == 8, "one 8x8 coarse level");
-#pragma unroll 1
-    for (int face = 0; face < 6; ++face) {
+    // whole faces first (lanes 0..5), then 8x8 coarse cells, then the cells
+    unsigned faces = __ballot_sync(0xffffffffu, lane < 6 && rt_grid_test_light(q0, q1, q2, lane, 0, 0, RT_GRID_G, RT_GRID_G));
+    while (faces) {
+      const int face = __ffs(faces) - 1;
+      faces &= faces - 1;
 #pragma unroll 1
       for (int r1 = 0; r1 < 2; ++r1) {
         const int x1 = lane & 7, y1 = r1 * 4 + (lane >> 3);
