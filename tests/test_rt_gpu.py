@@ -260,3 +260,27 @@ def test_unnormalised_normals(b200, renderer):
     tris["normal"][::7, :3] *= np.float32(0.01)
     run_both(b200, renderer, tris, sph, 80, 60, 60.0, h.f32(0.1, -0.1, -2.5, 1), h.yaw_R(0.2),
              h.DEFAULT_RT_LIGHTS, "unnormalised normals")
+
+
+def test_tessellated_frame_matches_the_plain_cornell_frame(b200, renderer, cornell_rt):
+    """the tessellated box is the same surface, so its frame must equal the
+    plain Cornell frame except where a sample falls on a tessellation edge (ties / ulp-level
+    differences of the hit distance): a built-in cross-check of the large-scene path."""
+    tris, sph = cornell_rt
+    tess, _ = b200.scene_cornell_rt_tessellated(12)       # 4032 triangles: direction grids on
+    # (not the default pose: with cam z = -3 and an integer focal length the outline of the box
+    # falls exactly on pixel-centre rays and every outline sample is a tie)
+    c = b200.make_camera(h.f32(0.013, -0.021, -3.02, 1), 163.7, h.identity_R(), 200, 160)
+    a = renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
+    b = renderer.render_raytrace(tess, sph, c, h.DEFAULT_RT_LIGHTS)
+    miss_a, miss_b = np.isinf(a["depth"]), np.isinf(b["depth"])
+    assert np.count_nonzero(miss_a != miss_b) <= 0.002 * miss_a.size            # same silhouette up to edge samples
+    hit = ~miss_a & ~miss_b
+    assert np.allclose(a["depth"][hit], b["depth"][hit], rtol=2e-5, atol=0)
+    # spheres keep their index; triangle hits map back to their parent (144 children each)
+    ia, ib = a["index"][hit], b["index"][hit]
+    parent = np.where(ib >= 0, ib // 144, ib)
+    assert np.count_nonzero(parent != ia) <= 0.002 * hit.sum()                  # ties on shared parent edges
+    diff = np.abs(a["rgb"] - b["rgb"]).max(axis=-1)
+    assert np.count_nonzero(diff > 1e-4) <= 0.01 * diff.size                    # shadow / tessellation edges only
+    assert np.median(diff) <= 1e-6
