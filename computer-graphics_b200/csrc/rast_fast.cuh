@@ -143,7 +143,9 @@ __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_
   const size_t q = (size_t)y * p.W + x;
   float out[3] = {0.f, 0.f, 0.f};
   const bool interior = y >= 1 && y <= p.H - 2 && x >= 1 && x <= p.W - 2;
-  if (interior) {
+  // five empty taps average to +0 exactly: nothing to compute (most pixels of a sparse scene)
+  const bool any = (owner[c0] & owner[c0 - RS_HW] & owner[c0 + RS_HW] & owner[c0 - 1] & owner[c0 + 1]) >= 0;
+  if (interior && any) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float acc[3];
