@@ -32,7 +32,7 @@
 
 constexpr int RAST_LIST_CAP = 2048;   // tile list entries sorted in shared memory
 constexpr int RAST_BATCH = 32;        // triangles per shared-memory row batch
-constexpr int RAST_CHUNK_LOG2 = 1;    // rows per work item of the per-row kernels (2^k consecutive rows of one triangle)
+constexpr int RAST_CHUNK_LOG2 = 0;    // rows per work item of the per-row kernels (2^k consecutive rows of one triangle)
 constexpr int RAST_CHUNK = 1 << RAST_CHUNK_LOG2;
 
 struct RastVtx {
