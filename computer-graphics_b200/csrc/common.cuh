@@ -187,9 +187,12 @@ static inline void tl_mark(b200_ctx *ctx, const char *name) {
 // rows [a, b) of the packed frame are final on ctx->stream: start their copy to the host (no-op unless sliced)
 int band_slice_done(b200_ctx *ctx, int a, int b);
 // slice boundaries of a band of `rows` rows split k ways on multiples of `align` rows
+// (slices shrink towards the end, 1 - ((k - i) / k)^2 of the rows before edge i: the copy of the
+// last slice is the only one that nothing overlaps)
 static inline int band_slice_edge(int row0, int rows, int i, int k, int align) {
   if (i >= k) return row0 + rows;
-  const int e = (int)((long long)rows * i / k) / align * align;
+  const long long rem = (long long)(k - i) * (k - i), all = (long long)k * k;
+  const int e = (int)((long long)rows * (all - rem) / all) / align * align;
   return row0 + e;
 }
 int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int32_t *d_index,
