@@ -492,7 +492,8 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
     // of the box's longest axis and keep a tight box around each half.
     float wc2[3] = {0.f, 0.f, 0.f}, wh2[3] = {0.f, 0.f, 0.f}, wnorm2 = 0.f;
     bool two = false;
-    if (GRID && warp_active) {
+    // (a compact bundle -- extent below 3 % of its distance from the light -- is left alone)
+    if (GRID && warp_active && fmaxf(wh[0], fmaxf(wh[1], wh[2])) > 0.03f * wnorm) {
       const int ax = (wh[0] >= wh[1] && wh[0] >= wh[2]) ? 0 : (wh[1] >= wh[2] ? 1 : 2);
       const float mid = ax == 0 ? wc[0] : (ax == 1 ? wc[1] : wc[2]);
       float alo[3] = {INFINITY, INFINITY, INFINITY}, ahi[3] = {-INFINITY, -INFINITY, -INFINITY};
