@@ -168,7 +168,7 @@ struct RtFrame {
   float lights[8][7];  // pos[4], colour[3]
 };
 #define B200_MAX_LIGHTS 8
-constexpr int RT_GRID_AUTO_TRIS = 1536;   // B200_OPT_RT_GRID = 0: scenes this large get direction grids
+constexpr int RT_GRID_AUTO_TRIS = 1024;   // B200_OPT_RT_GRID = 0: scenes this large get direction grids
 
 // spec = true: pipelined (no host synchronisation; see b200_ctx::rast_spec)
 int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row0, int row1,

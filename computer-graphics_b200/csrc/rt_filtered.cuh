@@ -40,6 +40,7 @@ constexpr int RT_GRID_FACE = RT_GRID_G * RT_GRID_G;
 constexpr int RT_WTILE = 64;               // records per tile of a warp's private ring (grid kernels)
 constexpr int RT_GRID_MAX_CELLS = 96;      // shadow phase: distinct cells one warp (8x4 pixels, 288 rays) may walk, else it streams the scene
 constexpr int RT_GRID_TABLE_LOG2 = 8;      // hash set used to collect them
+constexpr int RT_SEEN_LOG2 = 8, RT_SEEN = 1 << RT_SEEN_LOG2;   // per-warp set of triangles already met in this light phase
 
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+/sm_100a PTX) ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

@@ -255,6 +255,9 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
   __shared__ int s_cells_all[GRID ? NRING * RT_GRID_MAX_CELLS : 1];
   __shared__ int s_table_all[GRID ? NRING * (1 << RT_GRID_TABLE_LOG2) : 1];
   __shared__ int s_ncells_all[NRING];
+  // grid kernels: the L0 survivors a warp has already worked on in this light phase (a triangle
+  // is in the list of every cell it overlaps; a warp that walks several cells meets it again)
+  __shared__ int s_seen_all[GRID ? NRING * RT_SEEN : 1];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // warp = 8x4 pixel patch; 8 warps tile a 16x16 block as 2 columns x 4 rows
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
   int *s_cells = s_cells_all + (GRID ? ring_id * RT_GRID_MAX_CELLS : 0);
   int *s_table = s_table_all + (GRID ? ring_id * (1 << RT_GRID_TABLE_LOG2) : 0);
   int &s_ncells = s_ncells_all[ring_id];
+  int *s_seen = s_seen_all + (GRID ? ring_id * RT_SEEN : 0);
   const bool issuer = GRID ? lane == 0 : threadIdx.x == 0;     // who issues the ring's TMA copies
   auto ring_sync = [] { if (GRID) __syncwarp(); else __syncthreads(); };
   RtRing ring;
@@ -540,9 +544,11 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
     // phase's final one; every thread left it at that phase's last barrier
     ring_sync();
     RtCursor cursor = rt_cursor_scene(src, p.n_tris);
+    bool dedupe = false;
     if (GRID) {
       // the cube-map cells around this light that the block's shadow rays fall into
       for (int i = lane; i < (1 << RT_GRID_TABLE_LOG2); i += 32) s_table[i] = -1;
+      for (int i = lane; i < RT_SEEN; i += 32) s_seen[i] = -1;
       if (lane == 0) s_ncells = 0;
       __syncwarp();
       const int cell_base = (int)gridDim.x * p.blocks_y + l * 6 * RT_GRID_FACE;
@@ -562,6 +568,7 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
       __syncwarp();
       if (s_ncells <= RT_GRID_MAX_CELLS) cursor = rt_cursor_cells(s_cells, s_ncells);
       else if (!warp_active) cursor = rt_cursor_cells(s_cells, 0);
+      dedupe = s_ncells > 1 && s_ncells <= RT_GRID_MAX_CELLS;
 #ifdef RT_PROFILE_COUNTERS
       if (lane == 0) {
         if (s_ncells > RT_GRID_MAX_CELLS) atomicAdd(p.counters + 10, 1ull);
@@ -606,6 +613,18 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
             const float mN2 = fmaf(nx, wc2[0], fmaf(ny, wc2[1], nz * wc2[2])) +
                               fmaf(fabsf(nx), wh2[0], fmaf(fabsf(ny), wh2[1], fabsf(nz) * wh2[2]));
             pass = rt_box_may_hit_light<GRID>(q0, q1, q2, wc2, wh2, Eg2) && !(mN2 + 1.1f * Eg2 < q2.z);
+          }
+          if (GRID && pass && listed && dedupe) {
+            // met in an earlier cell of this phase?  (open addressing; a full table only means
+            // that the triangle is worked on again, which changes nothing)
+            const int tri = Tidx[r0 + lane];
+            unsigned hsh = ((unsigned)tri * 2654435761u) >> (32 - RT_SEEN_LOG2);
+            for (int probe = 0; probe < 8; ++probe) {
+              const int old = atomicCAS(s_seen + hsh, -1, tri);
+              if (old == tri) { pass = false; break; }
+              if (old == -1) break;
+              hsh = (hsh + 1) & (RT_SEEN - 1);
+            }
           }
         }
         unsigned mask = __ballot_sync(0xffffffffu, pass);

@@ -152,7 +152,7 @@ int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int
   return rt_launch_filtered(ctx, f, p);
 }
 
-// scenes this large get direction grids (declared in common.cuh; measured crossover at 4K: ~1300 triangles)
+// scenes this large get direction grids (declared in common.cuh; measured crossover at 4K: ~800 triangles)
 constexpr unsigned long long RT_GRID_MAX_ENTRIES = 1ull << 26;   // 64 Mi list entries = 3.25 GiB
 
 int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {

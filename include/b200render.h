@@ -131,7 +131,7 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
 #define B200_OPT_RAST_PIPELINED 4
 /* Raytracer direction grids (per-frame lists of the triangles each 16x16 pixel
  * block and each cube-map cell around a light can see): 0 = automatic (scenes of
- * 1536 triangles or more), 1 = always, 2 = never.  Results are identical. */
+ * 1024 triangles or more), 1 = always, 2 = never.  Results are identical. */
 #define B200_OPT_RT_GRID 5
 /* Raytracer work split for N cooperating contexts (one per GPU) that render the SAME row
  * range into one full-frame buffer: with INTERLEAVE_N = n > 1 and INTERLEAVE_R = r this
