@@ -25,8 +25,12 @@ def run_both(b200, renderer, tris, sph, W, H, focal, cam, R, lights, what, brute
     c = b200.make_camera(cam, focal, R, W, H)
     want = h.oracle_rt_render(W, H, focal, cam, R, h.lights_array(lights), tris, sph if sph is not None and len(sph) else None)
     renderer.set_option(b200.OPT_RT_BRUTEFORCE, 0)
-    got = renderer.render_raytrace(tris, sph, c, lights)
-    st = renderer.stats()
+    renderer.set_option(b200.OPT_RT_GRID, 2)          # the scene-streaming kernel, whatever the scene size
+    try:
+        got = renderer.render_raytrace(tris, sph, c, lights)
+        st = renderer.stats()
+    finally:
+        renderer.set_option(b200.OPT_RT_GRID, 0)
     check_equal(got, want, what + " [filtered]")
     assert st["primary_rays"] == want["primary"] and st["shadow_rays"] == want["shadow"]
     # the same frame through the direction grids (automatic only for large scenes)
@@ -161,10 +165,12 @@ def test_grid_tessellated_scene(b200, renderer):
     for the direction grids to switch on by themselves."""
     tris, sph = b200.scene_cornell_rt_tessellated(10)        # 2800 triangles
     assert len(tris) == 2800
-    _, _, st = run_both(b200, renderer, tris, sph, 150, 110, 75.0, h.f32(0, 0, -3, 1), h.identity_R(),
-                        h.DEFAULT_RT_LIGHTS, "tessellated 2800", brute=False)
-    # with the lists the kernel launches next to the binning kernels; without them only prep + render
-    assert st["kernel_launches"] >= 7
+    run_both(b200, renderer, tris, sph, 150, 110, 75.0, h.f32(0, 0, -3, 1), h.identity_R(),
+             h.DEFAULT_RT_LIGHTS, "tessellated 2800", brute=False)
+    # automatic mode: with the lists the kernel launches next to the binning kernels; without them only prep + render
+    c = b200.make_camera(h.f32(0, 0, -3, 1), 75.0, h.identity_R(), 150, 110)
+    renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS, want=("rgb",))
+    assert renderer.stats()["kernel_launches"] >= 7
     run_both(b200, renderer, tris, sph, 97, 61, 50.0, h.f32(0.2, -0.1, -0.7, 1), h.yaw_R(-0.6),
              [((0.3, -0.6, -0.2, 1), (9, 9, 9)), ((-0.4, 0.5, -0.9, 1), (4, 5, 6))], "tessellated, inside, 2 lights",
              brute=False)
