@@ -106,6 +106,8 @@ void b200_destroy(b200_ctx *ctx);
 const char *b200_last_error(const b200_ctx *ctx);
 /* The CUDA stream (cudaStream_t) every call on this context is enqueued on. */
 void *b200_stream(b200_ctx *ctx);
+/* Waits for everything enqueued on the context.  Also the point where a pipelined
+ * raster frame (B200_OPT_RAST_PIPELINED) is verified, and rendered again if needed. */
 int b200_synchronize(b200_ctx *ctx);
 /* Makes the context enqueue on a caller-owned stream (e.g. the one the caller's
  * collectives run on); NULL restores the context's own stream. */
@@ -184,7 +186,10 @@ int draw_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_s
                   int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
                   uint32_t *argb_out);
 
-/* Band variant: argb_out is band-sized, (row_end - row_begin) * W. */
+/* Band variant: argb_out is band-sized, (row_end - row_begin) * W.  Frames of a
+ * megapixel or more come back in slices copied on a second stream while the next
+ * slice is rendered (pass pinned memory to benefit); the call returns when the
+ * whole band is in argb_out. */
 int draw_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris,
                        const rt_sphere *spheres, int n_spheres, const camera_t *cam,
                        const light_t *lights, int n_lights, int row_begin, int row_end,
