@@ -1,5 +1,7 @@
+import os
 import sys, os, importlib
-sys.path.insert(0,"/root/repo"); sys.path.insert(0,"/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, numpy as np
 import helpers as h, bench
 b=importlib.import_module("computer-graphics_b200")
