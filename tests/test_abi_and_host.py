@@ -151,3 +151,30 @@ dist.destroy_process_group()
                           "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
                          capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_committed_launch_lists_parse():
+    """profiles/ncu_summary.py finds the timed frame of every committed ncu launch list (the
+    lists also hold the sliced end-to-end frames and the FFMA peak microbenchmark)."""
+    want = {"rt_cornell_4k": ("rt_prep_planes_kernel", "rt_filtered_kernel<0, 0>"),
+            "rt_tess100k_4k": ("rt_grid_bin_kernel<1>", "rt_filtered_kernel<0, 1>"),
+            "rast_soup_4k": ("rast_geom_kernel<2>", "rast_scatter_kernel", "rast_resolve_kernel"),
+            "rast_cornell_4k": ("rast_fill_kernel<5>", "rast_post_kernel")}
+    for workload, kernels in want.items():
+        path = os.path.join(ROOT, "profiles", "r01", f"launches_{workload}.csv")
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "ncu_summary.py"), path],
+                             capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0, out.stderr
+        assert "last timed frame" in out.stdout
+        for k in kernels:
+            assert k in out.stdout, (workload, k)
+        assert "b200_ffma_peak_kernel" not in out.stdout
+
+
+def test_bench_sample_windows():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.sample_windows(2160, 1, 1) == [(1079, 1)]
+    w = bench.sample_windows(2160, 30, 16)
+    assert len(w) == 30 and w[0] == (0, 16) and w[-1] == (2144, 16)
+    assert all(b[0] >= a[0] + 16 for a, b in zip(w, w[1:]))          # disjoint, top to bottom
