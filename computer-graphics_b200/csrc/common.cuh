@@ -106,7 +106,7 @@ struct b200_ctx {
   // RAST scene (device)
   DevBuf rast_src;    // rast_triangle[n] clipped list
   int rast_n_tris = 0;
-  DevBuf rast_setup, rast_rowsA, rast_rowsB, rast_bins, rast_tile_count, rast_tmp;
+  DevBuf rast_setup, rast_rowsA, rast_rowsB, rast_bins, rast_tile_count, rast_tmp, rast_tile_bits;
   DevBuf rast_keys;      // fast path: 64-bit (zinv, triangle) key per pixel
   int rast_has_shadow = 0;   // the uploaded list can contain shadow-volume triangles
   int opt_rast_path = 0;     // 0 auto, 1 ordered tiles, 2 scatter (shadow-free lists only)

@@ -79,6 +79,10 @@ struct RastParams {
   const unsigned long long *n_tris_dev, *n_chunks_dev;
   int spread_in_setup;   // long lists: rast_setup_kernel hands the row chunks out itself (no rast_spread_kernel<0>)
   unsigned *tile_count, *tile_off, *tile_cursor;
+  // short lists (n_tris <= RAST_BITS_MAX_TRIS): a tile's list is a bit per triangle -- no count /
+  // scan / append passes and nothing to sort, the bits come out in list order
+  unsigned *tile_bits;
+  int bits_words;    // words per tile (0: the list representation above)
   int *bins, *bins_tmp;
   unsigned bin_cap;
   float *depth, *screen, *low, *high;
@@ -130,6 +134,7 @@ __device__ __forceinline__ void warp_spread(int n, int a, int b, int c, int d, F
   }
 }
 
+constexpr int RAST_BITS_MAX_TRIS = 2048;
 constexpr int SETUP_THREADS = 256;
 constexpr int TRI_WORDS = sizeof(rast_triangle) / 4, SETUP_WORDS = sizeof(RastSetup) / 4;
 
@@ -433,6 +438,7 @@ __global__ void rast_spread_kernel(const __grid_constant__ RastParams p, int blo
     if (WHAT == 0) { p.chunk_owner[(unsigned)x0 + k] = tri; return; }
     const size_t tile = (size_t)(y0 + k / w - p.ty0) * p.tiles_x + x0 + k % w;
     if (WHAT == 1) { atomicAdd(p.tile_count + tile, 1u); return; }
+    if (WHAT == 3) { atomicOr(p.tile_bits + tile * p.bits_words + (tri >> 5), 1u << (tri & 31)); return; }
     const unsigned pos = atomicAdd(p.tile_cursor + tile, 1u);
     const unsigned at = p.tile_off[tile] + pos;
     if (at < p.bin_cap) p.bins[at] = tri;
@@ -451,6 +457,7 @@ static void rast_spread_launch(b200_ctx *ctx, const RastParams &p, int what) {
   const dim3 grid(per_block ? n : (n + 255) / 256);
   if (what == 0) rast_spread_kernel<0><<<grid, 256, 0, ctx->stream>>>(p, per_block);
   else if (what == 1) rast_spread_kernel<1><<<grid, 256, 0, ctx->stream>>>(p, per_block);
+  else if (what == 3) rast_spread_kernel<3><<<grid, 256, 0, ctx->stream>>>(p, per_block);
   else rast_spread_kernel<2><<<grid, 256, 0, ctx->stream>>>(p, per_block);
   ctx->stats.kernel_launches++;
   tl_mark(ctx, "rast_spread_kernel");
@@ -536,15 +543,45 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
 
   const int tile_x = blockIdx.x, tile_y = p.ty0 + blockIdx.y;
   const size_t tile = (size_t)blockIdx.y * p.tiles_x + tile_x;
-  const unsigned off = p.tile_off[tile];
-  const int cnt = (int)min(p.tile_off[tile + 1] - off, p.bin_cap > off ? p.bin_cap - off : 0u);
+  unsigned off = 0;
+  int cnt = 0;
+  if (!p.bits_words) {
+    off = p.tile_off[tile];
+    cnt = (int)min(p.tile_off[tile + 1] - off, p.bin_cap > off ? p.bin_cap - off : 0u);
+  }
   const int lx_ = threadIdx.x & (TS - 1), ly_ = threadIdx.x >> TS_LOG2;
   const int x = (tile_x << TS_LOG2) + lx_, y = (tile_y << TS_LOG2) + ly_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // ---- the tile's triangle list in ascending order ----
   const int *sorted;
-  if (cnt <= RAST_LIST_CAP) {
+  if (p.bits_words) {
+    // bit per triangle: thread i expands word i after an exclusive prefix of the word populations
+    // (bits_words <= 64: two warps' worth, scanned through shared memory)
+    const int nwords = p.bits_words;
+    unsigned word = 0;
+    if ((int)threadIdx.x < nwords) word = __ldg(p.tile_bits + tile * nwords + threadIdx.x);
+    if (warp < 2) {                       // bits_words <= 64: the first two warps scan the word populations
+      const int pc = __popc(word);
+      int incl = pc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) scratch[warp] = (unsigned)incl;
+      // warp 1 needs warp 0's total: both publish, the block barrier below orders the reads
+      scratch[2 + threadIdx.x] = (unsigned)(incl - pc);
+    }
+    __syncthreads();
+    if (warp < 2) {
+      int at = (int)scratch[2 + threadIdx.x] + (warp == 1 ? (int)scratch[0] : 0);
+      for (unsigned w = word; w; w &= w - 1) list[at++] = (int)threadIdx.x * 32 + (__ffs(w) - 1);
+    }
+    cnt = (int)(scratch[0] + scratch[1]);
+    __syncthreads();
+    sorted = list;
+  } else if (cnt <= RAST_LIST_CAP) {
     int m = 1;
     while (m < cnt) m <<= 1;
     for (int i = threadIdx.x; i < m; i += NT) list[i] = i < cnt ? p.bins[off + i] : INT_MAX;
@@ -843,17 +880,27 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   p.shadow = (int *)ctx->rast_shadow.p;
   p.index = (int *)ctx->rast_index.p;
 
-  CU_CHECK(ctx, cudaMemsetAsync(p.tile_count, 0, sizeof(unsigned) * (size_t)(n_tiles + 1), ctx->stream));
+  const bool bits = n <= RAST_BITS_MAX_TRIS;      // short list: bit-per-triangle tile lists
+  if (bits) {
+    p.bits_words = (n + 31) / 32 > 0 ? (n + 31) / 32 : 1;
+    if (int rc = ensure(ctx, ctx->rast_tile_bits, sizeof(unsigned) * (size_t)n_tiles * p.bits_words)) return rc;
+    p.tile_bits = (unsigned *)ctx->rast_tile_bits.p;
+    CU_CHECK(ctx, cudaMemsetAsync(p.tile_bits, 0, sizeof(unsigned) * (size_t)n_tiles * p.bits_words, ctx->stream));
+  } else {
+    CU_CHECK(ctx, cudaMemsetAsync(p.tile_count, 0, sizeof(unsigned) * (size_t)(n_tiles + 1), ctx->stream));
+  }
   if (n > 0) {
     rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     tl_mark(ctx, "rast_setup_kernel");
     if (!p.spread_in_setup) rast_spread_launch(ctx, p, 0);
-    rast_spread_launch(ctx, p, 1);
+    rast_spread_launch(ctx, p, bits ? 3 : 1);
   }
-  rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
-  ctx->stats.kernel_launches++;
-  tl_mark(ctx, "rast_scan_kernel");
+  if (!bits) {
+    rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
+    ctx->stats.kernel_launches++;
+    tl_mark(ctx, "rast_scan_kernel");
+  }
   CU_CHECK(ctx, cudaGetLastError());
   if (!spec) {
     // the bin array is sized from the scanned total: read it back (tiny, one sync)
@@ -873,7 +920,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     ctx->stats.kernel_launches++;
     tl_mark(ctx, "rast_rows_kernel");
   }
-  if (n > 0 && bin_cap > 0) rast_spread_launch(ctx, p, 2);
+  if (n > 0 && bin_cap > 0 && !bits) rast_spread_launch(ctx, p, 2);
   dim3 grid(p.tiles_x, p.tiles_y);
   switch (ts) {
     case 3: rast_fill_kernel<3><<<grid, 64, 0, ctx->stream>>>(p); break;
