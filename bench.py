@@ -2,24 +2,29 @@
 """Benchmark of the two hot paths on B200 (contract: see the task prompt).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload rt_cornell_4k|rt_tess100k_4k|rast_cornell_4k|rast_soup_4k]
+                    [--workload rt_cornell_4k|rt_tess100k_4k|rast_cornell_4k|rast_soup_4k|...]
 
-One JSON line on stdout (rank 0).  The headline line is the raytracer on
-BASELINE config 3 (Cornell box at 3840x2160, 9 spp, shadow rays, rows banded over
-the GPUs): metric Mrays/s = (primary + shadow rays) / s, whole job.  The same
-line carries the rasteriser figure (frames/s on BASELINE config 4, the 1M-triangle
-soup at 3840x2160) under "raster" when --workload is left at its default.
+One JSON line on stdout (rank 0).  The headline line is the raytracer on BASELINE
+config 3 (Cornell box at 3840x2160, 9 spp, shadow rays, rows shared by the GPUs):
+metric Mrays/s = (primary + shadow rays) / s, whole job.  With --workload left at its
+default the same line carries, as nested objects with the same keys,
+    "raster"       BASELINE config 4: frames/s of the 1M-triangle soup at 3840x2160
+    "rt_tess100k"  BASELINE config 5: Mrays/s of the 100 800-triangle Cornell box at 3840x2160
 
-A "step" is one frame.  `value` times the device-resident path (scene already in
-HBM) with CUDA events on the launching stream; `e2e` times the host-pointer C-ABI
-call (H2D of the scene from pinned memory, render, D2H of the packed framebuffer
-into pinned memory).  N > 1: one process per GPU (torchrun), each rank renders a
-band of rows; the bands are assembled on rank 0 by an NCCL gather inside the
-timed region.
+A "step" is one frame.  `value` times the device-resident path (scene already in HBM)
+with CUDA events on the launching stream; `e2e` times the host-pointer C-ABI call (H2D
+of the scene from pinned memory, render, D2H of the packed framebuffer into pinned
+memory).  N > 1: one process per GPU (torchrun); every rank stores its share of the frame
+straight into rank 0's frame over NVLink (or, --gather nccl, an NCCL gather) inside the
+timed region; afterwards rank 0 renders the whole frame alone and bit-compares it with
+the assembled one ("parity").
 
---impl reference times the reference's own CPU renderer (oracle/_ref, the
-unmodified reference compiled as a library) on the box's host cores, on a bounded
-sample of rows of the same frame, with one process per core.
+`cpu_baseline` (N = 1) runs the unmodified reference (oracle/_ref) on one core over a
+bounded sample of the same frame and bit-compares what it rendered with the GPU's pixels.
+
+--impl reference times the reference's own CPU renderer (oracle/_ref, the unmodified
+reference compiled as a library) on the box's host cores, one process per core, on a
+bounded sample of rows of the same frame.  That arm never loads the product library.
 """
 import argparse
 import importlib
@@ -36,9 +41,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-FLOP_PER_RT_TEST = 39.0          # SURVEY.md §8(d): always-executed stage of one ray-triangle test
+FLOP_PER_RT_TEST = 39.0          # SURVEY.md 8(d): always-executed stage of one ray-triangle test
 RAST_BYTES_PER_PIXEL = 16.0      # RGB f32 + depth f32 written once
 RAST_BYTES_PER_TRI = 84.0        # input triangle read once
+PROFILE_ROUND = "r02"
 
 WORKLOADS = {
     # name: (kind, W, H, focal)
@@ -49,21 +55,25 @@ WORKLOADS = {
     "rast_soup_4k": ("rast", 3840, 2160, 1536.0),
     "rast_cornell_default": ("rast", 900, 720, 512.0),
 }
+DEFAULT_WORKLOADS = ["rt_cornell_4k", "rast_soup_4k", "rt_tess100k_4k"]
+NESTED_KEY = {"rast_soup_4k": "raster", "rt_tess100k_4k": "rt_tess100k"}
 RT_CAM = (0.0, 0.0, -3.0, 1.0)
 RT_LIGHTS = [((0.0, -0.5, -0.7, 1.0), (14.0, 14.0, 14.0))]
 RAST_CAM = (0.0, 0.0, -3.001, 1.0)
 RAST_LIGHT = dict(pos=(0.0, -0.5, 0.0, 1.0), power=(20.0, 20.0, 20.0), indirect=(0.2, 0.2, 0.2))
+TESS_WINDOW = (1680, 1800, 480, 1)     # x0, y0, w, h of the config-5 CPU sample: sphere outline, floor, shadow edge
 
 
-def captured_traffic(workload):
-    """DRAM bytes per launch of the workload's dominant kernel, from the committed ncu capture."""
-    path = os.path.join(ROOT, "profiles", "r01", "traffic.json")
-    try:
-        with open(path) as f:
-            t = json.load(f).get(workload)
-        return (t["traffic_bytes"], t["kernel"]) if t else (None, None)
-    except (OSError, ValueError, KeyError):
-        return None, None
+def profile_json(name):
+    """profiles/<round>/<name>: figures read out of the committed ncu captures."""
+    for rnd in (PROFILE_ROUND, "r01"):
+        path = os.path.join(ROOT, "profiles", rnd, name)
+        try:
+            with open(path) as f:
+                return json.load(f), f"profiles/{rnd}/{name}"
+        except (OSError, ValueError):
+            continue
+    return {}, None
 
 
 def measured_peaks():
@@ -72,6 +82,37 @@ def measured_peaks():
         with open(path) as f:
             return json.load(f), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def workload_config(workload, world):
+    """Names the workload; identical in the B200 arm and the reference arm."""
+    kind, W, H, focal = WORKLOADS[workload]
+    c = {"workload": workload, "width": W, "height": H, "focal": focal}
+    if kind == "rt":
+        c.update(spp=9, triangles=100800 if workload == "rt_tess100k_4k" else 28, spheres=1, lights=len(RT_LIGHTS))
+    else:
+        c.update(triangles_in=1_000_000 if workload == "rast_soup_4k" else 30)
+    c["parallelism"] = f"rows of one frame shared by {world} GPU(s)"
+    c["l2"] = "GPU arm: L2 flushed between timed steps (256 MiB write)"
+    return c
+
+
+def scenes_rt(workload):
+    import helpers as h
+    return h.scene_cornell_rt_tessellated(60) if workload == "rt_tess100k_4k" else h.golden_cornell_rt()
+
+
+_rast_scene_cache = {}
+
+
+def scenes_rast(workload):
+    import helpers as h
+    if workload not in _rast_scene_cache:
+        if workload == "rast_soup_4k":
+            _rast_scene_cache[workload] = (h.scene_soup_rast(1_000_000), np.zeros(0, h.RAST_TRI))
+        else:
+            _rast_scene_cache[workload] = h.golden_cornell_rast()
+    return _rast_scene_cache[workload]
 
 
 class ClockSampler:
@@ -124,28 +165,36 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm: the unmodified reference on the host cores
+# the unmodified reference on the host cores (reference arm and cpu_baseline)
 # ------------------------------------------------------------------------------------------
-def _ref_rt_rows_worker(args):
-    """Renders rows [y0, y0+h) of the W x H frame with the reference's own Draw.  The
-    crop is expressed through the translation column of R (dir = R * (x, y, f, 1),
-    raytracer/Source/skeleton.cpp:126-128), exact for an identity rotation."""
+def window_R(W, H, x0, y0, w, hh):
+    """R whose translation column turns a w x hh frame into the window at (x0, y0) of the W x H
+    frame: dir = R * (u - w/2, v - hh/2, f, 1) (raytracer/Source/skeleton.cpp:126-128); exact for
+    integer offsets and an identity rotation."""
     import helpers as h
-    W, H, focal, y0, hh, tris_b, sph_b = args
-    tris = np.frombuffer(tris_b, h.RT_TRI) if tris_b is not None else None
-    sph = np.frombuffer(sph_b, h.RT_SPHERE) if sph_b is not None else None
     R = h.identity_R()
+    R[12] = float(x0 - W // 2 + w // 2)
     R[13] = float(y0 - H // 2 + hh // 2)
+    return R
+
+
+def _ref_rt_window_worker(args):
+    """Renders the window (x0, y0, w, hh) of the W x H frame with the reference's own Draw."""
+    import helpers as h
+    W, H, focal, x0, y0, w, hh, tris_b, sph_b, want_pixels = args
+    tris = np.frombuffer(tris_b, h.RT_TRI)
+    sph = np.frombuffer(sph_b, h.RT_SPHERE)
     t0 = time.perf_counter()
-    h.ref_rt_draw(W, hh, focal, h.f32(*RT_CAM), R, h.lights_array(RT_LIGHTS), tris, sph)
-    return time.perf_counter() - t0
+    out = h.ref_rt_draw(w, hh, focal, h.f32(*RT_CAM), window_R(W, H, x0, y0, w, hh), h.lights_array(RT_LIGHTS), tris, sph)
+    dt = time.perf_counter() - t0
+    return (dt, out["rgb"]) if want_pixels else dt
 
 
 def _oracle_rt_count_worker(args):
     import helpers as h
-    W, H, focal, y0, hh, tris, sph = args
-    o = h.oracle_rt_render(W, H, focal, h.f32(*RT_CAM), h.identity_R(), h.lights_array(RT_LIGHTS),
-                           np.frombuffer(tris, h.RT_TRI), np.frombuffer(sph, h.RT_SPHERE), y0, y0 + hh, want=())
+    W, H, focal, x0, y0, w, hh, tris, sph, _ = args
+    o = h.oracle_rt_render(w, hh, focal, h.f32(*RT_CAM), window_R(W, H, x0, y0, w, hh), h.lights_array(RT_LIGHTS),
+                           np.frombuffer(tris, h.RT_TRI), np.frombuffer(sph, h.RT_SPHERE), want=())
     return o["primary"] + o["shadow"]
 
 
@@ -159,53 +208,52 @@ def sample_windows(H, n_windows, rows_each):
 
 
 def run_reference(args, workload):
+    """--impl reference.  No product code on this path: scenes come from tests/helpers.py (numpy)
+    and the committed fixtures, rendering from oracle/_ref."""
     import helpers as h
     from multiprocessing import get_context
     kind, W, H, focal = WORKLOADS[workload]
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return None
-    cores = os.cpu_count() or 1
-    b200 = importlib.import_module("computer-graphics_b200")
+    cores = args.ref_cores or os.cpu_count() or 1
     if kind != "rt":
-        return run_reference_rast(args, workload, b200, cores)
+        return run_reference_rast(args, workload, cores)
+    tris, sph = scenes_rt(workload)
+    warmup, steps = args.warmup, args.steps
     if workload == "rt_tess100k_4k":
-        tris, sph = b200.scene_cornell_rt_tessellated(60)
-        rows_each, per_proc = 1, 1          # ~0.9 s per row per core at 100 800 triangles
+        # ~16 ms per pixel per core at 100 800 triangles: a 96-pixel piece of a row per core and step
+        x0, y0, _, _ = TESS_WINDOW
+        wins = [(x0 + 96 * (i % 8), y0 + 40 * (i // 8), 96, 1) for i in range(cores)]
+        warmup, steps = min(warmup, 1), min(steps, 3)
     else:
-        tris, sph = b200.scene_cornell_rt()
-        rows_each, per_proc = 16, 2
-    wins = sample_windows(H, cores * per_proc, rows_each)
-    jobs = [(W, H, focal, y0, hh, tris.tobytes(), sph.tobytes()) for (y0, hh) in wins]
+        wins = [(0, y, W, hh) for (y, hh) in sample_windows(H, cores * 2, 16)]
+    jobs = [(W, H, focal, x, y, w, hh, tris.tobytes(), sph.tobytes(), False) for (x, y, w, hh) in wins]
     ctx = get_context("fork")
     with ctx.Pool(cores) as pool:
-        rays = sum(pool.map(_oracle_rt_count_worker, jobs))   # untimed: ray count of the sample
+        rays = sum(pool.map(_oracle_rt_count_worker, jobs, chunksize=1))   # untimed: ray count of the sample
         times = []
-        for step in range(args.warmup + args.steps):
+        for step in range(warmup + steps):
             t0 = time.perf_counter()
-            pool.map(_ref_rt_rows_worker, jobs, chunksize=1)
+            pool.map(_ref_rt_window_worker, jobs, chunksize=1)
             dt = time.perf_counter() - t0
-            if step >= args.warmup:
+            if step >= warmup:
                 times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = rays / (ms * 1e-3) / 1e6
-    sample = f"{len(wins)} windows x {rows_each} rows of the {W}x{H} frame ({rays} rays) per step"
-    line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+    sample = f"{len(wins)} windows of {wins[0][2]}x{wins[0][3]} px of the {W}x{H} frame ({rays} rays) per step"
+    return {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "width": W, "height": H, "focal": focal, "spp": 9,
-                       "triangles": int(len(tris)), "spheres": int(len(sph))},
+            "config": workload_config(workload, args.gpus),
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    return line
 
 
-def run_reference_rast(args, workload, b200, cores):
+def run_reference_rast(args, workload, cores):
     """Rasteriser reference arm: whole reference Draw (geometry + clip + triangle loop +
-    post) at the workload's resolution; single-threaded by construction, so `cores`
-    independent frames are rendered concurrently and frames/s is their aggregate."""
-    import helpers as h
+    post) at the workload's resolution; single-threaded by construction, so independent
+    frames are rendered concurrently and frames/s is their aggregate."""
     from multiprocessing import get_context
     kind, W, H, focal = WORKLOADS[workload]
     n_proc = max(1, min(cores, 8))      # each process owns ~365 MB of static frame buffers at 4K
@@ -215,86 +263,88 @@ def run_reference_rast(args, workload, b200, cores):
         times = []
         for step in range(warmup + steps):
             t0 = time.perf_counter()
-            pool.map(_ref_rast_worker, [(workload,)] * n_proc, chunksize=1)
+            pool.map(_ref_rast_worker, [(workload, False)] * n_proc, chunksize=1)
             dt = time.perf_counter() - t0
             if step >= warmup:
                 times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = n_proc / (ms * 1e-3)
-    line = {"impl": "reference", "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+    return {"impl": "reference", "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "width": W, "height": H, "focal": focal},
+            "config": workload_config(workload, args.gpus),
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": n_proc, "kind": "reference",
                              "sample": f"{n_proc} whole frames per step, one per process"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    return line
-
-
-_rast_scene_cache = {}
-
-
-def rast_scene(b200, workload):
-    if workload not in _rast_scene_cache:
-        if workload == "rast_soup_4k":
-            _rast_scene_cache[workload] = (b200.scene_soup_rast(1_000_000), np.zeros(0, b200.RAST_TRI))
-        else:
-            _rast_scene_cache[workload] = b200.scene_cornell_rast()
-    return _rast_scene_cache[workload]
 
 
 def _ref_rast_worker(args):
     import helpers as h
-    (workload,) = args
+    workload, want_pixels = args
     kind, W, H, focal = WORKLOADS[workload]
-    b200 = importlib.import_module("computer-graphics_b200")
-    room, boxes = rast_scene(b200, workload)
+    room, boxes = scenes_rast(workload)
     lib = h.ref_lib(h.ref_rast_name(W, H))
-    n = h.c_i(0)
+    argb = np.zeros((H, W), np.uint32) if want_pixels else None
     t0 = time.perf_counter()
     rc = lib.ref_rast_draw(h.c_f(focal), h.ptr(h.f32(*RAST_CAM)), h.ptr(h.identity_R()), h.ptr(h.f32(*RAST_LIGHT["pos"])),
                            h.ptr(h.f32(*RAST_LIGHT["power"])), h.ptr(h.f32(*RAST_LIGHT["indirect"])),
                            h.ptr(room), h.c_i(len(room)), h.ptr(boxes), h.c_i(len(boxes)),
-                           None, None, None, None, None, None, None, None, h.c_i(0), None, None)
+                           h.ptr(argb), None, None, None, None, None, None, None, h.c_i(0), None, None)
     assert rc == 0
-    return time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    return (dt, argb) if want_pixels else dt
 
 
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
 def cpu_baseline_rt(b200, r, workload, W, H, focal, tris, sph):
-    """The unmodified reference (oracle/_ref), one core, on a bounded sample of rows of
-    the same frame; the sample's ray count comes from the (parity-tested) device counters."""
+    """The unmodified reference (oracle/_ref), one core, on a bounded sample of the same frame.
+    The GPU renders the same windows through the C ABI: its counters give the sample's ray
+    count, and its float colours are bit-compared with the reference's (parity on the headline
+    configuration, every run)."""
     import helpers as h
     if not h.have_ref("libref_rt.so"):
         return {"value": None, "unit": "Mrays/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref missing"}
     if workload == "rt_tess100k_4k":
-        wins = sample_windows(H, 1, 1)      # one row of 3840 pixels: ~4.7e9 ray-triangle tests, about a minute on one core
+        wins = [TESS_WINDOW]                     # ~7.5 s on one core at 100 800 triangles
     else:
-        wins = sample_windows(H, 30, 16)
-    cam = b200.make_camera(RT_CAM, focal, h.identity_R(), W, H)
-    rays, secs = 0, 0.0
-    for (y0, hh) in wins:
-        r.render_raytrace(tris, sph, cam, RT_LIGHTS, y0, y0 + hh, want=())
+        wins = [(0, y, W, hh) for (y, hh) in sample_windows(H, 30, 16)]
+    rays, secs, px, bad = 0, 0.0, 0, 0
+    for (x0, y0, w, hh) in wins:
+        cam = b200.make_camera(RT_CAM, focal, window_R(W, H, x0, y0, w, hh), w, hh)
+        got = r.render_raytrace(tris, sph, cam, RT_LIGHTS, want=("rgb",))
         st = r.stats()
         rays += st["primary_rays"] + st["shadow_rays"]
-        secs += _ref_rt_rows_worker((W, H, focal, y0, hh, tris.tobytes(), sph.tobytes()))
+        dt, ref_rgb = _ref_rt_window_worker((W, H, focal, x0, y0, w, hh, tris.tobytes(), sph.tobytes(), True))
+        secs += dt
+        px += w * hh
+        bad += int(np.count_nonzero((bits(got["rgb"]) != bits(ref_rgb)).any(axis=-1)))
     return {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "reference",
-            "sample": f"{len(wins)} windows x {wins[0][1]} rows of the {W}x{H} frame, {rays} rays, {secs:.1f} s"}
+            "sample": f"{len(wins)} windows of {wins[0][2]}x{wins[0][3]} px of the {W}x{H} frame, {rays} rays, {secs:.1f} s",
+            "parity_pixels_checked": px, "parity_rows_checked": sum(w[3] for w in wins), "mismatches": bad,
+            "parity": "float RGB of the sampled windows, GPU (render_raytrace) vs reference Draw, bit for bit"}
 
 
-def cpu_baseline_rast(workload):
+def cpu_baseline_rast(b200, r, workload, room, boxes, cam, L):
     import helpers as h
     kind, W, H, focal = WORKLOADS[workload]
     if not h.have_ref(h.ref_rast_name(W, H)):
         return {"value": None, "unit": "frames/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref missing"}
     n = 2 if workload == "rast_soup_4k" else 6
-    _ref_rast_worker((workload,))
-    secs = [_ref_rast_worker((workload,)) for _ in range(n)]
+    _, ref_argb = _ref_rast_worker((workload, True))
+    secs = [_ref_rast_worker((workload, False)) for _ in range(n)]
+    got = r.draw_raster(room, boxes, cam, L)
+    bad = int(np.count_nonzero(got != ref_argb))
     return {"value": 1.0 / float(np.median(secs)), "unit": "frames/s", "cores": 1, "kind": "reference",
-            "sample": f"{n} whole frames (median), reference Draw incl. geometry and post pass"}
+            "sample": f"{n} whole frames (median), reference Draw incl. geometry and post pass",
+            "parity_pixels_checked": W * H, "parity_rows_checked": H, "mismatches": bad,
+            "parity": "screen->buffer of the whole frame, GPU (draw_raster) vs reference Draw, bit for bit"}
 
 
 def run_b200(args, workloads):
@@ -340,16 +390,16 @@ def run_b200_one(args, workload):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- where each rank's band goes --------------------------------------------------
+    # ---- where each rank's share of the frame goes ------------------------------------
     # N == 1: plain device buffers.  N > 1: the frame lives on rank 0 and
     #   "p2p_store"  (default) every rank is handed a peer mapping of rank 0's frame
-    #                (torch symmetric memory over NVLink) and its kernels store the band
+    #                (torch symmetric memory over NVLink) and its kernels store their rows
     #                straight into it -- the exchange happens in the epilogue of the render
     #                kernels, followed by one device-side barrier;
     #   "nccl"       each rank renders into a local band, then an NCCL gather to rank 0.
     # The device entry points address outputs as full frames (pixel (x, y) at y*W + x).
     gather, gather_note, symm_handles = "none", None, []
-    band_rgb = band_depth = full_rgb = full_depth = None
+    band_rgb = band_depth = full_rgb = full_depth = frame_rgb = frame_depth = None
     if world > 1 and args.gather == "p2p":
         try:
             import torch.distributed._symmetric_memory as symm
@@ -375,15 +425,24 @@ def run_b200_one(args, workload):
 
     def exchange():
         if gather == "p2p_store":
-            symm_handles[0].barrier(channel=0)      # every band has landed in rank 0's frame
+            symm_handles[0].barrier(channel=0)      # every rank's rows have landed in rank 0's frame
         elif gather == "nccl_gather":
             dist.gather(band_rgb, list(full_rgb.view(world, rows, W, 3).unbind(0)) if rank == 0 else None, dst=0)
             dist.gather(band_depth, list(full_depth.view(world, rows, W).unbind(0)) if rank == 0 else None, dst=0)
 
+    def assembled():
+        """rank 0: the frame the exchange left behind."""
+        if gather == "p2p_store":
+            return frame_rgb, frame_depth
+        if gather == "nccl_gather":
+            return full_rgb, full_depth
+        return band_rgb, band_depth
+
     result = {}
     pinned = torch.empty(rows * W, dtype=torch.int32).pin_memory()
+    interleaved = False
     if kind == "rt":
-        tris, sph = b200.scene_cornell_rt_tessellated(60) if workload == "rt_tess100k_4k" else b200.scene_cornell_rt()
+        tris, sph = scenes_rt(workload)
         cam = b200.make_camera(RT_CAM, focal, h.identity_R(), W, H)
         r.rt_upload_scene(tris, sph)
 
@@ -401,6 +460,11 @@ def run_b200_one(args, workload):
                 r.rt_render_device(cam, RT_LIGHTS, row0, row1, p_rgb, p_depth)
             exchange()
 
+        def render_alone(d_rgb, d_depth):
+            r.set_option(b200.OPT_RT_INTERLEAVE_N, 1)
+            r.rt_render_device(cam, RT_LIGHTS, 0, H, d_rgb, d_depth)
+            r.synchronize()
+
         tris_pin = torch.from_numpy(tris.view(np.uint8).copy()).pin_memory()
         sph_pin = torch.from_numpy(sph.view(np.uint8).copy()).pin_memory()
         tris_h = tris_pin.numpy().view(b200.RT_TRI)
@@ -412,7 +476,7 @@ def run_b200_one(args, workload):
         h2d = tris.nbytes + sph.nbytes
         d2h = rows * W * 4
     else:
-        room, boxes = rast_scene(b200, workload)
+        room, boxes = scenes_rast(workload)
         cam = b200.make_camera(RAST_CAM, focal, h.identity_R(), W, H)
         L = b200.make_rast_light(RAST_LIGHT["pos"], RAST_LIGHT["power"], RAST_LIGHT["indirect"])
         r.rast_upload_scene(room, boxes)
@@ -426,6 +490,10 @@ def run_b200_one(args, workload):
             r.rast_draw_device(cam, L, row0, row1, p_rgb, p_depth)
             r.synchronize()
             exchange()
+
+        def render_alone(d_rgb, d_depth):
+            r.rast_draw_device(cam, L, 0, H, d_rgb, d_depth)
+            r.synchronize()
 
         room_pin = torch.from_numpy(room.view(np.uint8).copy()).pin_memory()
         boxes_pin = torch.from_numpy(boxes.view(np.uint8).copy() if len(boxes) else np.zeros(84, np.uint8)).pin_memory()
@@ -468,33 +536,69 @@ def run_b200_one(args, workload):
     ms, launches, st, clocks, wall = timed(step, args.steps, max(args.warmup, 3))
     # whole-job units per step (sum over ranks of what each rank processed)
     if kind == "rt":
-        units = torch.tensor([st["primary_rays"] + st["shadow_rays"], st["prim_tests"]], dtype=torch.float64, device="cuda")
+        units = torch.tensor([st["primary_rays"] + st["shadow_rays"], st["prim_tests"], st["exact_evals"]],
+                             dtype=torch.float64, device="cuda")
     else:
-        units = torch.tensor([1.0 / world, float(st["fragments"])], dtype=torch.float64, device="cuda")
+        units = torch.tensor([1.0 / world, float(st["fragments"]), 0.0], dtype=torch.float64, device="cuda")
     kernel_ms = torch.tensor([st["gpu_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(units, op=dist.ReduceOp.SUM)
         dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
+
+    # ---- N > 1: the assembled frame against rank 0 rendering the whole frame alone ----------
+    parity = None
+    if world > 1:
+        step()                                   # one more exchange whose result is inspected
+        barrier()
+        if rank == 0:
+            a_rgb, a_depth = assembled()
+            own_rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+            own_depth = torch.empty((H, W), dtype=torch.float32, device="cuda")
+            render_alone(own_rgb.data_ptr(), own_depth.data_ptr())
+            torch.cuda.synchronize()
+            bad_rgb = int((a_rgb.view(torch.int32) != own_rgb.view(torch.int32)).any(dim=-1).sum().item())
+            bad_depth = int((a_depth.view(torch.int32) != own_depth.view(torch.int32)).sum().item())
+            parity = {"assembled_frame_vs_single_gpu": "bit-exact" if bad_rgb + bad_depth == 0 else "MISMATCH",
+                      "pixels_checked": W * H, "rgb_mismatches": bad_rgb, "depth_mismatches": bad_depth,
+                      "mode": ("interleaved 16-row blocks, " if interleaved else "row bands, ") + gather}
+            del own_rgb, own_depth
+        barrier()
+        if interleaved:
+            r.set_option(b200.OPT_RT_INTERLEAVE_N, world)
+            r.set_option(b200.OPT_RT_INTERLEAVE_R, rank)
+
     ms_e2e, _, _, _, _ = timed(step_e2e, max(2, args.steps // 2), 3)
 
+    config = workload_config(workload, world)
+    detail = {"gather": gather, "gather_note": gather_note,
+              "split": (f"interleaved 16-row blocks x{world}" if interleaved else f"row bands x{world}")}
     if kind == "rt":
         rays, tests = float(units[0]), float(units[1])
         value, unit, metric = rays / (ms * 1e-3) / 1e6, "Mrays/s", "Mrays/s"
         e2e_value = rays / (ms_e2e * 1e-3) / 1e6
         fp32_peak = r.measure_fp32_peak()
-        achieved = tests * FLOP_PER_RT_TEST / (float(kernel_ms) * 1e-3) / 1e12 / world   # per GPU
+        # executed FP32 work: thread-level FADD + FMUL + 2 x FFMA of all kernels of one whole frame, from
+        # the committed ncu counters of this workload (the count does not depend on the run)
+        flops, flops_src = profile_json("rt_flops.json")
+        fl = flops.get(workload)
+        executed = float(fl["flop_per_frame"]) if fl else None
+        achieved = executed / world / (float(kernel_ms) * 1e-3) / 1e12 if executed else None     # per GPU
+        delivered = tests * FLOP_PER_RT_TEST / (float(kernel_ms) * 1e-3) / 1e12 / world
         roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp32_peak, "traffic": None,
-                    "kernel": "rt_prep_planes_kernel + rt_filtered_kernel", "kernel_ms": float(kernel_ms),
+                    "frac": achieved / fp32_peak if achieved else None, "traffic": None,
+                    "kernel": "all kernels of the frame (rt_prep_planes_kernel, grid kernels, rt_filtered_kernel)",
+                    "kernel_ms": float(kernel_ms),
                     "peak_source": "FFMA microbenchmark run in this process (b200_measure_fp32_peak)",
-                    "algorithmic_work": f"{FLOP_PER_RT_TEST:.0f} flop per ray-primitive test x {tests:.0f} tests",
-                    "exact_evals": st["exact_evals"]}
-        config = {"workload": workload, "width": W, "height": H, "focal": focal, "spp": 9,
-                  "triangles": int(len(tris)), "spheres": int(len(sph)), "lights": len(RT_LIGHTS),
-                  "rays_per_frame": rays,
-                  "parallelism": (f"interleaved 16-row blocks x{world}" if world > 1 and gather == "p2p_store" else f"row bands x{world}"),
-                  "gather": gather, "gather_note": gather_note,
-                  "l2": "flushed between timed steps (256 MiB write); outputs 133 MB > L2"}
+                    "executed_flop_per_frame": executed,
+                    "executed_flop_source": (f"{flops_src}: smsp__sass_thread_inst_executed_op_fadd/fmul/ffma_pred_on.sum "
+                                             "(ffma x 2) summed over the frame's launches") if fl else
+                                            "no committed counter capture for this workload: achieved/frac not stated",
+                    "work_delivered": {"tflops": delivered, "vs_peak": delivered / fp32_peak,
+                                       "definition": f"{FLOP_PER_RT_TEST:.0f} flop per ray-primitive test x {tests:.0f} tests / time: "
+                                                     "the reference's work delivered per second, NOT pipe utilisation "
+                                                     "(the filters decide most pairs without executing them)",
+                                       "exact_evals": float(units[2])}}
+        detail["rays_per_frame"] = rays
     else:
         frames = 1.0
         value, unit, metric = frames / (ms * 1e-3), "frames/s", "frames/s"
@@ -506,26 +610,32 @@ def run_b200_one(args, workload):
                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "whole raster frame (all kernels)",
                     "kernel_ms": float(kernel_ms), "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})",
                     "algorithmic_work": f"{bytes_alg / 1e6:.1f} MB per frame (16 B/pixel + 84 B/triangle)"}
-        config = {"workload": workload, "width": W, "height": H, "focal": focal, "triangles_in": int(n_in),
-                  "fragments_per_frame": float(units[1]), "parallelism": f"row bands x{world}", "gather": gather, "gather_note": gather_note,
-                  "pipelined": not args.rast_sync, "frames_rendered_twice": int(r.stats()["respeculated"] - respec0),
-                  "l2": "flushed between timed steps (256 MiB write)"}
+        detail.update(fragments_per_frame=float(units[1]), pipelined=not args.rast_sync,
+                      frames_rendered_twice=int(r.stats()["respeculated"] - respec0))
 
-    roofline["traffic"], roofline["traffic_kernel"] = captured_traffic(workload)
+    traffic, traffic_src = profile_json("traffic.json")
+    t = traffic.get(workload)
+    if t:
+        roofline["traffic"] = t.get("traffic_bytes")
+        roofline["traffic_kernel"] = t.get("kernel")
+        roofline["traffic_source"] = traffic_src
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r.set_stream(None)
-        cpu = cpu_baseline_rt(b200, r, workload, W, H, focal, tris, sph) if kind == "rt" else cpu_baseline_rast(workload)
+        if kind == "rt":
+            cpu = cpu_baseline_rt(b200, r, workload, W, H, focal, tris, sph)
+        else:
+            cpu = cpu_baseline_rast(b200, r, workload, room, boxes, cam, L)
 
     if rank == 0:
-        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d) * world,
-                        "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": ms_e2e,
-                        "call": "draw_raytrace_band" if kind == "rt" else "draw_raster_band"},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        result = line
+        result = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+                  "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                  "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "detail": detail,
+                  "clocks": clocks,
+                  "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d) * world,
+                          "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": ms_e2e,
+                          "call": "draw_raytrace_band" if kind == "rt" else "draw_raster_band"},
+                  "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
     r.set_stream(None)
     r.close()
     return result
@@ -543,10 +653,12 @@ def main():
                     help="rasteriser: read list/table sizes back mid-frame instead of pipelined frames")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: peer stores into rank 0's frame (default) or an NCCL gather")
+    ap.add_argument("--ref-cores", type=int, default=0,
+                    help="--impl reference: worker processes (default: every host core; the count is reported)")
     args = ap.parse_args()
     # default: the headline raytracer line (BASELINE config 3) carrying the rasteriser figure
-    # (BASELINE config 4) as a nested "raster" object
-    workloads = ["rt_cornell_4k", "rast_soup_4k"] if args.workload == "default" else [args.workload]
+    # (config 4) and the large raytracer scene (config 5) as nested objects
+    workloads = DEFAULT_WORKLOADS if args.workload == "default" else [args.workload]
     if args.impl == "reference":
         lines = [run_reference(args, w) for w in workloads]
     else:
@@ -554,10 +666,11 @@ def main():
     if int(os.environ.get("RANK", "0")) != 0:
         return
     line = lines[0]
-    if len(lines) > 1 and lines[1]:
-        keep = ("metric", "value", "unit", "ms_per_step", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline",
-                "steps", "warmup")
-        line["raster"] = {k: lines[1][k] for k in keep if k in lines[1]}
+    keep = ("metric", "value", "unit", "ms_per_step", "config", "detail", "e2e", "gpu_launches", "roofline",
+            "cpu_baseline", "parity", "steps", "warmup")
+    for w, nested in zip(workloads[1:], lines[1:]):
+        if nested:
+            line[NESTED_KEY.get(w, w)] = {k: nested[k] for k in keep if k in nested}
     print(json.dumps(line), flush=True)
 
 

@@ -228,15 +228,15 @@ static int fill_frame(b200_ctx *ctx, const camera_t *cam, const light_t *lights,
   return B200_OK;
 }
 
-int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, int n_lights,
-                     int row_begin, int row_end, float *d_rgb, float *d_depth, int32_t *d_index,
-                     uint32_t *d_argb) {
-  if (!ctx) return B200_EINVAL;
+// One RT frame on device buffers; il_n / il_r: the 16-row block interleave (1, 0 = every row).
+static int rt_frame_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, int n_lights,
+                           int row_begin, int row_end, float *d_rgb, float *d_depth, int32_t *d_index,
+                           uint32_t *d_argb, int il_n, int il_r) {
   RtFrame f;
   if (int rc = fill_frame(ctx, cam, lights, n_lights, row_begin, row_end, f)) return rc;
   cudaSetDevice(ctx->device);
   if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // the counters are shared
-  f.il_n = ctx->opt_rt_il_n; f.il_r = ctx->opt_rt_il_r;
+  f.il_n = il_n; f.il_r = il_r;
   ctx->stats.kernel_launches = 0;
   CU_CHECK(ctx, cudaMemsetAsync(ctx->counters.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -251,12 +251,23 @@ int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, 
   return B200_OK;
 }
 
+// The interleave options apply to this entry only (see the header); the host-pointer
+// entries always render every row of their band.
+int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, int n_lights,
+                     int row_begin, int row_end, float *d_rgb, float *d_depth, int32_t *d_index,
+                     uint32_t *d_argb) {
+  if (!ctx) return B200_EINVAL;
+  return rt_frame_device(ctx, cam, lights, n_lights, row_begin, row_end, d_rgb, d_depth, d_index, d_argb,
+                         ctx->opt_rt_il_n, ctx->opt_rt_il_r);
+}
+
 static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const rast_light_t *light, int row_begin,
                       int row_end, float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb, bool allow_spec);
 
 // Waits for the last render and reads its device counters back.  A pipelined raster
 // frame is checked here against the sizes it was launched with.
 static int finish_stats(b200_ctx *ctx) {
+  CU_CHECK(ctx, cudaSetDevice(ctx->device));   // a re-render below allocates and launches: on this context's GPU
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   if (!ctx->pending) return B200_OK;
   const unsigned long long *c = (const unsigned long long *)ctx->pinned + 32;
@@ -318,7 +329,7 @@ static void band_slices_begin(b200_ctx *ctx, uint32_t *host_row0, const uint32_t
 }
 // every slice copy is ordered before whatever is enqueued on ctx->stream next
 static int band_slices_end(b200_ctx *ctx) {
-  ctx->slice_host = nullptr;
+  ctx->slice_host = nullptr;   // first: cleared even when the event calls below fail
   CU_CHECK(ctx, cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
   CU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
   return B200_OK;
@@ -341,10 +352,10 @@ int render_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris, con
   if (rgb_out) if (int rc = ensure(ctx, ctx->out_rgb, npix * 3 * sizeof(float))) return rc;
   if (depth_out) if (int rc = ensure(ctx, ctx->out_depth, npix * sizeof(float))) return rc;
   if (index_out) if (int rc = ensure(ctx, ctx->out_index, npix * sizeof(int32_t))) return rc;
-  if (int rc = rt_render_device(ctx, cam, lights, n_lights, row_begin, row_end,
-                                rgb_out ? (float *)ctx->out_rgb.p : nullptr,
-                                depth_out ? (float *)ctx->out_depth.p : nullptr,
-                                index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr))
+  if (int rc = rt_frame_device(ctx, cam, lights, n_lights, row_begin, row_end,
+                               rgb_out ? (float *)ctx->out_rgb.p : nullptr,
+                               depth_out ? (float *)ctx->out_depth.p : nullptr,
+                               index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr, 1, 0))
     return rc;
   const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
   if (int rc = copy_out(ctx, rgb_out, (float *)ctx->out_rgb.p + 3 * off, cnt * 3 * sizeof(float))) return rc;
@@ -384,17 +395,23 @@ int draw_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const
   const bool gridded = ctx->opt_rt_grid == 1 || (ctx->opt_rt_grid == 0 && n_tris >= RT_GRID_AUTO_TRIS);
   const int k = (!gridded && (size_t)rows * cam->width >= ((size_t)1 << 20)) ? B200_SLICES : 1;
   band_slices_begin(ctx, argb_out, (const uint32_t *)ctx->out_argb.p, row_begin, cam->width);
-  for (int i = 0; i < k; ++i) {
+  int rc_loop = B200_OK;
+  for (int i = 0; i < k && rc_loop == B200_OK; ++i) {
     RtFrame fi = f;
     fi.row0 = band_slice_edge(row_begin, rows, i, k, 16);
     fi.row1 = band_slice_edge(row_begin, rows, i + 1, k, 16);
     if (fi.row1 <= fi.row0) continue;
-    if (int rc = rt_launch(ctx, fi, nullptr, nullptr, nullptr, (uint32_t *)ctx->out_argb.p)) { ctx->slice_host = nullptr; return rc; }
-    if (i + 1 == k) CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    if (int rc = band_slice_done(ctx, fi.row0, fi.row1)) { ctx->slice_host = nullptr; return rc; }
+    rc_loop = rt_launch(ctx, fi, nullptr, nullptr, nullptr, (uint32_t *)ctx->out_argb.p);
+    if (rc_loop == B200_OK && i + 1 == k && cudaEventRecord(ctx->ev1, ctx->stream) != cudaSuccess)
+      rc_loop = ctx_fail(ctx, B200_ECUDA, "cudaEventRecord");
+    if (rc_loop == B200_OK) rc_loop = band_slice_done(ctx, fi.row0, fi.row1);
   }
-  if (rows <= 0) CU_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  if (int rc = band_slices_end(ctx)) return rc;
+  if (rc_loop == B200_OK && rows <= 0 && cudaEventRecord(ctx->ev1, ctx->stream) != cudaSuccess)
+    rc_loop = ctx_fail(ctx, B200_ECUDA, "cudaEventRecord");
+  // always: clears slice_host, so that no later launch on this context copies into the caller's buffer
+  const int rc_end = band_slices_end(ctx);
+  if (rc_loop) return rc_loop;
+  if (rc_end) return rc_end;
   ctx->stats.primary_rays = (uint64_t)f.W * (uint64_t)rows * 9u;
   if (int rc = enqueue_counter_readback(ctx)) return rc;
   ctx->pending = 1;
@@ -426,6 +443,7 @@ __global__ void b200_ffma_peak_kernel(float *out, int iters, float a, float b) {
 int b200_measure_fp32_peak(b200_ctx *ctx, float *tflops_out) {
   if (!ctx || !tflops_out) return B200_EINVAL;
   cudaSetDevice(ctx->device);
+  if (int rc = finish_stats(ctx)) return rc;   // ev0 / ev1 still time a pending frame
   const int blocks = ctx->sm_count * 2, threads = 1024, iters = 4096;
   DevBuf tmp;
   if (int rc = ensure(ctx, tmp, sizeof(float) * (size_t)blocks * threads)) return rc;

@@ -132,10 +132,13 @@ static void pixel_shader(o_frame *f, const o_pixel *p, const o_rtri *t, int tri_
       float D[3];
       illumination_D(f, p->pos, t->normal, D);
       for (int k = 0; k < 3; ++k) {
-        f->screen[3 * q + k] = t->color[k] * (D[k] + f->indirect[k]);
+        f->screen[3 * q + k] = t->color[k] * (D[k] + f->indirect[k]);   /* :580, the global as it stands */
         f->low[3 * q + k] = t->color[k] * (D[k] + 0.0f);
         f->high[3 * q + k] = t->color[k] * (D[k] + 0.4f);
       }
+      /* :585 leaves the GLOBAL indirectLightPowerPerArea at 0.2f * vec3(1): only the first
+       * shaded fragment of a Draw ever sees the value the global had on entry */
+      f->indirect[0] = f->indirect[1] = f->indirect[2] = 0.2f * 1.0f;
       f->depth[q] = p->zinv;
       if (f->index) f->index[q] = tri_index;
     } else if (p->zinv > f->depth[q] && t->color[0] < 0) {

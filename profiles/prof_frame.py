@@ -27,7 +27,7 @@ if kind == "rt":
         r.rt_render_device(cam, bench.RT_LIGHTS, 0, H, rgb.data_ptr(), depth.data_ptr())
         st = r.stats()
 else:
-    room, boxes = bench.rast_scene(b200, workload)
+    room, boxes = bench.scenes_rast(workload)
     cam = b200.make_camera(bench.RAST_CAM, focal, h.identity_R(), W, H)
     L = b200.make_rast_light(bench.RAST_LIGHT["pos"], bench.RAST_LIGHT["power"], bench.RAST_LIGHT["indirect"])
     r.rast_upload_scene(room, boxes)

@@ -9,7 +9,7 @@ w=sys.argv[1]
 kind,W,H,f=bench.WORKLOADS[w]
 r=b.Renderer(0)
 rgb=torch.empty((H,W,3),device="cuda"); depth=torch.empty((H,W),device="cuda")
-room,boxes=bench.rast_scene(b,w)
+room,boxes=bench.scenes_rast(w)
 cam=b.make_camera(bench.RAST_CAM,f,h.identity_R(),W,H)
 L=b.make_rast_light(bench.RAST_LIGHT["pos"],bench.RAST_LIGHT["power"],bench.RAST_LIGHT["indirect"])
 r.rast_upload_scene(room,boxes)

@@ -358,3 +358,66 @@ def random_clipped_list(n, seed, W, H, focal, shadow_frac=0.3, size=0.5):
     t["color"][sh] = -1.0
     compute_normals(t)
     return t
+
+
+# ----------------------------------------------------------------------------
+# BASELINE's synthetic scenes restated in numpy (so that bench.py's reference arm and
+# the CPU tests never load the product library); byte-equal to the product's builders
+# (computer-graphics_b200/host/scenes.cpp), which tests/test_abi_and_host.py checks.
+# ----------------------------------------------------------------------------
+def golden_cornell_rt():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rt_cornell.npz"))
+    return g["tris"].view(RT_TRI).copy(), g["spheres"].view(RT_SPHERE).copy()
+
+
+def golden_cornell_rast():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rast_ref_cornell_64x48.npz"))
+    return g["room"].view(RAST_TRI).copy(), g["boxes"].view(RAST_TRI).copy()
+
+
+def scene_cornell_rt_tessellated(n):
+    """BASELINE config 5: every Cornell triangle split into n*n similar triangles that keep the
+    parent's colour and normal (n = 60: 100 800), plus the sphere."""
+    base, sph = golden_cornell_rt()
+    f = np.float32
+    i_idx, j_idx = [], []
+    for i in range(n):
+        for j in range(2 * (n - i) - 1):
+            i_idx.append(i); j_idx.append(j)
+    i_idx, j_idx = np.array(i_idx), np.array(j_idx)
+    jj, odd = j_idx // 2, (j_idx & 1) == 1
+    # (s, u) of the three vertices of child (i, j)
+    s = np.stack([np.where(odd, jj + 1, jj), jj + 1, jj], axis=1)
+    u = np.stack([i_idx, np.where(odd, i_idx + 1, i_idx), i_idx + 1], axis=1)
+    fs = (s.astype(f) / f(n)).astype(f)          # (float)s / (float)n
+    fu = (u.astype(f) / f(n)).astype(f)
+    per = len(i_idx)
+    out = np.zeros(len(base) * per, RT_TRI)
+    p0 = base["v0"][:, None, None, :3]; p1 = base["v1"][:, None, None, :3]; p2 = base["v2"][:, None, None, :3]
+    d1 = (p1 - p0).astype(f); d2 = (p2 - p0).astype(f)
+    pts = ((p0 + (fs[None, :, :, None] * d1).astype(f)).astype(f) + (fu[None, :, :, None] * d2).astype(f)).astype(f)
+    pts = pts.reshape(len(base) * per, 3, 3)
+    for k, name in enumerate(("v0", "v1", "v2")):
+        out[name][:, :3] = pts[:, k]
+        out[name][:, 3] = 1.0
+    out["color"] = np.repeat(base["color"], per, axis=0)
+    out["normal"] = np.repeat(base["normal"], per, axis=0)
+    return out, sph
+
+
+def scene_soup_rast(n, seed=0x5EED, edge=0.01):
+    """BASELINE config 4: std::mt19937(seed) raw outputs, 24 bits each -> [0, 1)."""
+    f = np.float32
+    raw = np.random.RandomState(seed)._bit_generator.random_raw(12 * n).astype(np.uint32)   # init_genrand seeding
+    u = ((raw >> np.uint32(8)).astype(f) * f(1.0 / 16777216.0)).astype(f).reshape(n, 12)
+
+    def uni(lo, hi, x):
+        return (f(lo) + ((f(hi) - f(lo)) * x).astype(f)).astype(f)
+    t = np.zeros(n, RAST_TRI)
+    t["v0"][:, :3] = uni(-1, 1, u[:, 0:3])
+    t["v1"][:, :3] = (t["v0"][:, :3] + uni(-edge, edge, u[:, 3:6])).astype(f)
+    t["v2"][:, :3] = (t["v0"][:, :3] + uni(-edge, edge, u[:, 6:9])).astype(f)
+    t["v0"][:, 3] = t["v1"][:, 3] = t["v2"][:, 3] = 1.0
+    t["color"] = uni(0.15, 0.75, u[:, 9:12])
+    compute_normals(t)
+    return t

@@ -178,3 +178,47 @@ def test_bench_sample_windows():
     w = bench.sample_windows(2160, 30, 16)
     assert len(w) == 30 and w[0] == (0, 16) and w[-1] == (2144, 16)
     assert all(b[0] >= a[0] + 16 for a, b in zip(w, w[1:]))          # disjoint, top to bottom
+
+
+def test_numpy_scene_generators_match_the_product_builders(b200):
+    """bench.py's reference arm builds BASELINE's synthetic scenes with tests/helpers.py (numpy)
+    so that it never loads the product library: both generators must give the same bytes."""
+    a, sa = b200.scene_cornell_rt_tessellated(60)
+    c, sc = h.scene_cornell_rt_tessellated(60)
+    assert len(a) == 100800 and a.tobytes() == c.tobytes() and sa.tobytes()[:32] == sc.tobytes()[:32]
+    assert b200.scene_cornell_rt_tessellated(7)[0].tobytes() == h.scene_cornell_rt_tessellated(7)[0].tobytes()
+    assert b200.scene_soup_rast(50000).tobytes() == h.scene_soup_rast(50000).tobytes()
+    assert b200.scene_soup_rast(3000, seed=7, edge=0.03).tobytes() == h.scene_soup_rast(3000, seed=7, edge=0.03).tobytes()
+    room, boxes = h.golden_cornell_rast()
+    r2, b2 = b200.scene_cornell_rast()
+    assert room.tobytes() == r2.tobytes() and boxes.tobytes() == b2.tobytes()
+
+
+def test_reference_arm_does_not_load_the_product_library():
+    """bench.py --impl reference runs the unmodified reference only: nothing of the product is
+    imported or loaded on that path (the driver records the .so files the arm loads)."""
+    code = ("import sys, argparse; sys.argv=['bench.py']; import bench\n"
+            "a = argparse.Namespace(gpus=1, steps=1, warmup=0, ref_cores=2)\n"
+            "line = bench.run_reference(a, 'rt_cornell_default')\n"
+            "assert line['impl'] == 'reference' and line['value'] > 0\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libb200render' not in maps, 'product library loaded in the reference arm'\n"
+            "assert 'computer-graphics_b200' not in ' '.join(sys.modules), 'product package imported'\n"
+            "print('OK')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_bench_window_trick_is_exact():
+    """bench.py / the full-size tests render a window of the 4K frame as a small frame whose R
+    carries the offset in its translation column; the oracle's pixels must be those of the crop."""
+    sys.path.insert(0, ROOT)
+    import bench
+    tris, sph = h.golden_cornell_rt()
+    W, H, f = 96, 64, 64.0
+    L = h.lights_array(h.DEFAULT_RT_LIGHTS)
+    full = h.oracle_rt_render(W, H, f, h.f32(0, 0, -3, 1), h.identity_R(), L, tris, sph)
+    x0, y0, w, hh = 37, 21, 30, 11
+    win = h.oracle_rt_render(w, hh, f, h.f32(0, 0, -3, 1), bench.window_R(W, H, x0, y0, w, hh), L, tris, sph)
+    assert np.array_equal(win["rgb"].view(np.uint32), full["rgb"][y0:y0 + hh, x0:x0 + w].view(np.uint32))
+    assert np.array_equal(win["index"], full["index"][y0:y0 + hh, x0:x0 + w])

@@ -123,3 +123,36 @@ def test_whole_draw_default_config():
     assert np.array_equal(bits(o["rgb"]), bits(r["rgb"])) and np.array_equal(o["argb"], r["argb"])
     assert np.array_equal(bits(o["depth"]), bits(r["depth"])) and np.array_equal(o["shadow"], r["shadow"])
     assert not o["rgb"][0].any() and not o["rgb"][:, 0].any()   # border never written
+
+
+@pytest.mark.parametrize("entry", [0.15, 0.205, 0.0])
+def test_indirect_entry_value_reaches_only_the_first_shaded_fragment(entry):
+    """indirectLightPowerPerArea is a global that PixelShader leaves at 0.2 (:585): the value it
+    has when Draw is entered (0.15 at start-up :54, 0.2 +- 0.005 after keys 1 / 2) is seen by
+    the first shaded fragment only.  Oracle == the reference's own Draw, whole frame and
+    every intermediate buffer; and the frame differs from the steady-state one in at most
+    that fragment's pixel (before the post pass spreads it over its 5-tap neighbours)."""
+    if not h.have_ref(h.ref_rast_name(64, 48)):
+        pytest.skip("oracle/_ref not built")
+    W, H, f = 64, 48, 36.0
+    light = dict(h.DEFAULT_RAST_LIGHT, indirect=(entry, entry, entry))
+    room, boxes = h.ref_rast_testmodel(W, H)
+    r = h.ref_rast_draw(W, H, f, h.DEFAULT_RAST_CAM, h.identity_R(), light, room, boxes)
+    o = h.oracle_rast_draw(W, H, f, h.DEFAULT_RAST_CAM, h.identity_R(), light, room, boxes)
+    assert np.array_equal(bits(o["rgb"]), bits(r["rgb"])) and np.array_equal(o["argb"], r["argb"])
+    assert np.array_equal(bits(o["low"]), bits(r["low"])) and np.array_equal(bits(o["high"]), bits(r["high"]))
+    steady = h.oracle_rast_draw(W, H, f, h.DEFAULT_RAST_CAM, h.identity_R(), h.DEFAULT_RAST_LIGHT, room, boxes)
+    assert np.count_nonzero((bits(o["screen"]) != bits(steady["screen"])).any(axis=-1)) <= 1
+    # a random clipped list whose first triangle survives at its first fragment's pixel
+    tl = h.random_clipped_list(40, 9, W, H, f, shadow_frac=0.2)
+    tl["v0"][0, 2] = tl["v1"][0, 2] = tl["v2"][0, 2] = 0.3          # nearest: keeps its pixels
+    for k in ("v0", "v1", "v2"):
+        tl[k][0, 3] = tl[k][0, 2] / np.float32(f)
+    tl["color"][0] = (0.4, 0.5, 0.6)
+    lc = h.f32(0.1, -0.3, 1.2, 1.0)
+    r = h.ref_rast_draw_clipped(W, H, f, lc, light, tl)
+    o = h.oracle_rast_draw_clipped(W, H, f, lc, light, tl)
+    s = h.oracle_rast_draw_clipped(W, H, f, lc, h.DEFAULT_RAST_LIGHT, tl)
+    for key in ("rgb", "screen", "low", "high", "depth"):
+        assert np.array_equal(bits(o[key]), bits(r[key])), key
+    assert np.count_nonzero((bits(o["screen"]) != bits(s["screen"])).any(axis=-1)) == 1
