@@ -61,7 +61,7 @@ RT_CAM = (0.0, 0.0, -3.0, 1.0)
 RT_LIGHTS = [((0.0, -0.5, -0.7, 1.0), (14.0, 14.0, 14.0))]
 RAST_CAM = (0.0, 0.0, -3.001, 1.0)
 RAST_LIGHT = dict(pos=(0.0, -0.5, 0.0, 1.0), power=(20.0, 20.0, 20.0), indirect=(0.2, 0.2, 0.2))
-TESS_WINDOW = (1680, 1800, 480, 1)     # x0, y0, w, h of the config-5 CPU sample: sphere outline, floor, shadow edge
+TESS_WINDOW = (1200, 1800, 1440, 1)    # x0, y0, w, h of the config-5 CPU sample: sphere outline, floor, shadow edge (~12 s on one core)
 
 
 def profile_json(name):
