@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float cc = tr->color[c];
-      col[pos][c] = xmul(cc, xadd(D[c], p.indirect[c]));            // :580
+      col[pos][c] = xmul(cc, xadd(D[c], rast_indirect(p, c, t, (size_t)(y0 + pos / RS_HW) * p.W + gx)));   // :580
       col[pos][3 + c] = xmul(cc, xadd(D[c], 0.0f));                 // :581-582
       col[pos][6 + c] = xmul(cc, xadd(D[c], 0.4f));                 // :583-584
     }

@@ -63,7 +63,10 @@ struct RastParams {
   float focal;
   float light[4];
   float power[3];
-  float indirect[3];
+  float indirect[3];   // indirectLightPowerPerArea as it stands when Draw is entered
+  // PixelShader leaves the global at 0.2 (:585), so only the first shaded fragment of a Draw sees
+  // the entry value: (triangle << 32 | pixel) of that fragment, or null when the entry value is 0.2
+  const unsigned long long *first_frag;
   const rast_triangle *src;
   int n_tris;
   RastSetup *setup;
@@ -134,6 +137,32 @@ __device__ __forceinline__ void warp_spread(int n, int a, int b, int c, int d, F
   }
 }
 
+// VertexShader of the three vertices and Interpolate's per-edge steps (:531-538) of one clipped
+// triangle (tr: v0[4] v1[4] v2[4] normal[4] color[3] as floats).  false: a vertex does not
+// convert to int (the triangle is dropped).
+__device__ __forceinline__ bool rast_tri_setup(const float *tr, float focal, int W, int H, RastSetup &s) {
+  float v[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { v[0][k] = tr[k]; v[1][k] = tr[4 + k]; v[2][k] = tr[8 + k]; }
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) ok = rast_vertex(v[k], focal, W, H, s.v[k]) && ok;
+  s.flags = tr[16] < 0 ? 1 : 0;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {                                  // Interpolate :531-538, per edge
+    const RastVtx &a = s.v[e], &b = s.v[(e + 1) % 3];
+    const float den = (float)max(max(abs(a.x - b.x), abs(a.y - b.y)), 1);
+    const float apx = xmul(a.px, a.zinv), apy = xmul(a.py, a.zinv);
+    const float bpx = xmul(b.px, b.zinv), bpy = xmul(b.py, b.zinv);
+    s.sx[e] = xdiv((float)(b.x - a.x), den);
+    s.sy[e] = xdiv((float)(b.y - a.y), den);
+    s.sz[e] = xdiv(xsub(b.zinv, a.zinv), den);
+    s.spx[e] = xdiv(xsub(bpx, apx), den);
+    s.spy[e] = xdiv(xsub(bpy, apy), den);
+  }
+  return ok;
+}
+
 constexpr int RAST_BITS_MAX_TRIS = 2048;
 constexpr int SETUP_THREADS = 256;
 constexpr int TRI_WORDS = sizeof(rast_triangle) / 4, SETUP_WORDS = sizeof(RastSetup) / 4;
@@ -159,25 +188,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) rast_setup_kernel(const __grid_
   int xmin = 0, xmax = -1;
   if (t < n_tris) {
     const float *tr = reinterpret_cast<const float *>(stage) + threadIdx.x * TRI_WORDS;   // v0[4] v1[4] v2[4] normal[4] color[3]
-    float v[3][3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { v[0][k] = tr[k]; v[1][k] = tr[4 + k]; v[2][k] = tr[8 + k]; }
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) ok = rast_vertex(v[k], p.focal, p.W, p.H, s.v[k]) && ok;
-    s.flags = tr[16] < 0 ? 1 : 0;
-#pragma unroll
-    for (int e = 0; e < 3; ++e) {                                  // Interpolate :531-538, per edge
-      const RastVtx &a = s.v[e], &b = s.v[(e + 1) % 3];
-      const float den = (float)max(max(abs(a.x - b.x), abs(a.y - b.y)), 1);
-      const float apx = xmul(a.px, a.zinv), apy = xmul(a.py, a.zinv);
-      const float bpx = xmul(b.px, b.zinv), bpy = xmul(b.py, b.zinv);
-      s.sx[e] = xdiv((float)(b.x - a.x), den);
-      s.sy[e] = xdiv((float)(b.y - a.y), den);
-      s.sz[e] = xdiv(xsub(b.zinv, a.zinv), den);
-      s.spx[e] = xdiv(xsub(bpx, apx), den);
-      s.spy[e] = xdiv(xsub(bpy, apy), den);
-    }
+    const bool ok = rast_tri_setup(tr, p.focal, p.W, p.H, s);
     if (ok) {
       const int ymin = min(s.v[0].y, min(s.v[1].y, s.v[2].y));
       const int ymax = max(s.v[0].y, max(s.v[1].y, s.v[2].y));
@@ -354,6 +365,44 @@ __device__ __forceinline__ void rast_row_record(const RastSetup &s, int Y, float
     const float lpx = xmul(px[0], zinv[0]), lpy = xmul(py[0], zinv[0]);
     const float rpx = xmul(px[1], zinv[1]), rpy = xmul(py[1], zinv[1]);
     B = make_float4(lpx, xdiv(xsub(rpx, lpx), den), lpy, xdiv(xsub(rpy, lpy), den));
+  }
+}
+
+// ---- the first shaded fragment of the Draw ---------------------------------------------------
+// PixelShader shades with the global indirectLightPowerPerArea and then sets it to 0.2 (:580,
+// :585), so the value the caller left in the global reaches exactly one fragment: the first
+// one accepted, i.e. (the depth buffer is still clear, :247) the first in-bounds fragment with
+// zinv >= 0 of the first opaque triangle that has one, rows top to bottom, x left to right
+// (:500-508).  Only launched when the entry value differs from 0.2.  Whole frame, never a band.
+__device__ __forceinline__ float rast_indirect(const RastParams &p, int k, int tri, size_t q) {
+  constexpr float steady = 0.2f * 1.0f;                                            // :585
+  if (!p.first_frag) return steady;
+  return (((unsigned long long)(unsigned)tri << 32) | (unsigned long long)q) == *p.first_frag ? p.indirect[k] : steady;
+}
+
+__global__ void rast_first_fragment_kernel(const __grid_constant__ RastParams p, unsigned long long *first) {
+  const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (t >= rast_count_tris(p)) return;
+  if (((unsigned long long)(unsigned)t << 32) > *(volatile unsigned long long *)first) return;   // an earlier triangle has one
+  const float *tr = reinterpret_cast<const float *>(p.src + t);
+  if (!(tr[16] >= 0.0f)) return;                                                   // opaque triangles only (:574)
+  RastSetup s;
+  if (!rast_tri_setup(tr, p.focal, p.W, p.H, s)) return;
+  const int ymin = min(s.v[0].y, min(s.v[1].y, s.v[2].y)), ymax = max(s.v[0].y, max(s.v[1].y, s.v[2].y));
+  const int xmin = min(s.v[0].x, min(s.v[1].x, s.v[2].x)) - 1, xmax = max(s.v[0].x, max(s.v[1].x, s.v[2].x));
+  if (xmax <= 0 || xmin >= p.W || xmax <= xmin) return;
+  s.ymin = ymin;
+  for (int y = max(ymin, 0); y <= min(ymax, p.H - 1); ++y) {
+    float4 A, B;
+    rast_row_record<false>(s, y, A, B);
+    const int lx = __float_as_int(A.x), rx = __float_as_int(A.y);
+    for (int x = max(lx, 0); x < min(rx, p.W); ++x) {
+      const float zinv = xadd(A.z, xmul(A.w, (float)(x - lx)));
+      if (zinv >= 0.0f) {
+        atomicMin(first, ((unsigned long long)(unsigned)t << 32) | (unsigned long long)((size_t)y * p.W + x));
+        return;
+      }
+    }
   }
 }
 
@@ -666,7 +715,7 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const float c = tr->color[k];
-        sc[k] = xmul(c, xadd(D[k], p.indirect[k]));   // :580
+        sc[k] = xmul(c, xadd(D[k], rast_indirect(p, k, win, q)));   // :580
         lo[k] = xmul(c, xadd(D[k], 0.0f));            // :581-582
         hi[k] = xmul(c, xadd(D[k], 0.4f));            // :583-584
       }
@@ -799,6 +848,18 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   p.chunk_owner = (int *)ctx->rast_chunks.p;
   p.chunk_cap = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
   unsigned long long *hc = (unsigned long long *)ctx->pinned;
+
+  // the entry value of indirectLightPowerPerArea reaches the first shaded fragment only (:585)
+  const float steady = 0.2f * 1.0f;
+  if (n > 0 && (memcmp(&light->indirect[0], &steady, 4) || memcmp(&light->indirect[1], &steady, 4) ||
+                memcmp(&light->indirect[2], &steady, 4))) {
+    unsigned long long *first = p.counters + 9;
+    CU_CHECK(ctx, cudaMemsetAsync(first, 0xff, sizeof(unsigned long long), ctx->stream));
+    rast_first_fragment_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(p, first);
+    ctx->stats.kernel_launches++;
+    tl_mark(ctx, "rast_first_fragment_kernel");
+    p.first_frag = first;
+  }
 
   if (fast) {
     // ---- scatter / resolve (rast_fast.cuh) ----

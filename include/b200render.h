@@ -87,7 +87,11 @@ typedef struct light_t {
 
 /* rasteriser light globals: sceneCoordinatesLightPos (or, for the clipped-list
  * entry, the camera-space lightPos), lightPower, indirectLightPowerPerArea
- * (skeleton.cpp:51-54; steady-state indirect is 0.2, see :585). */
+ * (skeleton.cpp:51-54).  `indirect` is the value the global holds when Draw is
+ * entered (0.15 at start-up :54, 0.2 +- 0.005 after keys 1 / 2): PixelShader
+ * resets the global to 0.2 after every shaded fragment (:585), so, exactly like
+ * the reference, only the first shaded fragment of the frame sees `indirect`
+ * and every other one 0.2. */
 typedef struct rast_light_t {
   float pos[4];
   float power[3];

@@ -375,3 +375,46 @@ def test_sliced_framebuffer_return(b200, renderer):
         band = np.zeros((H - 203, W), np.uint32)
         renderer.draw_raster_band(scene[0], scene[1], cam, L, 3, H - 200, band.ctypes.data)
         assert np.array_equal(band, want[3:H - 200])
+
+
+@pytest.mark.parametrize("entry", [0.15, 0.205])
+def test_indirect_entry_value_first_fragment(b200, renderer, entry):
+    """indirectLightPowerPerArea on entry (0.15 at start-up, rasteriser/Source/skeleton.cpp:54)
+    reaches the first shaded fragment only (:580, :585): whole Draw of the Cornell box (ordered
+    path), a shadow-free clipped list (scatter path), and the same frame rendered as two bands
+    (the special fragment is found on the whole frame, whichever band asks)."""
+    import torch
+    W, H, f = 64, 48, 36.0
+    light = dict(h.DEFAULT_RAST_LIGHT, indirect=(entry, entry, entry))
+    room, boxes = b200.scene_cornell_rast()
+    cam = b200.make_camera(h.DEFAULT_RAST_CAM, f, h.identity_R(), W, H)
+    L = b200.make_rast_light(light["pos"], light["power"], light["indirect"])
+    want = h.oracle_rast_draw(W, H, f, h.DEFAULT_RAST_CAM, h.identity_R(), light, room, boxes)
+    steady = h.oracle_rast_draw(W, H, f, h.DEFAULT_RAST_CAM, h.identity_R(), h.DEFAULT_RAST_LIGHT, room, boxes)
+    got = renderer.render_raster(room, boxes, cam, L)
+    assert np.array_equal(bits(got["rgb"]), bits(want["rgb"]))
+    assert np.array_equal(renderer.draw_raster(room, boxes, cam, L), want["argb"])
+    # bands through the device entry
+    rgb = torch.zeros(H, W, 3, device="cuda")
+    renderer.rast_upload_scene(room, boxes)
+    for a, b in ((0, 20), (20, H)):
+        renderer.rast_draw_device(cam, L, a, b, rgb.data_ptr(), None)
+        renderer.synchronize()
+    assert np.array_equal(bits(rgb.cpu().numpy()), bits(want["rgb"]))
+    # scatter path: shadow-free list whose first triangle keeps its first fragment
+    tl = h.random_clipped_list(40, 9, W, H, f, shadow_frac=0.0)
+    tl["v0"][0, 2] = tl["v1"][0, 2] = tl["v2"][0, 2] = 0.3
+    for k in ("v0", "v1", "v2"):
+        tl[k][0, 3] = tl[k][0, 2] / np.float32(f)
+    lc = h.f32(0.1, -0.3, 1.2, 1.0)
+    cam0 = b200.make_camera((0, 0, 0, 1), f, h.identity_R(), W, H)
+    Lc = b200.make_rast_light(lc, light["power"], light["indirect"])
+    o = h.oracle_rast_draw_clipped(W, H, f, lc, light, tl)
+    s = h.oracle_rast_draw_clipped(W, H, f, lc, h.DEFAULT_RAST_LIGHT, tl)
+    for path in (0, 1):
+        renderer.set_option(b200.OPT_RAST_PATH, path)
+        g = renderer.render_raster_clipped(tl, cam0, Lc)
+        assert np.array_equal(bits(g["rgb"]), bits(o["rgb"])), path
+    renderer.set_option(b200.OPT_RAST_PATH, 0)
+    assert not np.array_equal(bits(o["rgb"]), bits(s["rgb"]))          # the quirk is visible in this frame
+    assert want is not None and steady is not None
