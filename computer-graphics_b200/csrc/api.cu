@@ -87,7 +87,7 @@ void b200_destroy(b200_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rt_dtcam, &ctx->rt_cells, &ctx->rt_cell_rec, &ctx->rt_cell_idx, &ctx->rast_src,
                     &ctx->rast_setup, &ctx->rast_rowsA, &ctx->rast_rowsB, &ctx->rast_bins, &ctx->rast_tile_count, &ctx->rast_tile_bits,
-                    &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
+                    &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_trimeta, &ctx->rast_big, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
                     &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
                     &ctx->out_argb, &ctx->counters};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -314,7 +314,7 @@ static int finish_stats(b200_ctx *ctx) {
     // what this frame needed sizes the next pipelined frame of the same shape
     b200_ctx::RastSpec &sp = ctx->rast_spec;
     sp.tris = (unsigned long long)ctx->rast_n_tris;
-    sp.chunks = c[6]; sp.rows = c[4]; sp.bins = c[3];
+    sp.chunks = c[6]; sp.rows = c[4]; sp.bins = c[3]; sp.big = c[10];
     sp.has_shadow = ctx->rast_has_shadow;
     sp.valid = 1;
   }

@@ -17,6 +17,10 @@ __device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+// a / den for a finite den > 0: a zero numerator (an edge with dx = 0, a row whose two ends are the
+// same sample, ...) sends the whole warp through __fdiv_rn's slow path (ncu: 13 % of the small-
+// triangle kernel's instructions at 9 of 32 lanes); 0 / den = a exactly, sign included.
+__device__ __forceinline__ float xdiv_pos(float a, float den) { return a == 0.0f ? a : __fdiv_rn(a, den); }
 
 // IEEE-exact x / C for the constants the reference divides by (5, 3, 9):
 // q = x*rc; r = fma(-C, q, x); q' = fma(r, rc, q) with rc = RN(1/C) is the
@@ -108,6 +112,7 @@ struct b200_ctx {
   int rast_n_tris = 0;
   DevBuf rast_setup, rast_rowsA, rast_rowsB, rast_bins, rast_tile_count, rast_tmp, rast_tile_bits;
   DevBuf rast_keys;      // fast path: 64-bit (zinv, triangle) key per pixel
+  DevBuf rast_trimeta, rast_big;   // fast path: per-triangle row-table origin; list of the triangles too big for the small-triangle kernel
   int rast_has_shadow = 0;   // the uploaded list can contain shadow-volume triangles
   int opt_rast_path = 0;     // 0 auto, 1 ordered tiles, 2 scatter (shadow-free lists only)
   DevBuf rast_chunks;    // owner triangle of each 8-row chunk of the row tables
@@ -124,7 +129,7 @@ struct b200_ctx {
   int opt_rast_pipelined = 0;
   struct RastSpec {
     int valid = 0, has_shadow = 0, n_room = 0, n_boxes = 0, n_list = 0, W = 0, H = 0, row0 = 0, row1 = 0, fast = 0, ts = 0, whole_draw = 0;
-    unsigned long long tris = 0, chunks = 0, rows = 0, bins = 0;
+    unsigned long long tris = 0, chunks = 0, rows = 0, bins = 0, big = 0;
   } rast_spec;
   struct RastInflight {
     int active = 0, whole_draw = 0, fast = 0;

@@ -4,22 +4,31 @@
 // list order, rasteriser/Source/skeleton.cpp:574,665) is order independent: the
 // pixel ends up owned by the fragment with the largest zinv, the LATEST triangle
 // on ties.  That is a lexicographic maximum of (zinv, index), so fragments can be
-// scattered in any order with one 64-bit atomicMax per fragment on
+// scattered in any order with one 64-bit atomic max per fragment on
 //   key = zinv bits << 32 | (triangle index + 1)          (0 = empty pixel)
 // (non-negative floats order like their bit patterns; fragments with zinv < 0 or
 // NaN fail `zinv >= depth` against the cleared buffer and are never drawn).
 //
-//   rast_scatter_kernel  one thread per (triangle,row): the row record (span ends,
-//                        zinv and position steps) is derived and stored, then one
-//                        atomicMax per pixel of the span
-//   rast_resolve_kernel  per 32x8 pixel tile + 1-pixel halo: the winners are
-//                        compacted, each winning fragment is re-derived exactly
-//                        from its row record (fragment, three
-//                        calculateIllumination) into shared memory, then the 5-tap
-//                        AA / HDR mean of the post pass (:283-307; no shadow flags
-//                        => nothing is darkened) is taken from shared memory and
-//                        the frame written once.
-// No per-pixel colour buffers and no tile lists touch HBM.
+//   rast_scatter2_kernel    one thread per triangle, straight from the 84-byte list
+//                           (no setup record in HBM): VertexShader, the per-edge steps,
+//                           then the reference's own edge walk (ComputePolygonRows
+//                           :481-495, sample by sample) into a packed row table in
+//                           shared memory.  The (triangle,row) pairs of a warp are then
+//                           dealt out evenly over its lanes: row record (span ends and
+//                           steps, :502-503), slim copy for the resolve pass, one atomic
+//                           max per fragment that can still win.  Triangles too large
+//                           for the shared-memory table go to a list for
+//   rast_setup_big_kernel + rast_scatter_kernel   per big triangle / per (big triangle,row):
+//                           the closed-form row records of rast_kernels.cu.
+//   rast_resolve_kernel     per 32x8 pixel tile + 1-pixel halo: the winners are
+//                           compacted, each winning fragment is re-derived exactly
+//                           from its row record (fragment, three
+//                           calculateIllumination) into shared memory, then the 5-tap
+//                           AA / HDR mean of the post pass (:283-307; no shadow flags
+//                           => nothing is darkened) is taken from shared memory and
+//                           the frame written once.
+// HBM holds per triangle 8 bytes (where its rows start) and per stored row 20 bytes
+// (left x, left p*zinv and steps); no per-pixel colour buffers and no tile lists.
 #pragma once
 
 __device__ __forceinline__ unsigned long long rast_key(float zinv, int tri) {
@@ -28,7 +37,7 @@ __device__ __forceinline__ unsigned long long rast_key(float zinv, int tri) {
 }
 
 // red.max on a key with an L2 evict-last policy: the 64-bit keys (66 MB at 4K) are what the
-// scatter revisits at random, while the setup records it reads and the row records it writes
+// scatter revisits at random, while the triangles it reads and the row records it writes
 // stream through once -- the policy keeps the keys resident while those pass.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;
@@ -39,28 +48,287 @@ __device__ __forceinline__ void red_max_u64_keep(unsigned long long *addr, unsig
   asm volatile("red.relaxed.gpu.global.max.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(addr), "l"(v), "l"(pol) : "memory");
 }
 
+// The fragments x0 <= x < x1 of one span (:504, :573): one atomic max per fragment, fire and
+// forget.  (A plain read in front of the atomic, to skip fragments that are already beaten, was
+// measured: the dependent L2 round trip per fragment made the span loop latency bound -- 49 % of
+// the kernel's stall samples -- while the atomics themselves are far from the REDG rate.)
+__device__ __forceinline__ void rast_span_scatter(unsigned long long *row, int lx, int x0, int x1, float zl, float zs,
+                                                  int tri, uint64_t keep) {
+  for (int x = x0; x < x1; ++x) {
+    const float zinv = xadd(zl, xmul(zs, (float)(x - lx)));   // :543
+    if (zinv >= 0.0f) red_max_u64_keep(row + x, rast_key(zinv, tri), keep);   // :574 against the cleared buffer
+  }
+}
+
+constexpr int S2_THREADS = 128;   // triangles per block
+constexpr int S2_ROWS = 24;       // a "small" triangle spans at most this many rows ...
+constexpr int S2_XSPAN = 60;      // ... and this many columns (edge samples and x offsets fit 6 bits)
+
+// COUNT: only classifies and counts (rows of the small triangles [4], big triangles [10], their
+// rows [11]) so that a frame that cannot size its buffers from a verified predecessor gets exact
+// sizes from one cheap extra pass.
+template <bool COUNT>
+__global__ void __launch_bounds__(S2_THREADS) rast_scatter2_kernel(const __grid_constant__ RastParams p) {
+  constexpr int TW = sizeof(rast_triangle) / 4;
+  // stage: the block's triangles, read as one coalesced word stream; once every thread holds its
+  // triangle in registers the same memory carries the per-edge constants the row tasks need
+  __shared__ uint32_t stage[S2_THREADS * TW];
+  __shared__ unsigned rowtab[S2_ROWS * S2_THREADS];          // [row][thread]: left | right << 16, each x << 8 | edge << 6 | sample
+  __shared__ unsigned short task[S2_THREADS / 32][32 * S2_ROWS];   // per warp: lane | table row << 5 of every row task
+  __shared__ int org[3 * S2_THREADS];                        // [0][thread] x origin of the packed offsets, [1][thread] ymin, [2][thread] storage index of table row 0
+  float *epar = reinterpret_cast<float *>(stage);            // [edge * 6 + k][thread]: a.zinv, sz, a.px*a.zinv, spx, a.py*a.zinv, spy
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = blockIdx.x * S2_THREADS, t = t0 + tid;
+  const int n_tris = rast_count_tris(p);
+  if (t0 >= n_tris) return;   // pipelined launches are sized by a bound on the list length
+  const int n_here = min(S2_THREADS, n_tris - t0);
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.src + t0);
+    for (int i = tid; i < n_here * TW; i += S2_THREADS) stage[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  RastSetup s;
+  int ymin = 0, xorg = 0, row_first = 0, cnt = 0, span_rows = 0;   // cnt: stored rows (band-clamped), small triangles only
+  bool big = false;
+  if (t < n_tris) {
+    const float *tr = reinterpret_cast<const float *>(stage) + tid * TW;
+    const bool ok = rast_tri_setup(tr, p.focal, p.W, p.H, s);
+    if (ok) {
+      ymin = min(s.v[0].y, min(s.v[1].y, s.v[2].y));
+      const int ymax = max(s.v[0].y, max(s.v[1].y, s.v[2].y));
+      const int vxmin = min(s.v[0].x, min(s.v[1].x, s.v[2].x)), xmax = max(s.v[0].x, max(s.v[1].x, s.v[2].x));
+      xorg = vxmin - 1;                                     // a minor-axis sample can undershoot by one
+      row_first = max(ymin, p.fb0);
+      const int rlast = min(ymax, p.fb1 - 1);
+      int nrows = max(0, rlast - row_first + 1);
+      if (xmax <= 0 || xorg >= p.W || xmax <= xorg) nrows = 0;   // no pixel of [xorg, xmax) on screen
+      span_rows = ymax - ymin + 1;
+      big = nrows > 0 && (span_rows > S2_ROWS || xmax - vxmin > S2_XSPAN);
+      cnt = big ? 0 : nrows;
+      if (COUNT && big) atomicAdd(p.counters + 11, (unsigned long long)nrows);
+    }
+  }
+  __syncthreads();   // every thread has its triangle in registers: `stage` may be overwritten
+
+  // ---- big triangles: to the list of rast_setup_big_kernel (warp-aggregated append) ----
+  {
+    const unsigned m = __ballot_sync(0xffffffffu, big);
+    if (m) {
+      unsigned at0 = 0;
+      if (lane == 0) at0 = (unsigned)atomicAdd(p.counters + 10, (unsigned long long)__popc(m));
+      at0 = __shfl_sync(0xffffffffu, at0, 0);
+      if (!COUNT && big) {
+        const unsigned at = at0 + __popc(m & ((1u << lane) - 1));
+        if (at < p.big_cap) p.big_list[at] = t;
+        else atomicExch(p.counters + 5, 1ull);
+      }
+    }
+  }
+  // ---- row space of the warp's small triangles: one atomic per warp ----
+  unsigned incl = (unsigned)cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned base = 0;
+  if (lane == 31 && total) base = (unsigned)atomicAdd(p.counters + 4, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (COUNT) return;
+  if (total == 0) return;                     // nothing small and visible in this warp (no block barrier below)
+  if (base + total > p.row_cap) {             // the guessed row space is too small: the frame is rendered again
+    if (lane == 0) atomicExch(p.counters + 5, 1ull);
+    return;
+  }
+  const unsigned excl = incl - (unsigned)cnt;
+  if (cnt > 0) p.trimeta[t] = make_int2((int)(base + excl), row_first);
+
+  // ---- ComputePolygonRows (:455-495): every sample of the three edges, in order ----
+  if (cnt > 0) {
+    unsigned *rt = rowtab + tid;
+    for (int r = 0; r < span_rows; ++r) rt[r * S2_THREADS] = 0xffffffffu;   // left.x = +INT_MAX, right.x = -INT_MAX
+    const int n0 = max(abs(s.v[0].x - s.v[1].x), abs(s.v[0].y - s.v[1].y)) + 1;
+    const int n1 = max(abs(s.v[1].x - s.v[2].x), abs(s.v[1].y - s.v[2].y)) + 1;
+    const int n2 = max(abs(s.v[2].x - s.v[0].x), abs(s.v[2].y - s.v[0].y)) + 1;
+    const int n_all = n0 + n1 + n2;
+    float ax = (float)s.v[0].x, ay = (float)s.v[0].y, sx = s.sx[0], sy = s.sy[0];
+    int e = 0, i = 0, ne = n0;
+    for (int k = 0; k < n_all; ++k) {
+      const float fi = (float)i;
+      const int x = (int)floorf(xadd(ax, xmul(sx, fi)));   // :541
+      const int y = (int)floorf(xadd(ay, xmul(sy, fi)));   // :542
+      const int r = y - ymin;
+      if (r >= 0 && r < span_rows) {                        // r < 0: the :485 guard
+        const unsigned w = rt[r * S2_THREADS];
+        const unsigned xr = (unsigned)(x - xorg);
+        const unsigned f = (xr << 8) | ((unsigned)e << 6) | (unsigned)i;
+        unsigned L = w & 0xffffu, R = w >> 16;
+        if (L == 0xffffu || xr <= (L >> 8)) L = f;          // :487 `<=`: the later sample wins ties
+        if (R == 0xffffu || xr >= (R >> 8)) R = f;          // :491 `>=`
+        rt[r * S2_THREADS] = L | (R << 16);
+      }
+      if (++i == ne) {
+        i = 0; ++e;
+        const bool second = e == 1;
+        ax = (float)(second ? s.v[1].x : s.v[2].x); ay = (float)(second ? s.v[1].y : s.v[2].y);
+        sx = second ? s.sx[1] : s.sx[2]; sy = second ? s.sy[1] : s.sy[2];
+        ne = second ? n1 : n2;
+      }
+    }
+    // what the row tasks of OTHER lanes need of this triangle
+#pragma unroll
+    for (int ed = 0; ed < 3; ++ed) {
+      const RastVtx &a = s.v[ed];
+      epar[(ed * 6 + 0) * S2_THREADS + tid] = a.zinv;
+      epar[(ed * 6 + 1) * S2_THREADS + tid] = s.sz[ed];
+      epar[(ed * 6 + 2) * S2_THREADS + tid] = xmul(a.px, a.zinv);   // :526
+      epar[(ed * 6 + 3) * S2_THREADS + tid] = s.spx[ed];
+      epar[(ed * 6 + 4) * S2_THREADS + tid] = xmul(a.py, a.zinv);   // :527
+      epar[(ed * 6 + 5) * S2_THREADS + tid] = s.spy[ed];
+    }
+    org[tid] = xorg;
+    org[S2_THREADS + tid] = ymin;
+    org[2 * S2_THREADS + tid] = (int)(base + excl) - (row_first - ymin);
+  }
+  // Row tasks: only rows that draw something (right end excluded, :504: a row whose ends
+  // coincide -- the top and bottom rows of most small triangles -- has no fragment, and no
+  // pixel can ever ask for its record).
+  unsigned n_task = 0;
+  if (cnt > 0) {
+    const unsigned *rt = rowtab + tid;
+    const int r_off = row_first - ymin;
+    for (int r = 0; r < cnt; ++r) {
+      const unsigned w = rt[(r_off + r) * S2_THREADS];
+      n_task += (w != 0xffffffffu && (w >> 24) > ((w >> 8) & 0xffu)) ? 1u : 0u;
+    }
+  }
+  unsigned tincl = n_task;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned n = __shfl_up_sync(0xffffffffu, tincl, o);
+    if (lane >= o) tincl += n;
+  }
+  const unsigned n_tasks = __shfl_sync(0xffffffffu, tincl, 31);
+  if (cnt > 0) {
+    const unsigned *rt = rowtab + tid;
+    const int r_off = row_first - ymin;
+    unsigned at = tincl - n_task;
+    for (int r = 0; r < cnt; ++r) {
+      const unsigned w = rt[(r_off + r) * S2_THREADS];
+      if (w != 0xffffffffu && (w >> 24) > ((w >> 8) & 0xffu)) task[warp][at++] = (unsigned short)(lane | ((r_off + r) << 5));
+    }
+  }
+  __syncwarp();
+
+  // ---- row tasks, dealt out evenly: DrawPolygonRows (:500-508) ----
+  const uint64_t keep = l2_policy_evict_last();
+  unsigned long long n_frag = 0;
+  for (unsigned k = lane; k < n_tasks; k += 32) {
+    const unsigned tk = task[warp][k];
+    const int src = warp * 32 + (int)(tk & 31u), r = (int)(tk >> 5);
+    const unsigned w = rowtab[r * S2_THREADS + src];
+    const unsigned L = w & 0xffffu, R = w >> 16;
+    {
+      const int xo = org[src], y = org[S2_THREADS + src] + r;
+      const int lx = xo + (int)(L >> 8);
+      const int rx = xo + (int)(R >> 8);
+      float zinv[2], px[2], py[2];
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const unsigned E = side ? R : L;
+        const int ed = (int)((E >> 6) & 3u);
+        const float fi = (float)(E & 63u);
+        const float *ep = epar + (ed * 6) * S2_THREADS + src;
+        zinv[side] = xadd(ep[0], xmul(ep[S2_THREADS], fi));                                  // :543
+        px[side] = xdiv(xadd(ep[2 * S2_THREADS], xmul(ep[3 * S2_THREADS], fi)), zinv[side]);   // :547
+        py[side] = xdiv(xadd(ep[4 * S2_THREADS], xmul(ep[5 * S2_THREADS], fi)), zinv[side]);   // :548
+      }
+      const float den = (float)max(rx - lx, 1);                      // Interpolate(left, right, rx - lx + 1) :502-503
+      const float zs = xdiv_pos(xsub(zinv[1], zinv[0]), den);        // :535
+      const float lpx = xmul(px[0], zinv[0]), lpy = xmul(py[0], zinv[0]);   // :526-527
+      const float rpx = xmul(px[1], zinv[1]), rpy = xmul(py[1], zinv[1]);
+      const float4 B = make_float4(lpx, xdiv_pos(xsub(rpx, lpx), den), lpy, xdiv_pos(xsub(rpy, lpy), den));
+      const int x0 = max(lx, 0), x1 = min(rx, p.W);                  // right end excluded (:504); bounds (:573)
+      rast_span_scatter(p.keys + (size_t)y * p.W, lx, x0, x1, zinv[0], zs, t0 + src, keep);
+      n_frag += x1 > x0 ? (unsigned long long)(x1 - x0) : 0ull;
+      const int at = org[2 * S2_THREADS + src] + r;
+      __stcs(p.rowsB + at, B);   // for the resolve pass; streaming stores: the keys should stay in L2
+      __stcs(p.rowsL + at, lx);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_frag += __shfl_xor_sync(0xffffffffu, n_frag, o);
+  if (lane == 0 && n_frag) atomicAdd(p.counters + 16, n_frag);
+}
+
+// ---- big triangles -----------------------------------------------------------------------
+// Setup record, row space and row chunks (the work items of rast_scatter_kernel) of every
+// triangle rast_scatter2_kernel put on the big list.
+__global__ void __launch_bounds__(128) rast_setup_big_kernel(const __grid_constant__ RastParams p) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const unsigned n_big = (unsigned)min((unsigned long long)p.big_cap, p.counters[10]);
+  int nrows = 0, t = 0;
+  RastSetup s;
+  s.flags = 0; s.ymin = 0; s.row0 = 0; s.nrows = 0; s.row_off = 0; s.chunk_off = 0; s.tri = 0;
+  if (k < n_big) {
+    t = p.big_list[k];
+    rast_tri_setup(reinterpret_cast<const float *>(p.src + t), p.focal, p.W, p.H, s);   // ok: rast_scatter2_kernel checked
+    s.tri = t;
+    const int ymin = min(s.v[0].y, min(s.v[1].y, s.v[2].y)), ymax = max(s.v[0].y, max(s.v[1].y, s.v[2].y));
+    s.ymin = ymin;
+    s.row0 = max(ymin, p.fb0);
+    nrows = max(0, min(ymax, p.fb1 - 1) - s.row0 + 1);
+    s.nrows = nrows;
+  }
+  unsigned incl = (unsigned)nrows;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned base = 0, cbase = 0;
+  if (lane == 31 && total) {
+    base = (unsigned)atomicAdd(p.counters + 4, (unsigned long long)total);
+    cbase = (unsigned)atomicAdd(p.counters + 6, (unsigned long long)total);   // one row per chunk
+  }
+  base = __shfl_sync(0xffffffffu, base, 31);
+  cbase = __shfl_sync(0xffffffffu, cbase, 31);
+  s.row_off = base + incl - (unsigned)nrows;
+  s.chunk_off = cbase + incl - (unsigned)nrows;
+  if (k < n_big && (s.row_off + (unsigned)nrows > p.row_cap || s.chunk_off + (unsigned)nrows > p.chunk_cap)) {
+    s.nrows = 0; nrows = 0;
+    atomicExch(p.counters + 5, 1ull);
+  }
+  warp_spread(nrows, (int)s.chunk_off, 0, 0, (int)k, [&](int j, int x0, int, int, int owner) { p.chunk_owner[(unsigned)x0 + j] = owner; });
+  if (k < n_big) {
+    p.setup[k] = s;
+    if (nrows > 0) p.trimeta[t] = make_int2((int)s.row_off, s.row0);
+  }
+}
+
+// One thread per (big triangle,row): closed-form row record, slim copy for the resolve pass,
+// the span's fragments.
 __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
-  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned chunk = gid >> RAST_CHUNK_LOG2, sub = gid & (RAST_CHUNK - 1);
+  const unsigned chunk = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_frag = 0;
   if (chunk < rast_count_chunks(p)) {
-    const int t = (int)min((unsigned)p.chunk_owner[chunk], (unsigned)(p.n_tris - 1));   // stale owner after an overflow
-    const RastSetup &s = p.setup[t];
-    const int r = (int)((chunk - s.chunk_off) << RAST_CHUNK_LOG2) + (int)sub;
+    const unsigned k = min((unsigned)p.chunk_owner[chunk], p.big_cap ? p.big_cap - 1 : 0u);   // stale owner after an overflow
+    const RastSetup &s = p.setup[k];
+    const int r = (int)(chunk - s.chunk_off);
     if (r >= 0 && r < s.nrows) {
       const int y = s.row0 + r;
       float4 A, B;
       rast_row_record<true>(s, y, A, B);
-      __stcs(p.rowsA + s.row_off + r, A);   // kept for the resolve pass (the winner's fragment is re-derived
-      __stcs(p.rowsB + s.row_off + r, B);   // from its row record); streaming stores: the keys should stay in L2
       const int lx = __float_as_int(A.x), rx = __float_as_int(A.y);
+      __stcs(p.rowsB + s.row_off + r, B);
+      __stcs(p.rowsL + s.row_off + r, lx);
       const int x0 = max(lx, 0), x1 = min(rx, p.W);      // right end excluded (:504); bounds (:573)
-      unsigned long long *row = p.keys + (size_t)y * p.W;
-      const uint64_t keep = l2_policy_evict_last();
-      for (int x = x0; x < x1; ++x) {
-        const float zinv = xadd(A.z, xmul(A.w, (float)(x - lx)));   // :543
-        if (zinv >= 0.0f) red_max_u64_keep(row + x, rast_key(zinv, t), keep);   // :574 against the cleared buffer
-      }
+      rast_span_scatter(p.keys + (size_t)y * p.W, lx, x0, x1, A.z, A.w, s.tri, l2_policy_evict_last());
       n_frag = x1 > x0 ? (unsigned long long)(x1 - x0) : 0ull;
     }
   }
@@ -92,7 +360,8 @@ __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_
       if (gx >= 0 && gx < p.W && gy >= p.fb0 && gy < p.fb1) key = p.keys[(size_t)gy * p.W + gx];
       owner[pos] = (int)(unsigned)(key & 0xffffffffull) - 1;
 #pragma unroll
-      for (int k = 0; k < 10; ++k) col[pos][k] = 0.f;
+      for (int k = 0; k < 9; ++k) col[pos][k] = 0.f;
+      col[pos][9] = __uint_as_float((unsigned)(key >> 32));           // :665: the winner's zinv (0: empty)
     }
     const bool covered = key != 0;
     const unsigned m = __ballot_sync(0xffffffffu, covered);
@@ -111,13 +380,13 @@ __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_
   // ---- deferred PixelShader of every winner (:575-586) ----
   for (int k = tid; k < n_work; k += RS_W * RS_H) {
     const int pos = work[k];
-    const int gx = x0 + pos % RS_HW;
+    const int gx = x0 + pos % RS_HW, gy = y0 + pos / RS_HW;
     const int t = owner[pos];
-    const RastSetup &s = p.setup[t];
-    const unsigned rr = s.row_off + (unsigned)(y0 + pos / RS_HW - s.row0);
-    const float4 A = p.rowsA[rr], B = p.rowsB[rr];
-    const float fi = (float)(gx - __float_as_int(A.x));
-    const float zinv = xadd(A.z, xmul(A.w, fi));
+    const int2 m = p.trimeta[t];
+    const unsigned rr = (unsigned)m.x + (unsigned)(gy - m.y);
+    const float4 B = p.rowsB[rr];
+    const float fi = (float)(gx - p.rowsL[rr]);
+    const float zinv = col[pos][9];                                 // as the scatter computed it (:543)
     const float pz = xdiv(1.0f, zinv);                              // :546
     const float px = xdiv(xadd(B.x, xmul(B.y, fi)), zinv);          // :547
     const float py = xdiv(xadd(B.z, xmul(B.w, fi)), zinv);          // :548
@@ -127,11 +396,10 @@ __global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float cc = tr->color[c];
-      col[pos][c] = xmul(cc, xadd(D[c], rast_indirect(p, c, t, (size_t)(y0 + pos / RS_HW) * p.W + gx)));   // :580
+      col[pos][c] = xmul(cc, xadd(D[c], rast_indirect(p, c, t, (size_t)gy * p.W + gx)));   // :580
       col[pos][3 + c] = xmul(cc, xadd(D[c], 0.0f));                 // :581-582
       col[pos][6 + c] = xmul(cc, xadd(D[c], 0.4f));                 // :583-584
     }
-    col[pos][9] = zinv;                                             // :665
   }
   __syncthreads();
 

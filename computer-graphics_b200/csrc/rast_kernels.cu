@@ -51,7 +51,8 @@ struct RastSetup {   // 160 bytes
   // Interpolate's per-edge steps for edge e = v[e] -> v[(e+1)%3] with
   // N = max(|dx|,|dy|)+1 samples (:533-538): they depend on the edge only
   float sx[3], sy[3], sz[3], spx[3], spy[3];
-  float pad[4];
+  int tri;           // scatter path: list index of this (big) triangle; setup records are indexed by big-list position
+  float pad[3];
 };
 
 struct RastParams {
@@ -70,12 +71,16 @@ struct RastParams {
   const rast_triangle *src;
   int n_tris;
   RastSetup *setup;
-  float4 *rowsA;     // lx, rx (bit-cast ints), left zinv, zinv step
+  float4 *rowsA;     // lx, rx (bit-cast ints), left zinv, zinv step (ordered path only)
   float4 *rowsB;     // left px*zinv, its step, left py*zinv, its step
   unsigned row_cap;
   int fast;          // shadow-free list: scatter/resolve path (rast_fast.cuh)
   unsigned long long *keys;   // fast path: per-pixel (zinv bits, triangle + 1)
-  int *chunk_owner;  // triangle owning each RAST_CHUNK-row chunk
+  int *rowsL;        // fast path: left x of every stored row
+  int2 *trimeta;     // fast path: per triangle, index of its first stored row and that row's y
+  int *big_list;     // fast path: triangles too large for rast_scatter2_kernel's shared-memory row table
+  unsigned big_cap;
+  int *chunk_owner;  // triangle (fast path: big-list position) owning each RAST_CHUNK-row chunk
   unsigned chunk_cap, n_chunks;
   // pipelined mode: the list length / chunk count are not known on the host yet; n_tris and
   // n_chunks above are then launch bounds and the kernels clamp to these device values
@@ -94,7 +99,7 @@ struct RastParams {
   float *out_depth;
   int *out_index;
   uint32_t *out_argb;
-  unsigned long long *counters;  // [3] bin entries, [4] rows, [5] overflow flag, [6] row chunks, second cache line: [16] fragments (updated while [6] is read), [24] list length (read while [4]/[6] are updated)
+  unsigned long long *counters;  // [3] bin entries, [4] rows, [5] overflow flag, [6] row chunks, [9] first shaded fragment, [10] big triangles, [11] their rows (counting pass), second cache line: [16] fragments (updated while [6] is read), [24] list length (read while [4]/[6] are updated)
 };
 
 __device__ __forceinline__ int rast_count_tris(const RastParams &p) {
@@ -154,11 +159,11 @@ __device__ __forceinline__ bool rast_tri_setup(const float *tr, float focal, int
     const float den = (float)max(max(abs(a.x - b.x), abs(a.y - b.y)), 1);
     const float apx = xmul(a.px, a.zinv), apy = xmul(a.py, a.zinv);
     const float bpx = xmul(b.px, b.zinv), bpy = xmul(b.py, b.zinv);
-    s.sx[e] = xdiv((float)(b.x - a.x), den);
-    s.sy[e] = xdiv((float)(b.y - a.y), den);
-    s.sz[e] = xdiv(xsub(b.zinv, a.zinv), den);
-    s.spx[e] = xdiv(xsub(bpx, apx), den);
-    s.spy[e] = xdiv(xsub(bpy, apy), den);
+    s.sx[e] = xdiv_pos((float)(b.x - a.x), den);
+    s.sy[e] = xdiv_pos((float)(b.y - a.y), den);
+    s.sz[e] = xdiv_pos(xsub(b.zinv, a.zinv), den);
+    s.spx[e] = xdiv_pos(xsub(bpx, apx), den);
+    s.spy[e] = xdiv_pos(xsub(bpy, apy), den);
   }
   return ok;
 }
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) rast_setup_kernel(const __grid_
   __syncthreads();
   int nrows = 0;
   RastSetup s;
-  s.flags = 0; s.ymin = 0; s.row0 = 0; s.nrows = 0; s.row_off = 0; s.chunk_off = 0;
+  s.flags = 0; s.ymin = 0; s.row0 = 0; s.nrows = 0; s.row_off = 0; s.chunk_off = 0; s.tri = t;
   int xmin = 0, xmax = -1;
   if (t < n_tris) {
     const float *tr = reinterpret_cast<const float *>(stage) + threadIdx.x * TRI_WORDS;   // v0[4] v1[4] v2[4] normal[4] color[3]
@@ -360,11 +365,11 @@ __device__ __forceinline__ void rast_row_record(const RastSetup &s, int Y, float
   }
   const int n = R.x - L.x + 1;
   const float den = (float)max(n - 1, 1);
-  A = make_float4(__int_as_float(L.x), __int_as_float(R.x), zinv[0], xdiv(xsub(zinv[1], zinv[0]), den));
+  A = make_float4(__int_as_float(L.x), __int_as_float(R.x), zinv[0], xdiv_pos(xsub(zinv[1], zinv[0]), den));
   if (WITH_POS) {
     const float lpx = xmul(px[0], zinv[0]), lpy = xmul(py[0], zinv[0]);
     const float rpx = xmul(px[1], zinv[1]), rpy = xmul(py[1], zinv[1]);
-    B = make_float4(lpx, xdiv(xsub(rpx, lpx), den), lpy, xdiv(xsub(rpy, lpy), den));
+    B = make_float4(lpx, xdiv_pos(xsub(rpx, lpx), den), lpy, xdiv_pos(xsub(rpy, lpy), den));
   }
 }
 
@@ -825,8 +830,6 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   p.fast = fast ? 1 : 0;
   p.out_rgb = d_rgb; p.out_depth = d_depth; p.out_index = d_index; p.out_argb = d_argb;
   p.counters = (unsigned long long *)ctx->counters.p;
-  if (int rc = ensure(ctx, ctx->rast_setup, sizeof(RastSetup) * (size_t)(n ? n : 1))) return rc;
-  p.setup = (RastSetup *)ctx->rast_setup.p;
   // worst case rows: every triangle spans the whole band
   size_t row_cap = (size_t)n * (size_t)(p.fb1 - p.fb0);
   const size_t row_budget = (size_t)64 << 20;   // 64 Mi rows = 2 GiB of row records
@@ -844,9 +847,6 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     ctx->rast_inflight.cap_bins = bin_cap;
     ctx->rast_inflight.fast = fast ? 1 : 0;
   }
-  if (int rc = ensure(ctx, ctx->rast_chunks, sizeof(int) * chunk_cap)) return rc;
-  p.chunk_owner = (int *)ctx->rast_chunks.p;
-  p.chunk_cap = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
   unsigned long long *hc = (unsigned long long *)ctx->pinned;
 
   // the entry value of indirectLightPowerPerArea reaches the first shaded fragment only (:585)
@@ -864,40 +864,72 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (fast) {
     // ---- scatter / resolve (rast_fast.cuh) ----
     ctx->rast_w = 0; ctx->rast_h = 0;   // no intermediate buffers in this path
-    p.row_cap = spec ? (unsigned)(row_cap > 0xffffffffull ? 0xffffffffull : row_cap) : 0xffffffffu;
     if (int rc = ensure(ctx, ctx->rast_keys, npix * sizeof(unsigned long long))) return rc;
     p.keys = (unsigned long long *)ctx->rast_keys.p;
-    size_t n_rows = row_cap;
-    if (n > 0) {
-      rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
-      ctx->stats.kernel_launches++;
-      tl_mark(ctx, "rast_setup_kernel");
-      if (!p.spread_in_setup) rast_spread_launch(ctx, p, 0);
-      CU_CHECK(ctx, cudaGetLastError());
-    }
-    if (!spec) {
+    if (int rc = ensure(ctx, ctx->rast_trimeta, sizeof(int2) * (size_t)(n ? n : 1))) return rc;
+    p.trimeta = (int2 *)ctx->rast_trimeta.p;
+    const int s2_blocks = (n + S2_THREADS - 1) / S2_THREADS;
+    size_t n_rows = 1, big_cap = 0;
+    if (spec) {
+      // sizes guessed from the last verified frame; the kernels flag any overflow.  A frame whose
+      // predecessor had no big triangle does not launch the big-triangle kernels at all.
+      n_rows = row_cap;
+      big_cap = ctx->rast_spec.big ? (size_t)rast_spec_cap(ctx->rast_spec.big) : 0;
+    } else {
+      chunk_cap = 1;
       p.n_chunks = 0;
-      n_rows = 1;
       if (n > 0) {
-        CU_CHECK(ctx, cudaMemcpyAsync(hc, ctx->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the chunk count sizes the next grid
-        if (hc[5]) return ctx_fail(ctx, B200_ENOMEM, "row chunk budget exceeded");
-        p.n_chunks = (unsigned)hc[6];
-        if (hc[4]) n_rows = (size_t)hc[4];     // exact: the setup kernel counted them
+        // exact sizes from a counting pass: [4] rows of the small triangles, [10] big triangles, [11] their rows
+        rast_scatter2_kernel<true><<<s2_blocks, S2_THREADS, 0, ctx->stream>>>(p);
+        ctx->stats.kernel_launches++;
+        tl_mark(ctx, "rast_scatter2_kernel<count>");
+        CU_CHECK(ctx, cudaGetLastError());
+        CU_CHECK(ctx, cudaMemcpyAsync(hc, ctx->counters.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_CHECK(ctx, cudaMemsetAsync(p.counters + 4, 0, sizeof(unsigned long long), ctx->stream));
+        CU_CHECK(ctx, cudaMemsetAsync(p.counters + 10, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (hc[4] + hc[11] > 0xfffffff0ull) return ctx_fail(ctx, B200_ENOMEM, "row table budget exceeded");
+        n_rows = (size_t)(hc[4] + hc[11]);
+        big_cap = (size_t)hc[10];
+        chunk_cap = (size_t)hc[11];
+        p.n_chunks = (unsigned)hc[11];
+        if (n_rows < 1) n_rows = 1;
+        if (chunk_cap < 1) chunk_cap = 1;
       }
     }
-    if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(float4) * n_rows)) return rc;
+    if (big_cap > 0x7fffffffull) big_cap = 0x7fffffffull;
+    if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(int) * n_rows)) return rc;
     if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * n_rows)) return rc;
-    p.rowsA = (float4 *)ctx->rast_rowsA.p;
+    if (int rc = ensure(ctx, ctx->rast_setup, sizeof(RastSetup) * (big_cap ? big_cap : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_big, sizeof(int) * (big_cap ? big_cap : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_chunks, sizeof(int) * chunk_cap)) return rc;
+    p.rowsL = (int *)ctx->rast_rowsA.p;
     p.rowsB = (float4 *)ctx->rast_rowsB.p;
+    p.row_cap = (unsigned)(n_rows > 0xffffffffull ? 0xffffffffull : n_rows);
+    p.setup = (RastSetup *)ctx->rast_setup.p;
+    p.big_list = (int *)ctx->rast_big.p;
+    p.big_cap = (unsigned)big_cap;
+    p.chunk_owner = (int *)ctx->rast_chunks.p;
+    p.chunk_cap = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
     // cleared right before the scatter so that the 64-bit keys (66 MB at 4K, less than the L2)
     // are still cache-resident when the atomics arrive
     CU_CHECK(ctx, cudaMemsetAsync(p.keys + (size_t)p.fb0 * W, 0, (size_t)(p.fb1 - p.fb0) * W * sizeof(unsigned long long), ctx->stream));
     tl_mark(ctx, "memset keys");
-    if (p.n_chunks > 0 && n > 0) {
-      rast_scatter_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
+    if (n > 0) {
+      rast_scatter2_kernel<false><<<s2_blocks, S2_THREADS, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
-      tl_mark(ctx, "rast_scatter_kernel");
+      tl_mark(ctx, "rast_scatter2_kernel");
+      if (big_cap > 0) {
+        rast_setup_big_kernel<<<(int)((big_cap + 127) / 128), 128, 0, ctx->stream>>>(p);
+        ctx->stats.kernel_launches++;
+        tl_mark(ctx, "rast_setup_big_kernel");
+        if (p.n_chunks > 0) {
+          rast_scatter_kernel<<<(int)(((size_t)p.n_chunks + 255) / 256), 256, 0, ctx->stream>>>(p);
+          ctx->stats.kernel_launches++;
+          tl_mark(ctx, "rast_scatter_kernel");
+        }
+      }
+      CU_CHECK(ctx, cudaGetLastError());
     }
     // host-pointer entries: resolve in slices, each slice's packed rows leave for the host
     // while the next one is resolved (band_slice_done is a no-op otherwise)
@@ -917,6 +949,11 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   }
 
   // ---- ordered tile path ----
+  if (int rc = ensure(ctx, ctx->rast_setup, sizeof(RastSetup) * (size_t)(n ? n : 1))) return rc;
+  p.setup = (RastSetup *)ctx->rast_setup.p;
+  if (int rc = ensure(ctx, ctx->rast_chunks, sizeof(int) * chunk_cap)) return rc;
+  p.chunk_owner = (int *)ctx->rast_chunks.p;
+  p.chunk_cap = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
   if (row_cap > row_budget) row_cap = row_budget;
   if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(float4) * row_cap)) return rc;
   if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * row_cap)) return rc;

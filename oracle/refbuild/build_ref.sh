@@ -4,6 +4,10 @@
 #   oracle/_ref/libref_rt.so                 raytracer  (resolution is run-time)
 #   oracle/_ref/libref_rast_<W>x<H>.so       rasteriser (one per resolution: its
 #                                            frame buffers are static arrays)
+#   oracle/_ref/libprog_{rt,rast}_ref*.so    the reference PROGRAMS (main + Update + Draw) headless
+#   oracle/_ref/libprog_{rt,rast}_dropin*.so the same programs with this repository's Draw shim in
+#                                            place of the reference's Draw, linked to libb200render.so
+#                                            (prog_harness.cpp; the executed drop-in test)
 #
 # The reference sources are compiled where they lie under $REF (default
 # /root/reference); nothing is copied into the repository.  The only edits are
@@ -51,3 +55,40 @@ for sz in $RAST_SIZES; do
 done
 wait
 for sz in $RAST_SIZES; do echo "built $OUT/libref_rast_${sz}.so"; done
+
+# ---- the programs, with the reference's Draw and with the drop-in Draw -----------
+# Only the DEFINITION line of Draw is renamed for the drop-in flavour (RT skeleton.cpp:104, RAST
+# :203); its declaration and the call in main() stay, and now resolve to the shim's Draw.
+PKG="$HERE/../../computer-graphics_b200"
+PROG_SIZES="${PROG_SIZES:-900x720 64x48}"
+RENAME='s/^void Draw(screen\* screen)\([^;]*\)$/void reference_Draw(screen* screen)\1/'
+PFLAGS="-O3 -pipe -w -fPIC -shared -std=c++11 -DB200_SDL_SCRIPTED"
+LINK="-L$PKG -lb200render -Wl,-rpath,\$ORIGIN/../../computer-graphics_b200"
+mkdir -p "$TMP/rt_ref" "$TMP/rt_dropin" "$TMP/rast_ref" "$TMP/rast_dropin"
+cp "$TMP/skeleton_rt_patched.cpp" "$TMP/rt_ref/skeleton_prog.cpp"
+sed -e "$RENAME" "$TMP/skeleton_rt_patched.cpp" > "$TMP/rt_dropin/skeleton_prog.cpp"
+cp "$TMP/skeleton_rast_patched.cpp" "$TMP/rast_ref/skeleton_prog.cpp"
+sed -e "$RENAME" "$TMP/skeleton_rast_patched.cpp" > "$TMP/rast_dropin/skeleton_prog.cpp"
+grep -q "^void reference_Draw" "$TMP/rt_dropin/skeleton_prog.cpp" && grep -q "^void reference_Draw" "$TMP/rast_dropin/skeleton_prog.cpp" \
+  || { echo "build_ref: could not rename the reference's Draw definition" >&2; exit 1; }
+RT_INC="-I$HERE/stubs -I$REF/raytracer/Source -I$REF/glm"
+RAST_INC="-I$HERE/stubs -I$REF/rasteriser/Source -I$REF/glm"
+$CXX $PFLAGS -DPROG_RT -I"$TMP/rt_ref" $RT_INC "$HERE/prog_harness.cpp" -o "$OUT/libprog_rt_ref.so" &
+for sz in $PROG_SIZES; do
+  W="${sz%x*}"; H="${sz#*x}"
+  $CXX $PFLAGS -mcmodel=medium -DPROG_RAST -DREF_W="$W" -DREF_H="$H" -I"$TMP/rast_ref" $RAST_INC \
+      "$HERE/prog_harness.cpp" -o "$OUT/libprog_rast_ref_${W}x${H}.so" &
+done
+if [ -f "$PKG/libb200render.so" ]; then
+  SHIM="-I$PKG/host/shim -I$HERE/../../include"
+  $CXX $PFLAGS -DPROG_RT -DDROPIN -I"$TMP/rt_dropin" $RT_INC $SHIM "$HERE/prog_harness.cpp" $LINK -o "$OUT/libprog_rt_dropin.so" &
+  for sz in $PROG_SIZES; do
+    W="${sz%x*}"; H="${sz#*x}"
+    $CXX $PFLAGS -mcmodel=medium -DPROG_RAST -DDROPIN -DREF_W="$W" -DREF_H="$H" -I"$TMP/rast_dropin" $RAST_INC $SHIM \
+        "$HERE/prog_harness.cpp" $LINK -o "$OUT/libprog_rast_dropin_${W}x${H}.so" &
+  done
+else
+  echo "build_ref: $PKG/libb200render.so not built yet; drop-in programs skipped" >&2
+fi
+wait
+ls "$OUT"/libprog_* | sed 's/^/built /'

@@ -76,8 +76,35 @@ static inline SDL_Surface *SDL_CreateRGBSurfaceFrom(void *px, int w, int h, int,
                                                     uint32_t, uint32_t, uint32_t, uint32_t) {
   static SDL_Surface s; s.pixels = px; s.w = w; s.h = h; s.pitch = pitch; return &s;
 }
-static inline int SDL_SaveBMP(SDL_Surface *, const char *) { return 0; }
 static inline uint32_t SDL_GetTicks(void) { return 0; }
+#ifdef B200_SDL_SCRIPTED
+/* Scripted mode (oracle/refbuild/prog_harness.cpp): the reference's own main() / Update() loop
+ * runs headless.  The script is a list of frames, each a list of key codes: SDL_PollEvent hands
+ * out the current frame's keys as SDL_KEYDOWN events, then returns 0 (Update() returns true and
+ * main() draws the frame); once every frame has been drawn it delivers SDL_QUIT.  SDL_SaveBMP
+ * (the screenshot main() takes after its loop, SDLauxiliary.h:24-53) copies the surface out. */
+static const int *sdl_script_keys = 0;      /* all key codes, frame after frame */
+static const int *sdl_script_lens = 0;      /* keys per frame */
+static int sdl_script_frames = 0, sdl_script_frame = 0, sdl_script_key = 0, sdl_script_at = 0;
+static uint32_t *sdl_script_shot = 0;       /* receives the screenshot */
+static inline int SDL_PollEvent(SDL_Event *e) {
+  if (sdl_script_frame >= sdl_script_frames) { e->type = SDL_QUIT; return 1; }
+  if (sdl_script_key < sdl_script_lens[sdl_script_frame]) {
+    e->type = SDL_KEYDOWN;
+    e->key.keysym.sym = sdl_script_keys[sdl_script_at++];
+    ++sdl_script_key;
+    return 1;
+  }
+  ++sdl_script_frame; sdl_script_key = 0;
+  return 0;
+}
+static inline int SDL_SaveBMP(SDL_Surface *s, const char *) {
+  if (sdl_script_shot) memcpy(sdl_script_shot, s->pixels, (size_t)s->pitch * (size_t)s->h);
+  return 0;
+}
+#else
+static inline int SDL_SaveBMP(SDL_Surface *, const char *) { return 0; }
 static inline int SDL_PollEvent(SDL_Event *) { return 0; }
+#endif
 
 #endif
