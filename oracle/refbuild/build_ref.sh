@@ -63,6 +63,9 @@ PKG="$HERE/../../computer-graphics_b200"
 PROG_SIZES="${PROG_SIZES:-900x720 64x48}"
 RENAME='s/^void Draw(screen\* screen)\([^;]*\)$/void reference_Draw(screen* screen)\1/'
 PFLAGS="-O3 -pipe -w -fPIC -shared -std=c++11 -DB200_SDL_SCRIPTED"
+# The programs print through iostream: they must share the process's libstdc++ (a compiler wrapper
+# that links it statically gives the library a second, half-preempted copy inside Python).
+PCXX="${PROG_CXX:-$( [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo "$CXX" )}"
 LINK="-L$PKG -lb200render -Wl,-rpath,\$ORIGIN/../../computer-graphics_b200"
 mkdir -p "$TMP/rt_ref" "$TMP/rt_dropin" "$TMP/rast_ref" "$TMP/rast_dropin"
 cp "$TMP/skeleton_rt_patched.cpp" "$TMP/rt_ref/skeleton_prog.cpp"
@@ -73,18 +76,18 @@ grep -q "^void reference_Draw" "$TMP/rt_dropin/skeleton_prog.cpp" && grep -q "^v
   || { echo "build_ref: could not rename the reference's Draw definition" >&2; exit 1; }
 RT_INC="-I$HERE/stubs -I$REF/raytracer/Source -I$REF/glm"
 RAST_INC="-I$HERE/stubs -I$REF/rasteriser/Source -I$REF/glm"
-$CXX $PFLAGS -DPROG_RT -I"$TMP/rt_ref" $RT_INC "$HERE/prog_harness.cpp" -o "$OUT/libprog_rt_ref.so" &
+$PCXX $PFLAGS -DPROG_RT -I"$TMP/rt_ref" $RT_INC "$HERE/prog_harness.cpp" -o "$OUT/libprog_rt_ref.so" &
 for sz in $PROG_SIZES; do
   W="${sz%x*}"; H="${sz#*x}"
-  $CXX $PFLAGS -mcmodel=medium -DPROG_RAST -DREF_W="$W" -DREF_H="$H" -I"$TMP/rast_ref" $RAST_INC \
+  $PCXX $PFLAGS -mcmodel=medium -DPROG_RAST -DREF_W="$W" -DREF_H="$H" -I"$TMP/rast_ref" $RAST_INC \
       "$HERE/prog_harness.cpp" -o "$OUT/libprog_rast_ref_${W}x${H}.so" &
 done
 if [ -f "$PKG/libb200render.so" ]; then
   SHIM="-I$PKG/host/shim -I$HERE/../../include"
-  $CXX $PFLAGS -DPROG_RT -DDROPIN -I"$TMP/rt_dropin" $RT_INC $SHIM "$HERE/prog_harness.cpp" $LINK -o "$OUT/libprog_rt_dropin.so" &
+  $PCXX $PFLAGS -DPROG_RT -DDROPIN -I"$TMP/rt_dropin" $RT_INC $SHIM "$HERE/prog_harness.cpp" $LINK -o "$OUT/libprog_rt_dropin.so" &
   for sz in $PROG_SIZES; do
     W="${sz%x*}"; H="${sz#*x}"
-    $CXX $PFLAGS -mcmodel=medium -DPROG_RAST -DDROPIN -DREF_W="$W" -DREF_H="$H" -I"$TMP/rast_dropin" $RAST_INC $SHIM \
+    $PCXX $PFLAGS -mcmodel=medium -DPROG_RAST -DDROPIN -DREF_W="$W" -DREF_H="$H" -I"$TMP/rast_dropin" $RAST_INC $SHIM \
         "$HERE/prog_harness.cpp" $LINK -o "$OUT/libprog_rast_dropin_${W}x${H}.so" &
   done
 else

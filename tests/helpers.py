@@ -421,3 +421,34 @@ def scene_soup_rast(n, seed=0x5EED, edge=0.01):
     t["color"] = uni(0.15, 0.75, u[:, 9:12])
     compute_normals(t)
     return t
+
+
+# ---- the reference PROGRAMS (oracle/refbuild/prog_harness.cpp) ---------------------------
+SDLK = {"UP": 0x40000052, "DOWN": 0x40000051, "LEFT": 0x40000050, "RIGHT": 0x4000004F,
+        **{c: ord(c) for c in "wsadqenmiozxfg12"}}
+
+
+def prog_run(name, frames):
+    """Runs the reference program `name` (libprog_*.so under oracle/_ref): its own main() with a
+    script of key presses, `frames` = one list of key names per frame drawn.  The library is
+    loaded from a private copy so that every run starts from the program's initial globals.
+    Returns the screenshot main() saves after its loop, (H, W) uint32."""
+    import shutil
+    import tempfile
+    src = os.path.join(REF_DIR, name)
+    with tempfile.TemporaryDirectory() as tmp:
+        # keep the $ORIGIN-relative rpath of the drop-in flavour working: same depth below ROOT
+        d = os.path.join(ROOT, "oracle", "_ref")
+        path = os.path.join(d, f".run_{os.getpid()}_{abs(hash((name, str(frames), tmp))) & 0xffffff:x}_{name}")
+        shutil.copyfile(src, path)
+        try:
+            lib = ctypes.CDLL(path)
+            keys = np.array([SDLK[k] for fr in frames for k in fr] + [0], np.int32)
+            lens = np.array([len(fr) for fr in frames], np.int32)
+            shot = np.zeros(3840 * 2160, np.uint32)
+            W, H = c_i(0), c_i(0)
+            rc = lib.prog_run(ptr(keys), ptr(lens), c_i(len(frames)), ptr(shot), ctypes.byref(W), ctypes.byref(H))
+            assert rc == 0
+            return shot[: W.value * H.value].reshape(H.value, W.value).copy()
+        finally:
+            os.unlink(path)
