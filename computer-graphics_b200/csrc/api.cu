@@ -87,7 +87,7 @@ void b200_destroy(b200_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rt_dtcam, &ctx->rt_cells, &ctx->rt_cell_rec, &ctx->rt_cell_idx, &ctx->rast_src,
                     &ctx->rast_setup, &ctx->rast_rowsA, &ctx->rast_rowsB, &ctx->rast_bins, &ctx->rast_tile_count, &ctx->rast_tile_bits,
-                    &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_trimeta, &ctx->rast_big, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
+                    &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_trimeta, &ctx->rast_big, &ctx->rast_srowsB, &ctx->rast_srowsL, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
                     &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
                     &ctx->out_argb, &ctx->counters};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -515,7 +515,18 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
   ctx->tl_n = 0;
   tl_mark(ctx, "frame start");
   rast_light_t lc = *light;
+  ctx->rast_clear_ptr = nullptr; ctx->rast_keys_cleared = 0;
   if (whole_draw) {
+    if (spec && (ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow))) {
+      // the frame is bound for the scatter path: its geometry kernel clears the key rows on the way
+      const size_t W = (size_t)cam->width;
+      const int fb0 = row_begin - 2 > 0 ? row_begin - 2 : 0, fb1 = row_end + 2 < cam->height ? row_end + 2 : cam->height;
+      if (int rc = ensure(ctx, ctx->rast_keys, W * cam->height * sizeof(unsigned long long))) return rc;
+      if (fb1 > fb0) {
+        ctx->rast_clear_ptr = (unsigned long long *)ctx->rast_keys.p + (size_t)fb0 * W;
+        ctx->rast_clear_bytes = (size_t)(fb1 - fb0) * W * sizeof(unsigned long long);
+      }
+    }
     if (int rc = rast_geometry(ctx, cam, light, &lc, spec)) return rc;
     if (spec) f.cap_tris = (unsigned long long)ctx->rast_n_tris;
   }

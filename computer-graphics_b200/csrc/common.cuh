@@ -112,6 +112,10 @@ struct b200_ctx {
   int rast_n_tris = 0;
   DevBuf rast_setup, rast_rowsA, rast_rowsB, rast_bins, rast_tile_count, rast_tmp, rast_tile_bits;
   DevBuf rast_keys;      // fast path: 64-bit (zinv, triangle) key per pixel
+  void *rast_clear_ptr = nullptr;    // key rows the single-pass geometry kernel should clear (set per frame by rast_frame)
+  size_t rast_clear_bytes = 0;
+  int rast_keys_cleared = 0;         // ... and whether it did (rast_launch then skips its memset)
+  DevBuf rast_srowsB, rast_srowsL;   // fast path: row records of the small triangles
   DevBuf rast_trimeta, rast_big;   // fast path: per-triangle row-table origin; list of the triangles too big for the small-triangle kernel
   int rast_has_shadow = 0;   // the uploaded list can contain shadow-volume triangles
   int opt_rast_path = 0;     // 0 auto, 1 ordered tiles, 2 scatter (shadow-free lists only)

@@ -27,13 +27,21 @@
 //                           AA / HDR mean of the post pass (:283-307; no shadow flags
 //                           => nothing is darkened) is taken from shared memory and
 //                           the frame written once.
-// HBM holds per triangle 8 bytes (where its rows start) and per stored row 20 bytes
-// (left x, left p*zinv and steps); no per-pixel colour buffers and no tile lists.
+// HBM holds per drawn row 20 bytes (left x, left p*zinv and steps; small triangles: at a place the key
+// itself names, big ones: through 8 bytes per triangle); no per-pixel colour buffers and no tile lists.
 #pragma once
 
-__device__ __forceinline__ unsigned long long rast_key(float zinv, int tri) {
+// Low word of a key: (triangle << 5 | code) + 1.  Triangle order decides ties, as in the reference;
+// the code tells the resolve pass where the fragment's row record is WITHOUT another look-up:
+// code < S2_ROWS: a small triangle, record at triangle * S2_ROWS + code (code = y mod S2_ROWS: a small
+// triangle spans at most S2_ROWS rows, so y mod S2_ROWS is unique within it); RAST_CODE_BIG: a big
+// triangle, rows found through trimeta.
+constexpr int S2_ROWS = 24;       // a "small" triangle spans at most this many rows
+constexpr unsigned RAST_CODE_BIG = 31u;
+constexpr int RAST_FAST_MAX_TRIS = 1 << 27;
+__device__ __forceinline__ unsigned long long rast_key(float zinv, unsigned low) {
   const unsigned hi = zinv == 0.0f ? 0u : __float_as_uint(zinv);   // -0.0 passes `>= 0` too
-  return ((unsigned long long)hi << 32) | (unsigned)(tri + 1);
+  return ((unsigned long long)hi << 32) | (low + 1u);
 }
 
 // red.max on a key with an L2 evict-last policy: the 64-bit keys (66 MB at 4K) are what the
@@ -53,18 +61,17 @@ __device__ __forceinline__ void red_max_u64_keep(unsigned long long *addr, unsig
 // measured: the dependent L2 round trip per fragment made the span loop latency bound -- 49 % of
 // the kernel's stall samples -- while the atomics themselves are far from the REDG rate.)
 __device__ __forceinline__ void rast_span_scatter(unsigned long long *row, int lx, int x0, int x1, float zl, float zs,
-                                                  int tri, uint64_t keep) {
+                                                  unsigned low, uint64_t keep) {
   for (int x = x0; x < x1; ++x) {
     const float zinv = xadd(zl, xmul(zs, (float)(x - lx)));   // :543
-    if (zinv >= 0.0f) red_max_u64_keep(row + x, rast_key(zinv, tri), keep);   // :574 against the cleared buffer
+    if (zinv >= 0.0f) red_max_u64_keep(row + x, rast_key(zinv, low), keep);   // :574 against the cleared buffer
   }
 }
 
 constexpr int S2_THREADS = 128;   // triangles per block
-constexpr int S2_ROWS = 24;       // a "small" triangle spans at most this many rows ...
-constexpr int S2_XSPAN = 60;      // ... and this many columns (edge samples and x offsets fit 6 bits)
+constexpr int S2_XSPAN = 60;      // a "small" triangle spans at most S2_ROWS rows and this many columns (edge samples and x offsets fit 6 bits)
 
-// COUNT: only classifies and counts (rows of the small triangles [4], big triangles [10], their
+// COUNT: only classifies and counts (big triangles [10], their
 // rows [11]) so that a frame that cannot size its buffers from a verified predecessor gets exact
 // sizes from one cheap extra pass.
 template <bool COUNT>
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(S2_THREADS) rast_scatter2_kernel(const __grid_
   __shared__ uint32_t stage[S2_THREADS * TW];
   __shared__ unsigned rowtab[S2_ROWS * S2_THREADS];          // [row][thread]: left | right << 16, each x << 8 | edge << 6 | sample
   __shared__ unsigned short task[S2_THREADS / 32][32 * S2_ROWS];   // per warp: lane | table row << 5 of every row task
-  __shared__ int org[3 * S2_THREADS];                        // [0][thread] x origin of the packed offsets, [1][thread] ymin, [2][thread] storage index of table row 0
+  __shared__ int org[2 * S2_THREADS];                        // [0][thread] x origin of the packed offsets, [1][thread] ymin, 
   float *epar = reinterpret_cast<float *>(stage);            // [edge * 6 + k][thread]: a.zinv, sz, a.px*a.zinv, spx, a.py*a.zinv, spy
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -126,25 +133,8 @@ __global__ void __launch_bounds__(S2_THREADS) rast_scatter2_kernel(const __grid_
       }
     }
   }
-  // ---- row space of the warp's small triangles: one atomic per warp ----
-  unsigned incl = (unsigned)cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += n;
-  }
-  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned base = 0;
-  if (lane == 31 && total) base = (unsigned)atomicAdd(p.counters + 4, (unsigned long long)total);
-  base = __shfl_sync(0xffffffffu, base, 31);
   if (COUNT) return;
-  if (total == 0) return;                     // nothing small and visible in this warp (no block barrier below)
-  if (base + total > p.row_cap) {             // the guessed row space is too small: the frame is rendered again
-    if (lane == 0) atomicExch(p.counters + 5, 1ull);
-    return;
-  }
-  const unsigned excl = incl - (unsigned)cnt;
-  if (cnt > 0) p.trimeta[t] = make_int2((int)(base + excl), row_first);
+  if (!__any_sync(0xffffffffu, cnt > 0)) return;   // nothing small and visible in this warp (no block barrier below)
 
   // ---- ComputePolygonRows (:455-495): every sample of the three edges, in order ----
   if (cnt > 0) {
@@ -191,7 +181,6 @@ __global__ void __launch_bounds__(S2_THREADS) rast_scatter2_kernel(const __grid_
     }
     org[tid] = xorg;
     org[S2_THREADS + tid] = ymin;
-    org[2 * S2_THREADS + tid] = (int)(base + excl) - (row_first - ymin);
   }
   // Row tasks: only rows that draw something (right end excluded, :504: a row whose ends
   // coincide -- the top and bottom rows of most small triangles -- has no fragment, and no
@@ -252,11 +241,12 @@ __global__ void __launch_bounds__(S2_THREADS) rast_scatter2_kernel(const __grid_
       const float rpx = xmul(px[1], zinv[1]), rpy = xmul(py[1], zinv[1]);
       const float4 B = make_float4(lpx, xdiv_pos(xsub(rpx, lpx), den), lpy, xdiv_pos(xsub(rpy, lpy), den));
       const int x0 = max(lx, 0), x1 = min(rx, p.W);                  // right end excluded (:504); bounds (:573)
-      rast_span_scatter(p.keys + (size_t)y * p.W, lx, x0, x1, zinv[0], zs, t0 + src, keep);
+      const unsigned slot = (unsigned)y % (unsigned)S2_ROWS, tri = (unsigned)(t0 + src);
+      rast_span_scatter(p.keys + (size_t)y * p.W, lx, x0, x1, zinv[0], zs, (tri << 5) | slot, keep);
       n_frag += x1 > x0 ? (unsigned long long)(x1 - x0) : 0ull;
-      const int at = org[2 * S2_THREADS + src] + r;
-      __stcs(p.rowsB + at, B);   // for the resolve pass; streaming stores: the keys should stay in L2
-      __stcs(p.rowsL + at, lx);
+      const size_t at = (size_t)tri * S2_ROWS + slot;
+      __stcs(p.srowsB + at, B);   // for the resolve pass; streaming stores: the keys should stay in L2
+      __stcs(p.srowsL + at, lx);
     }
   }
 #pragma unroll
@@ -328,7 +318,7 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
       __stcs(p.rowsB + s.row_off + r, B);
       __stcs(p.rowsL + s.row_off + r, lx);
       const int x0 = max(lx, 0), x1 = min(rx, p.W);      // right end excluded (:504); bounds (:573)
-      rast_span_scatter(p.keys + (size_t)y * p.W, lx, x0, x1, A.z, A.w, s.tri, l2_policy_evict_last());
+      rast_span_scatter(p.keys + (size_t)y * p.W, lx, x0, x1, A.z, A.w, ((unsigned)s.tri << 5) | RAST_CODE_BIG, l2_policy_evict_last());
       n_frag = x1 > x0 ? (unsigned long long)(x1 - x0) : 0ull;
     }
   }
@@ -338,99 +328,137 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
 }
 
 constexpr int RS_W = 32, RS_H = 8, RS_HW = RS_W + 2, RS_HH = RS_H + 2, RS_N = RS_HW * RS_HH;   // 34 x 10 = 340
+constexpr int RS_HALO = 2 * RS_HW + 2 * RS_H;                                                   // 84 halo positions
 
-__global__ void __launch_bounds__(RS_W * RS_H) rast_resolve_kernel(const __grid_constant__ RastParams p) {
-  __shared__ float col[RS_N][10];           // screen rgb, low rgb, high rgb, depth
+__global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __grid_constant__ RastParams p) {
+  __shared__ float col[9][RS_N];            // [screen rgb, low rgb, high rgb][position]: conflict-free taps
+  __shared__ float zinv_s[RS_N];            // the winner's zinv (:665); 0 = empty
   __shared__ int owner[RS_N];
   __shared__ unsigned short work[RS_N];
-  __shared__ int warp_base[RS_W * RS_H / 32 + 1];
   __shared__ int n_work;
+  __shared__ __align__(16) float out_stage[RS_H][3 * RS_W];   // one row of RGB per warp, for 128-bit stores
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int tx = tid % RS_W, ty = tid / RS_W;                                   // a warp is one row of the tile
   const int x0 = blockIdx.x * RS_W - 1, y0 = p.row0 + blockIdx.y * RS_H - 1;   // halo origin
 
-  // ---- gather the winners of the tile + halo, compact the covered ones ----
   if (tid == 0) n_work = 0;
   __syncthreads();
-  for (int base = 0; base < RS_N; base += RS_W * RS_H) {
-    const int pos = base + tid;
+
+  // ---- the winners of the tile (every thread its own pixel) and of the 1-pixel halo (the first 84
+  // threads one more); covered positions are appended to the work list, warp-aggregated ----
+  auto take = [&](bool active, int hx, int hy) {
+    const int pos = hy * RS_HW + hx;
+    const int gx = x0 + hx, gy = y0 + hy;
     unsigned long long key = 0;
-    if (pos < RS_N) {
-      const int gx = x0 + pos % RS_HW, gy = y0 + pos / RS_HW;
-      if (gx >= 0 && gx < p.W && gy >= p.fb0 && gy < p.fb1) key = p.keys[(size_t)gy * p.W + gx];
-      owner[pos] = (int)(unsigned)(key & 0xffffffffull) - 1;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) col[pos][k] = 0.f;
-      col[pos][9] = __uint_as_float((unsigned)(key >> 32));           // :665: the winner's zinv (0: empty)
-    }
+    if (active && gx >= 0 && gx < p.W && gy >= p.fb0 && gy < p.fb1) key = __ldcs(p.keys + (size_t)gy * p.W + gx);   // read once
     const bool covered = key != 0;
-    const unsigned m = __ballot_sync(0xffffffffu, covered);
-    if (lane == 0) warp_base[warp] = __popc(m);
-    __syncthreads();
-    if (tid == 0) {
-      int acc = n_work;
-      for (int w = 0; w < RS_W * RS_H / 32; ++w) { const int c = warp_base[w]; warp_base[w] = acc; acc += c; }
-      n_work = acc;
+    if (active) {
+      owner[pos] = (int)(unsigned)(key & 0xffffffffull) - 1;             // triangle << 5 | code, or -1
+      zinv_s[pos] = __uint_as_float((unsigned)(key >> 32));
+      if (!covered) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) col[k][pos] = 0.f;                          // cleared buffers (:244-249)
+      }
     }
-    __syncthreads();
-    if (covered) work[warp_base[warp] + __popc(m & ((1u << lane) - 1))] = (unsigned short)pos;
-    __syncthreads();
+    const unsigned m = __ballot_sync(0xffffffffu, covered);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&n_work, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (covered) work[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)pos;
+    }
+  };
+  take(true, tx + 1, ty + 1);
+  if (tid < 96) {   // warps 0..2, whole warps
+    const int h = tid;
+    int hx, hy;
+    if (h < RS_HW) { hx = h; hy = 0; }
+    else if (h < 2 * RS_HW) { hx = h - RS_HW; hy = RS_HH - 1; }
+    else if (h < 2 * RS_HW + RS_H) { hx = 0; hy = h - 2 * RS_HW + 1; }
+    else { hx = RS_HW - 1; hy = h - 2 * RS_HW - RS_H + 1; }
+    take(h < RS_HALO, h < RS_HALO ? hx : 0, h < RS_HALO ? hy : 0);
   }
+  __syncthreads();
 
   // ---- deferred PixelShader of every winner (:575-586) ----
-  for (int k = tid; k < n_work; k += RS_W * RS_H) {
+  const int nw = n_work;
+  for (int k = tid; k < nw; k += RS_W * RS_H) {
     const int pos = work[k];
     const int gx = x0 + pos % RS_HW, gy = y0 + pos / RS_HW;
-    const int t = owner[pos];
-    const int2 m = p.trimeta[t];
-    const unsigned rr = (unsigned)m.x + (unsigned)(gy - m.y);
-    const float4 B = p.rowsB[rr];
-    const float fi = (float)(gx - p.rowsL[rr]);
-    const float zinv = col[pos][9];                                 // as the scatter computed it (:543)
+    const unsigned low = (unsigned)owner[pos], code = low & 31u;
+    const int t = (int)(low >> 5);
+    float4 B;
+    int lx;
+    if (code < (unsigned)S2_ROWS) {                                 // small triangle: the record's place is in the key
+      const size_t rr = (size_t)t * S2_ROWS + code;
+      B = __ldg(p.srowsB + rr);
+      lx = __ldg(p.srowsL + rr);
+    } else {
+      const int2 m = __ldg(p.trimeta + t);
+      const unsigned rr = (unsigned)m.x + (unsigned)(gy - m.y);
+      B = __ldg(p.rowsB + rr);
+      lx = __ldg(p.rowsL + rr);
+    }
+    const float fi = (float)(gx - lx);
+    const float zinv = zinv_s[pos];                                 // as the scatter computed it (:543)
     const float pz = xdiv(1.0f, zinv);                              // :546
     const float px = xdiv(xadd(B.x, xmul(B.y, fi)), zinv);          // :547
     const float py = xdiv(xadd(B.z, xmul(B.w, fi)), zinv);          // :548
-    const rast_triangle *tr = p.src + t;
+    const float *tr = reinterpret_cast<const float *>(p.src + t);   // normal at words 12..14, colour at 16..18
     float D[3];
-    rast_illum_D(p, px, py, pz, tr->normal[0], tr->normal[1], tr->normal[2], D);
+    rast_illum_D(p, px, py, pz, __ldg(tr + 12), __ldg(tr + 13), __ldg(tr + 14), D);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float cc = tr->color[c];
-      col[pos][c] = xmul(cc, xadd(D[c], rast_indirect(p, c, t, (size_t)gy * p.W + gx)));   // :580
-      col[pos][3 + c] = xmul(cc, xadd(D[c], 0.0f));                 // :581-582
-      col[pos][6 + c] = xmul(cc, xadd(D[c], 0.4f));                 // :583-584
+      const float cc = __ldg(tr + 16 + c);
+      col[c][pos] = xmul(cc, xadd(D[c], rast_indirect(p, c, t, (size_t)gy * p.W + gx)));   // :580
+      col[3 + c][pos] = xmul(cc, xadd(D[c], 0.0f));                 // :581-582
+      col[6 + c][pos] = xmul(cc, xadd(D[c], 0.4f));                 // :583-584
     }
   }
   __syncthreads();
 
   // ---- post pass on the core pixels (:283-307, antiAliasing :1736-1753) ----
-  const int tx = tid % RS_W, ty = tid / RS_W;
   const int x = x0 + 1 + tx, y = y0 + 1 + ty;
-  if (x >= p.W || y >= p.row1) return;
+  if (y >= p.row1) return;                                           // warp-uniform: a warp is one row
+  const bool in_x = x < p.W;
   const int c0 = (ty + 1) * RS_HW + (tx + 1);
   const size_t q = (size_t)y * p.W + x;
   float out[3] = {0.f, 0.f, 0.f};
   const bool interior = y >= 1 && y <= p.H - 2 && x >= 1 && x <= p.W - 2;
   // five empty taps average to +0 exactly: nothing to compute (most pixels of a sparse scene)
   const bool any = (owner[c0] & owner[c0 - RS_HW] & owner[c0 + RS_HW] & owner[c0 - 1] & owner[c0 + 1]) >= 0;
-  if (interior && any) {
+  if (in_x && interior && any) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float acc[3];
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
-        const int k = 3 * b + c;
-        float a = xadd(col[c0][k], col[c0 - RS_HW][k]);
-        a = xadd(a, col[c0 + RS_HW][k]);
-        a = xadd(a, col[c0 - 1][k]);
-        a = xadd(a, col[c0 + 1][k]);
+        const float *cb = col[3 * b + c];
+        float a = xadd(cb[c0], cb[c0 - RS_HW]);
+        a = xadd(a, cb[c0 + RS_HW]);
+        a = xadd(a, cb[c0 - 1]);
+        a = xadd(a, cb[c0 + 1]);
         acc[b] = xdiv_const<5>(a);
       }
       out[c] = xdiv_const<3>(xadd(xadd(acc[0], acc[1]), acc[2]));     // :1750
     }
   }
-  if (p.out_rgb) { p.out_rgb[3 * q] = out[0]; p.out_rgb[3 * q + 1] = out[1]; p.out_rgb[3 * q + 2] = out[2]; }
+  if (p.out_rgb) {
+    const int xs = x0 + 1;                                           // first pixel of the warp's row segment
+    if (xs + RS_W <= p.W && (p.W & 3) == 0) {
+      // 32 pixels x 3 floats = 24 x 128-bit stores per warp instead of 96 scalar ones
+      float *st = out_stage[ty];
+      st[3 * tx] = out[0]; st[3 * tx + 1] = out[1]; st[3 * tx + 2] = out[2];
+      __syncwarp();
+      if (lane < 3 * RS_W / 4)
+        reinterpret_cast<float4 *>(p.out_rgb + 3 * ((size_t)y * p.W + xs))[lane] = reinterpret_cast<const float4 *>(st)[lane];
+    } else if (in_x) {
+      p.out_rgb[3 * q] = out[0]; p.out_rgb[3 * q + 1] = out[1]; p.out_rgb[3 * q + 2] = out[2];
+    }
+  }
+  if (!in_x) return;
   if (p.out_argb) p.out_argb[q] = interior ? put_pixel_argb(out[0], out[1], out[2]) : 0u;
-  if (p.out_depth) p.out_depth[q] = col[c0][9];
-  if (p.out_index) p.out_index[q] = owner[c0];
+  if (p.out_depth) p.out_depth[q] = zinv_s[c0];
+  if (p.out_index) p.out_index[q] = owner[c0] >> 5;                  // -1 >> 5 = -1
 }

@@ -31,6 +31,10 @@ struct GeomParams {
   unsigned *ticket;            // hands out block ids in scheduling order (forward progress of the look-back)
   unsigned long long *desc;    // per block: state << 62 | value; state 1 = block sum, 2 = inclusive prefix
   unsigned long long *total;   // list length
+  // single-pass mode on a list bound for the scatter path: the blocks also clear the key buffer
+  // (stores issued while their triangles are still on the way; saves a 66 MB memset launch at 4K)
+  uint4 *clear;
+  size_t clear_n;              // 16-byte units
 };
 
 // MODE 0: count the triangles each pre-clip triangle turns into; MODE 1: write them at the
@@ -48,6 +52,11 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
     __syncthreads();
   }
   const int bid = MODE == 2 ? (int)s_bid : (int)blockIdx.x;
+  if (MODE == 2 && p.clear_n) {
+    const size_t per = (p.clear_n + gridDim.x - 1) / gridDim.x;
+    const size_t a = (size_t)bid * per, b = a + per < p.clear_n ? a + per : p.clear_n;
+    for (size_t i = a + threadIdx.x; i < b; i += GT) p.clear[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   const int j0 = bid * GT;
   const int j = j0 + threadIdx.x;
   const int n_pre = p.n_room + 7 * p.n_boxes;
@@ -309,6 +318,11 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
     p.out = (rast_triangle *)ctx->rast_src.p;
     p.out_cap = (unsigned)cap;
     CU_CHECK(ctx, cudaMemsetAsync(p.ticket, 0, 16 + sizeof(unsigned long long) * (size_t)n_blocks, ctx->stream));
+    if (ctx->rast_clear_ptr && ((size_t)ctx->rast_clear_ptr & 15) == 0 && (ctx->rast_clear_bytes & 15) == 0) {
+      p.clear = (uint4 *)ctx->rast_clear_ptr;
+      p.clear_n = ctx->rast_clear_bytes / 16;
+      ctx->rast_keys_cleared = 1;
+    }
     rast_geom_kernel<2><<<n_blocks, 128, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     tl_mark(ctx, "rast_geom_kernel<2>");

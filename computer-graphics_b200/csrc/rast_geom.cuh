@@ -37,7 +37,7 @@ __device__ __forceinline__ GV gv_rotate(const float *R, const GV &v) {
   return o;
 }
 
-struct ClipCtx { int plane, W, H; float focal; };
+struct ClipCtx { int plane, W, H; float focal, wfar; };   // wfar = 5 / focal, the far limit of w (:1509)
 
 __device__ __forceinline__ float clip_coord(const ClipCtx &c, const GV &v) {
   return c.plane <= 2 ? v.x : (c.plane <= 4 ? v.y : v.w);
@@ -45,11 +45,13 @@ __device__ __forceinline__ float clip_coord(const ClipCtx &c, const GV &v) {
 // the plane's limit for this vertex: `dot[k]` (:732, :922, :1115, :1307) or wlimit (:1509)
 __device__ __forceinline__ float clip_limit(const ClipCtx &c, const GV &v) {
   switch (c.plane) {
-    case 1: return xdiv(xmul(v.w, (float)(-c.W)), 2.0f);
-    case 2: return xdiv(xmul(v.w, (float)(c.W)), 2.0f);
-    case 3: return xdiv(xmul(v.w, (float)(c.H)), 2.0f);
-    case 4: return xdiv(xmul(v.w, (float)(-c.H)), 2.0f);
-    default: return xdiv(5.0f, c.focal);
+    // x / 2 == x * 0.5f bit for bit for every float (a power-of-two scale is exact; the one rounding
+    // at the bottom of the denormal range is the same real number rounded the same way)
+    case 1: return xmul(xmul(v.w, (float)(-c.W)), 0.5f);
+    case 2: return xmul(xmul(v.w, (float)(c.W)), 0.5f);
+    case 3: return xmul(xmul(v.w, (float)(c.H)), 0.5f);
+    case 4: return xmul(xmul(v.w, (float)(-c.H)), 0.5f);
+    default: return c.wfar;
   }
 }
 __device__ __forceinline__ bool clip_in(const ClipCtx &c, const GV &v) {
@@ -62,7 +64,7 @@ __device__ __forceinline__ bool clip_out(const ClipCtx &c, const GV &v) {
 }
 // intersection parameter along a (inside) -> b (outside), e.g. t_01 at :753 / :943 / :1524
 __device__ __forceinline__ float clip_t(const ClipCtx &c, const GV &a, const GV &b) {
-  if (c.plane == 6) return xdiv(xsub(xdiv(5.0f, c.focal), a.w), xsub(b.w, a.w));
+  if (c.plane == 6) return xdiv(xsub(c.wfar, a.w), xsub(b.w, a.w));
   const int S = c.plane <= 2 ? c.W : c.H;
   const float h = (float)(S / 2), nh = (float)((-S) / 2);
   const float ca = c.plane <= 2 ? a.x : a.y, cb = c.plane <= 2 ? b.x : b.y;
@@ -91,10 +93,10 @@ __device__ __forceinline__ int clip_one(const ClipCtx &c, const GTri &in, GTri &
     o1.v[0] = np02; o1.v[1] = np12; o1.v[2] = b;
     return 2;
   }
-  const bool c02 = c.plane == 6 ? (i0 && x1 && d.x <= xdiv(5.0f, c.focal)) : (i0 && x1 && i2);   // :1607
+  const bool c02 = c.plane == 6 ? (i0 && x1 && d.x <= c.wfar) : (i0 && x1 && i2);   // :1607
   if (c02) {                                                    // :849-881
     const float t01 = clip_t(c, a, b);
-    const float t21 = c.plane == 6 ? xdiv(xsub(xdiv(5.0f, c.focal), d.w), xsub(b.w, a.w))        // :1615
+    const float t21 = c.plane == 6 ? xdiv(xsub(c.wfar, d.w), xsub(b.w, a.w))        // :1615
                                    : clip_t(c, d, b);
     const GV np01 = gv_lerp(a, b, t01), np21 = gv_lerp(d, b, t21);
     o0.v[1] = np01;
@@ -115,9 +117,10 @@ __device__ __forceinline__ int clip_one(const ClipCtx &c, const GTri &in, GTri &
 static __device__ __noinline__ int clip_six_planes(int W, int H, float focal, GTri *cur) {
   GTri nxt[32];
   int n_cur = 1;
+  const float wfar = xdiv(5.0f, focal);
   for (int plane = 1; plane <= 6; ++plane) {
     ClipCtx c;
-    c.plane = plane; c.W = W; c.H = H; c.focal = focal;
+    c.plane = plane; c.W = W; c.H = H; c.focal = focal; c.wfar = wfar;
     int n_nxt = 0;
     for (int i = 0; i < n_cur; ++i) {
       GTri o0, o1;
@@ -184,10 +187,11 @@ __device__ __forceinline__ void geom_preclip(const GeomXform &p, const rast_tria
 // A triangle inside all six planes comes out of the clip unchanged (one descendant).
 __device__ __forceinline__ bool geom_all_in(const GeomXform &p, const GTri &t) {
   bool all_in = true;
+  const float wfar = xdiv(5.0f, p.focal);
 #pragma unroll
   for (int plane = 1; plane <= 6; ++plane) {
     ClipCtx c;
-    c.plane = plane; c.W = p.W; c.H = p.H; c.focal = p.focal;
+    c.plane = plane; c.W = p.W; c.H = p.H; c.focal = p.focal; c.wfar = wfar;
     if (plane == 5) all_in = all_in && t.v[0].z > 0.01f && t.v[1].z > 0.01f && t.v[2].z > 0.01f;
     else all_in = all_in && clip_in(c, t.v[0]) && clip_in(c, t.v[1]) && clip_in(c, t.v[2]);
   }

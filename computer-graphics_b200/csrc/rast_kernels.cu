@@ -76,7 +76,9 @@ struct RastParams {
   unsigned row_cap;
   int fast;          // shadow-free list: scatter/resolve path (rast_fast.cuh)
   unsigned long long *keys;   // fast path: per-pixel (zinv bits, triangle + 1)
-  int *rowsL;        // fast path: left x of every stored row
+  int *rowsL;        // fast path: left x of every stored row (big triangles; rowsB likewise)
+  float4 *srowsB;    // fast path, small triangles: row records at triangle * S2_ROWS + y mod S2_ROWS
+  int *srowsL;
   int2 *trimeta;     // fast path: per triangle, index of its first stored row and that row's y
   int *big_list;     // fast path: triangles too large for rast_scatter2_kernel's shared-memory row table
   unsigned big_cap;
@@ -826,7 +828,8 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   const size_t npix = (size_t)W * H;
   if (ctx->opt_rast_path == 2 && ctx->rast_has_shadow)
     return ctx_fail(ctx, B200_EINVAL, "the scatter path cannot draw shadow-volume triangles");
-  const bool fast = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow);
+  if (ctx->opt_rast_path == 2 && n >= RAST_FAST_MAX_TRIS) return ctx_fail(ctx, B200_EINVAL, "too many triangles for the scatter path");
+  const bool fast = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow && n < RAST_FAST_MAX_TRIS);
   p.fast = fast ? 1 : 0;
   p.out_rgb = d_rgb; p.out_depth = d_depth; p.out_index = d_index; p.out_argb = d_argb;
   p.counters = (unsigned long long *)ctx->counters.p;
@@ -868,6 +871,11 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     p.keys = (unsigned long long *)ctx->rast_keys.p;
     if (int rc = ensure(ctx, ctx->rast_trimeta, sizeof(int2) * (size_t)(n ? n : 1))) return rc;
     p.trimeta = (int2 *)ctx->rast_trimeta.p;
+    // small triangles: S2_ROWS record places each, addressed by the key (only the rows drawn are touched)
+    if (int rc = ensure(ctx, ctx->rast_srowsB, sizeof(float4) * S2_ROWS * (size_t)(n ? n : 1))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_srowsL, sizeof(int) * S2_ROWS * (size_t)(n ? n : 1))) return rc;
+    p.srowsB = (float4 *)ctx->rast_srowsB.p;
+    p.srowsL = (int *)ctx->rast_srowsL.p;
     const int s2_blocks = (n + S2_THREADS - 1) / S2_THREADS;
     size_t n_rows = 1, big_cap = 0;
     if (spec) {
@@ -879,17 +887,16 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
       chunk_cap = 1;
       p.n_chunks = 0;
       if (n > 0) {
-        // exact sizes from a counting pass: [4] rows of the small triangles, [10] big triangles, [11] their rows
+        // exact sizes from a counting pass: [10] big triangles, [11] their rows
         rast_scatter2_kernel<true><<<s2_blocks, S2_THREADS, 0, ctx->stream>>>(p);
         ctx->stats.kernel_launches++;
         tl_mark(ctx, "rast_scatter2_kernel<count>");
         CU_CHECK(ctx, cudaGetLastError());
         CU_CHECK(ctx, cudaMemcpyAsync(hc, ctx->counters.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_CHECK(ctx, cudaMemsetAsync(p.counters + 4, 0, sizeof(unsigned long long), ctx->stream));
         CU_CHECK(ctx, cudaMemsetAsync(p.counters + 10, 0, 2 * sizeof(unsigned long long), ctx->stream));
         CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (hc[4] + hc[11] > 0xfffffff0ull) return ctx_fail(ctx, B200_ENOMEM, "row table budget exceeded");
-        n_rows = (size_t)(hc[4] + hc[11]);
+        if (hc[11] > 0xfffffff0ull) return ctx_fail(ctx, B200_ENOMEM, "row table budget exceeded");
+        n_rows = (size_t)hc[11];
         big_cap = (size_t)hc[10];
         chunk_cap = (size_t)hc[11];
         p.n_chunks = (unsigned)hc[11];
@@ -913,8 +920,11 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     p.chunk_cap = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
     // cleared right before the scatter so that the 64-bit keys (66 MB at 4K, less than the L2)
     // are still cache-resident when the atomics arrive
-    CU_CHECK(ctx, cudaMemsetAsync(p.keys + (size_t)p.fb0 * W, 0, (size_t)(p.fb1 - p.fb0) * W * sizeof(unsigned long long), ctx->stream));
-    tl_mark(ctx, "memset keys");
+    if (!ctx->rast_keys_cleared) {   // (a pipelined whole-Draw frame: already done by its geometry kernel)
+      CU_CHECK(ctx, cudaMemsetAsync(p.keys + (size_t)p.fb0 * W, 0, (size_t)(p.fb1 - p.fb0) * W * sizeof(unsigned long long), ctx->stream));
+      tl_mark(ctx, "memset keys");
+    }
+    ctx->rast_keys_cleared = 0;
     if (n > 0) {
       rast_scatter2_kernel<false><<<s2_blocks, S2_THREADS, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
