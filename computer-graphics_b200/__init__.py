@@ -65,13 +65,13 @@ class Stats(ctypes.Structure):
 
 # Every symbol include/b200render.h declares; tests check they are all exported.
 ABI_SYMBOLS = [
-    "b200_init", "b200_destroy", "b200_last_error", "b200_stream", "b200_synchronize",
+    "b200_init", "b200_init_multi", "b200_device_count", "b200_destroy", "b200_last_error", "b200_stream", "b200_synchronize",
     "b200_set_stream", "b200_set_option", "b200_get_stats",
     "b200_scene_cornell_rt", "b200_scene_cornell_rt_tessellated", "b200_scene_cornell_rast",
     "b200_scene_soup_rast",
     "render_raytrace", "render_raytrace_band", "draw_raytrace", "draw_raytrace_band",
     "b200_measure_fp32_peak", "rt_upload_scene", "rt_render_device",
-    "render_raster_clipped", "render_raster", "draw_raster", "raster_read_buffers",
+    "render_raster_clipped", "render_raster", "render_raster_band", "draw_raster", "raster_read_buffers",
     "raster_read_clipped", "rast_upload_clipped", "rast_render_device", "draw_raster_band",
     "rast_upload_scene", "rast_draw_device",
     "b200_quantise", "b200_save_bmp",
@@ -134,15 +134,22 @@ class B200Error(RuntimeError):
 
 
 class Renderer:
-    """One context on one GPU (one process per GPU: pass LOCAL_RANK)."""
+    """One context on one GPU (one process per GPU: pass LOCAL_RANK), or -- n_gpus given -- one
+    context that shares every host-pointer frame among the first n_gpus devices of the box."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, n_gpus=None):
         self.lib = load_library()
         self.ctx = ctypes.c_void_p()
-        rc = self.lib.b200_init(int(device), ctypes.byref(self.ctx))
+        if n_gpus is not None:
+            rc = self.lib.b200_init_multi(int(n_gpus), ctypes.byref(self.ctx))
+        else:
+            rc = self.lib.b200_init(int(device), ctypes.byref(self.ctx))
         if rc != B200_OK:
-            raise B200Error(f"b200_init(device={device}) failed with code {rc} "
+            raise B200Error(f"b200_init(device={device}, n_gpus={n_gpus}) failed with code {rc} "
                             "(no CUDA device? there is no CPU fallback)")
+
+    def device_count(self):
+        return int(self.lib.b200_device_count(self.ctx))
 
     def close(self):
         if self.ctx:
@@ -241,15 +248,17 @@ class Renderer:
         self._check(rc, "render_raster_clipped")
         return dict(rgb=rgb, depth=depth, index=index)
 
-    def render_raster(self, room, boxes, cam, light, want=("rgb", "depth", "index")):
+    def render_raster(self, room, boxes, cam, light, want=("rgb", "depth", "index"), row_begin=0, row_end=None):
         W, H = cam.width, cam.height
-        rgb = np.zeros((H, W, 3), np.float32) if "rgb" in want else None
-        depth = np.zeros((H, W), np.float32) if "depth" in want else None
-        index = np.zeros((H, W), np.int32) if "index" in want else None
-        rc = self.lib.render_raster(self.ctx, _ptr(room), len(room), _ptr(boxes), len(boxes),
-                                    ctypes.byref(cam), ctypes.byref(light), _ptr(rgb), _ptr(depth),
-                                    _ptr(index))
-        self._check(rc, "render_raster")
+        row_end = H if row_end is None else row_end
+        rows = row_end - row_begin
+        rgb = np.zeros((rows, W, 3), np.float32) if "rgb" in want else None
+        depth = np.zeros((rows, W), np.float32) if "depth" in want else None
+        index = np.zeros((rows, W), np.int32) if "index" in want else None
+        rc = self.lib.render_raster_band(self.ctx, _ptr(room), len(room), _ptr(boxes), len(boxes),
+                                         ctypes.byref(cam), ctypes.byref(light), int(row_begin), int(row_end),
+                                         _ptr(rgb), _ptr(depth), _ptr(index))
+        self._check(rc, "render_raster_band")
         return dict(rgb=rgb, depth=depth, index=index)
 
     def draw_raster(self, room, boxes, cam, light, out=None):

@@ -81,8 +81,13 @@ int b200_init(int device, b200_ctx **out) {
   return B200_OK;
 }
 
+// Entry points that only exist per device (device pointers, streams, intermediate buffers).
+#define SINGLE_ONLY(ctx) \
+  do { if ((ctx)->multi) return ctx_fail(ctx, B200_EINVAL, "not available on a multi-GPU context: use one context per device"); } while (0)
+
 void b200_destroy(b200_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->multi) { multi_destroy(ctx); delete ctx; return; }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rt_dtcam, &ctx->rt_cells, &ctx->rt_cell_rec, &ctx->rt_cell_idx, &ctx->rast_src,
@@ -103,7 +108,7 @@ void b200_destroy(b200_ctx *ctx) {
 }
 
 const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-void *b200_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+void *b200_stream(b200_ctx *ctx) { return ctx && !ctx->multi ? (void *)ctx->stream : nullptr; }
 
 static int finish_stats(b200_ctx *ctx);
 
@@ -111,11 +116,13 @@ static int finish_stats(b200_ctx *ctx);
 // size guess was too small), so what is on the device afterwards is always exact.
 int b200_synchronize(b200_ctx *ctx) {
   if (!ctx) return B200_EINVAL;
+  if (ctx->multi) return multi_synchronize(ctx);
   return finish_stats(ctx);
 }
 
 int b200_set_stream(b200_ctx *ctx, void *cuda_stream) {
   if (!ctx) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   if (int rc = finish_stats(ctx)) return rc;
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return B200_OK;
@@ -123,6 +130,7 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream) {
 
 int b200_set_option(b200_ctx *ctx, int option, int value) {
   if (!ctx) return B200_EINVAL;
+  if (ctx->multi) return multi_set_option(ctx, option, value);
   switch (option) {
     case B200_OPT_RT_BRUTEFORCE: ctx->opt_rt_bruteforce = value != 0; return B200_OK;
     case B200_OPT_RAST_PATH:
@@ -156,6 +164,7 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
 
 int b200_get_stats(b200_ctx *ctx, b200_stats *out) {
   if (!ctx || !out) return B200_EINVAL;
+  if (ctx->multi) { *out = ctx->stats; return B200_OK; }   // summed over the devices by the last frame
   if (int rc = finish_stats(ctx)) return rc;
   *out = ctx->stats;
   return B200_OK;
@@ -181,6 +190,7 @@ static int check_camera(b200_ctx *ctx, const camera_t *cam) {
 int rt_upload_scene(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres,
                     int n_spheres) {
   if (!ctx) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   if (n_tris < 0 || n_spheres < 0 || (n_tris > 0 && !tris) || (n_spheres > 0 && !spheres))
     return ctx_fail(ctx, B200_EINVAL, "bad scene arguments");
   cudaSetDevice(ctx->device);
@@ -257,6 +267,7 @@ int rt_render_device(b200_ctx *ctx, const camera_t *cam, const light_t *lights, 
                      int row_begin, int row_end, float *d_rgb, float *d_depth, int32_t *d_index,
                      uint32_t *d_argb) {
   if (!ctx) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   return rt_frame_device(ctx, cam, lights, n_lights, row_begin, row_end, d_rgb, d_depth, d_index, d_argb,
                          ctx->opt_rt_il_n, ctx->opt_rt_il_r);
 }
@@ -346,6 +357,9 @@ int render_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris, con
                          int row_begin, int row_end, float *rgb_out, float *depth_out,
                          int32_t *index_out) {
   if (!ctx) return B200_EINVAL;
+  if (ctx->multi)
+    return multi_raytrace(ctx, tris, n_tris, spheres, n_spheres, cam, lights, n_lights, row_begin, row_end, rgb_out,
+                          depth_out, index_out, nullptr);
   if (int rc = check_camera(ctx, cam)) return rc;
   if (int rc = rt_upload_scene(ctx, tris, n_tris, spheres, n_spheres)) return rc;
   const size_t npix = (size_t)cam->width * cam->height;
@@ -378,6 +392,9 @@ int draw_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const
                        int row_begin, int row_end, uint32_t *argb_out) {
   if (!ctx) return B200_EINVAL;
   if (!argb_out) return ctx_fail(ctx, B200_EINVAL, "null framebuffer");
+  if (ctx->multi)
+    return multi_raytrace(ctx, tris, n_tris, spheres, n_spheres, cam, lights, n_lights, row_begin, row_end, nullptr,
+                          nullptr, nullptr, argb_out);
   if (int rc = check_camera(ctx, cam)) return rc;
   if (int rc = rt_upload_scene(ctx, tris, n_tris, spheres, n_spheres)) return rc;
   const size_t npix = (size_t)cam->width * cam->height;
@@ -442,6 +459,7 @@ __global__ void b200_ffma_peak_kernel(float *out, int iters, float a, float b) {
 
 int b200_measure_fp32_peak(b200_ctx *ctx, float *tflops_out) {
   if (!ctx || !tflops_out) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   cudaSetDevice(ctx->device);
   if (int rc = finish_stats(ctx)) return rc;   // ev0 / ev1 still time a pending frame
   const int blocks = ctx->sm_count * 2, threads = 1024, iters = 4096;
@@ -467,6 +485,7 @@ int b200_measure_fp32_peak(b200_ctx *ctx, float *tflops_out) {
 
 int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris) {
   if (!ctx) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   if (n_tris < 0 || (n_tris > 0 && !clipped)) return ctx_fail(ctx, B200_EINVAL, "bad triangle list");
   cudaSetDevice(ctx->device);
   if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // a re-render must see its own scene
@@ -550,6 +569,7 @@ static int rast_check_frame_args(b200_ctx *ctx, const camera_t *cam, const rast_
 int rast_render_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin,
                        int row_end, float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
   if (!ctx) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   if (int rc = rast_check_frame_args(ctx, cam, light, row_begin, row_end)) return rc;
   return rast_frame(ctx, false, cam, light, row_begin, row_end, d_rgb, d_depth, d_index, d_argb,
                     ctx->opt_rast_pipelined != 0);
@@ -568,6 +588,7 @@ static int raster_host_outputs(b200_ctx *ctx, const camera_t *cam, float *rgb_ou
 int render_raster_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris, const camera_t *cam,
                           const rast_light_t *light, float *rgb_out, float *depth_out, int32_t *index_out) {
   if (!ctx) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   if (int rc = check_camera(ctx, cam)) return rc;
   if (int rc = rast_upload_clipped(ctx, clipped, n_tris)) return rc;
   if (int rc = raster_host_outputs(ctx, cam, rgb_out, depth_out, index_out, nullptr)) return rc;
@@ -589,6 +610,7 @@ int render_raster_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tri
 int rast_upload_scene(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes,
                       int n_boxes) {
   if (!ctx) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   if (n_room < 0 || n_boxes < 0 || (n_room > 0 && !room) || (n_boxes > 0 && !boxes))
     return ctx_fail(ctx, B200_EINVAL, "bad scene arguments");
   if ((long long)n_room + 7ll * n_boxes > 0x3fffffffll) return ctx_fail(ctx, B200_EINVAL, "scene too large");
@@ -610,9 +632,52 @@ int rast_upload_scene(b200_ctx *ctx, const rast_triangle *room, int n_room, cons
 int rast_draw_device(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin, int row_end,
                      float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb) {
   if (!ctx) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   if (int rc = rast_check_frame_args(ctx, cam, light, row_begin, row_end)) return rc;
   return rast_frame(ctx, true, cam, light, row_begin, row_end, d_rgb, d_depth, d_index, d_argb,
                     ctx->opt_rast_pipelined != 0);
+}
+
+}  // extern "C"
+
+// Rows [row_begin, row_end) of the whole Draw on the scene already uploaded to this context,
+// into band-sized HOST buffers.  With only the packed frame asked for, the rows leave for the
+// host slice by slice while the next slice is resolved.
+int rast_band_resident(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin, int row_end,
+                       float *rgb_out, float *depth_out, int32_t *index_out, uint32_t *argb_out) {
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (int rc = raster_host_outputs(ctx, cam, rgb_out, depth_out, index_out, argb_out)) return rc;
+  if (int rc = rast_check_frame_args(ctx, cam, light, row_begin, row_end)) return rc;
+  const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
+  const bool sliced = argb_out && !rgb_out && !depth_out && !index_out;
+  if (sliced) band_slices_begin(ctx, argb_out, (const uint32_t *)ctx->out_argb.p, row_begin, cam->width);
+  const int rc_frame = rast_frame(ctx, true, cam, light, row_begin, row_end, rgb_out ? (float *)ctx->out_rgb.p : nullptr,
+                                  depth_out ? (float *)ctx->out_depth.p : nullptr,
+                                  index_out ? (int32_t *)ctx->out_index.p : nullptr,
+                                  argb_out ? (uint32_t *)ctx->out_argb.p : nullptr, true);
+  if (sliced) if (int rc = band_slices_end(ctx)) return rc;
+  if (rc_frame) return rc_frame;
+  const uint64_t twice = ctx->stats.respeculated;
+  if (int rc = finish_stats(ctx)) return rc;     // verifies a pipelined frame; renders it again if it outgrew its guess
+  if (sliced && ctx->stats.respeculated == twice) return B200_OK;   // every row already left with its slice
+  if (int rc = copy_out(ctx, rgb_out, (float *)ctx->out_rgb.p + 3 * off, cnt * 3 * sizeof(float))) return rc;
+  if (int rc = copy_out(ctx, depth_out, (float *)ctx->out_depth.p + off, cnt * sizeof(float))) return rc;
+  if (int rc = copy_out(ctx, index_out, (int32_t *)ctx->out_index.p + off, cnt * sizeof(int32_t))) return rc;
+  if (int rc = copy_out(ctx, argb_out, (uint32_t *)ctx->out_argb.p + off, cnt * sizeof(uint32_t))) return rc;
+  return finish_stats(ctx);
+}
+
+extern "C" {
+
+int render_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes, int n_boxes,
+                       const camera_t *cam, const rast_light_t *light, int row_begin, int row_end, float *rgb_out,
+                       float *depth_out, int32_t *index_out) {
+  if (!ctx) return B200_EINVAL;
+  if (ctx->multi)
+    return multi_raster(ctx, room, n_room, boxes, n_boxes, cam, light, row_begin, row_end, rgb_out, depth_out, index_out, nullptr);
+  if (int rc = check_camera(ctx, cam)) return rc;
+  if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
+  return rast_band_resident(ctx, cam, light, row_begin, row_end, rgb_out, depth_out, index_out, nullptr);
 }
 
 int render_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes, int n_boxes,
@@ -620,19 +685,7 @@ int render_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const ra
                   int32_t *index_out) {
   if (!ctx) return B200_EINVAL;
   if (int rc = check_camera(ctx, cam)) return rc;
-  if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
-  if (int rc = raster_host_outputs(ctx, cam, rgb_out, depth_out, index_out, nullptr)) return rc;
-  if (int rc = rast_check_frame_args(ctx, cam, light, 0, cam->height)) return rc;
-  if (int rc = rast_frame(ctx, true, cam, light, 0, cam->height, rgb_out ? (float *)ctx->out_rgb.p : nullptr,
-                          depth_out ? (float *)ctx->out_depth.p : nullptr,
-                          index_out ? (int32_t *)ctx->out_index.p : nullptr, nullptr, true))
-    return rc;
-  if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;
-  const size_t npix = (size_t)cam->width * cam->height;
-  if (int rc = copy_out(ctx, rgb_out, ctx->out_rgb.p, npix * 3 * sizeof(float))) return rc;
-  if (int rc = copy_out(ctx, depth_out, ctx->out_depth.p, npix * sizeof(float))) return rc;
-  if (int rc = copy_out(ctx, index_out, ctx->out_index.p, npix * sizeof(int32_t))) return rc;
-  return finish_stats(ctx);
+  return render_raster_band(ctx, room, n_room, boxes, n_boxes, cam, light, 0, cam->height, rgb_out, depth_out, index_out);
 }
 
 int draw_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes,
@@ -640,24 +693,11 @@ int draw_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room, const
                      uint32_t *argb_out) {
   if (!ctx) return B200_EINVAL;
   if (!argb_out) return ctx_fail(ctx, B200_EINVAL, "null framebuffer");
+  if (ctx->multi)
+    return multi_raster(ctx, room, n_room, boxes, n_boxes, cam, light, row_begin, row_end, nullptr, nullptr, nullptr, argb_out);
   if (int rc = check_camera(ctx, cam)) return rc;
   if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
-  if (int rc = raster_host_outputs(ctx, cam, nullptr, nullptr, nullptr, argb_out)) return rc;
-  if (int rc = rast_check_frame_args(ctx, cam, light, row_begin, row_end)) return rc;
-  // the packed rows leave for the host slice by slice while the next slice is resolved
-  band_slices_begin(ctx, argb_out, (const uint32_t *)ctx->out_argb.p, row_begin, cam->width);
-  const int rc_frame = rast_frame(ctx, true, cam, light, row_begin, row_end, nullptr, nullptr, nullptr,
-                                  (uint32_t *)ctx->out_argb.p, true);
-  if (int rc = band_slices_end(ctx)) return rc;
-  if (rc_frame) return rc_frame;
-  const uint64_t twice = ctx->stats.respeculated;
-  if (int rc = finish_stats(ctx)) return rc;     // verifies a pipelined frame; renders it again if it outgrew its guess
-  if (ctx->stats.respeculated != twice) {        // ... in which case the rows copied so far were not final
-    const size_t off = (size_t)row_begin * cam->width, cnt = (size_t)(row_end - row_begin) * cam->width;
-    if (int rc = copy_out(ctx, argb_out, (uint32_t *)ctx->out_argb.p + off, cnt * sizeof(uint32_t))) return rc;
-    return finish_stats(ctx);
-  }
-  return B200_OK;
+  return rast_band_resident(ctx, cam, light, row_begin, row_end, nullptr, nullptr, nullptr, argb_out);
 }
 
 int draw_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes, int n_boxes,
@@ -669,6 +709,7 @@ int draw_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast
 
 int raster_read_clipped(b200_ctx *ctx, rast_triangle *out, int cap, int *n_out) {
   if (!ctx || !n_out) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   if (int rc = finish_stats(ctx)) return rc;
   *n_out = ctx->rast_n_tris;
   const int n = ctx->rast_n_tris < cap ? ctx->rast_n_tris : cap;
@@ -678,6 +719,7 @@ int raster_read_clipped(b200_ctx *ctx, rast_triangle *out, int cap, int *n_out) 
 
 int raster_read_buffers(b200_ctx *ctx, float *screen_out, float *low_out, float *high_out, int32_t *shadow_out) {
   if (!ctx) return B200_EINVAL;
+  SINGLE_ONLY(ctx);
   if (ctx->rast_w <= 0)
     return ctx_fail(ctx, B200_EINVAL, "no intermediate buffers: nothing rendered yet, or the last frame took the "
                                       "scatter path (set B200_OPT_RAST_PATH to 1 to keep them)");

@@ -72,7 +72,9 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+struct b200_multi;   // multi.cu
 struct b200_ctx {
+  b200_multi *multi = nullptr;        // set on a context made by b200_init_multi: it only fans out to one ordinary context per device
   int device = 0;
   cudaStream_t stream = nullptr;      // where work is enqueued (own_stream unless overridden)
   cudaStream_t own_stream = nullptr;
@@ -207,3 +209,13 @@ static inline int band_slice_edge(int row0, int rows, int i, int k, int align) {
 }
 int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int32_t *d_index,
               uint32_t *d_argb);
+// multi.cu: entry points of a multi-GPU context (api.cu forwards to these)
+void multi_destroy(b200_ctx *ctx);
+int multi_synchronize(b200_ctx *ctx);
+int multi_set_option(b200_ctx *ctx, int option, int value);
+int multi_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres, int n_spheres,
+                   const camera_t *cam, const light_t *lights, int n_lights, int row_begin, int row_end,
+                   float *rgb_out, float *depth_out, int32_t *index_out, uint32_t *argb_out);
+int multi_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const rast_triangle *boxes, int n_boxes,
+                 const camera_t *cam, const rast_light_t *light, int row_begin, int row_end, float *rgb_out,
+                 float *depth_out, int32_t *index_out, uint32_t *argb_out);

@@ -105,6 +105,17 @@ typedef struct b200_ctx b200_ctx;
 /* Creates a context on CUDA device `device` (one process per GPU: pass
  * LOCAL_RANK).  Fails with B200_ENODEV when there is no GPU. */
 int b200_init(int device, b200_ctx **out);
+/* One context for the first n_gpus devices of the box (0: all of them).  This is the
+ * `b200_init(n_gpus)` of the drop-in contract: behind `Draw(screen*)` the HOST-pointer entry
+ * points (render_raytrace*, draw_raytrace*, render_raster, render_raster_band, draw_raster*)
+ * share every frame among the devices by row bands -- one host thread and one ordinary context
+ * per device, the raytracer's bands following the measured cost of the previous frame, the
+ * rasteriser's scene uploaded in N slices and all-gathered between the devices over NVLink --
+ * and return when the assembled frame is in the caller's buffers.  Results are bit-identical to
+ * a single device's.  The device-pointer entries, streams and intermediate buffers exist per
+ * device only (B200_EINVAL here).  b200_get_stats: sums over the devices, gpu_ms the slowest. */
+int b200_init_multi(int n_gpus, b200_ctx **out);
+int b200_device_count(const b200_ctx *ctx);
 void b200_destroy(b200_ctx *ctx);
 /* Human-readable text of the last error on this context ("" if none). */
 const char *b200_last_error(const b200_ctx *ctx);
@@ -232,6 +243,12 @@ int render_raster(b200_ctx *ctx, const rast_triangle *room, int n_room,
                   const rast_triangle *boxes, int n_boxes, const camera_t *cam,
                   const rast_light_t *light, float *rgb_out, float *depth_out,
                   int32_t *index_out);
+
+/* Rows [row_begin, row_end) of render_raster; the outputs are band-sized. */
+int render_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room,
+                       const rast_triangle *boxes, int n_boxes, const camera_t *cam,
+                       const rast_light_t *light, int row_begin, int row_end, float *rgb_out,
+                       float *depth_out, int32_t *index_out);
 
 /* screen->buffer of the whole rasteriser Draw. */
 int draw_raster(b200_ctx *ctx, const rast_triangle *room, int n_room,
