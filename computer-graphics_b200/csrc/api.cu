@@ -92,7 +92,7 @@ void b200_destroy(b200_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rt_dtcam, &ctx->rt_cells, &ctx->rt_cell_rec, &ctx->rt_cell_idx, &ctx->rast_src,
                     &ctx->rast_setup, &ctx->rast_rowsA, &ctx->rast_rowsB, &ctx->rast_bins, &ctx->rast_tile_count, &ctx->rast_tile_bits,
-                    &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_trimeta, &ctx->rast_big, &ctx->rast_srowsB, &ctx->rast_srowsL, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
+                    &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_trimeta, &ctx->rast_big, &ctx->rast_orig, &ctx->rast_srowsB, &ctx->rast_srowsL, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
                     &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
                     &ctx->out_argb, &ctx->counters};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -152,6 +152,10 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
       return B200_OK;
     case B200_OPT_RAST_PIPELINED:
       ctx->opt_rast_pipelined = value != 0;
+      ctx->rast_spec.valid = 0;
+      return B200_OK;
+    case B200_OPT_RAST_BAND_CULL:
+      ctx->opt_rast_band_cull = value != 0;
       ctx->rast_spec.valid = 0;
       return B200_OK;
     case B200_OPT_RAST_TILE_LOG2:
@@ -512,12 +516,12 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
   const int n_list = whole_draw ? -1 : ctx->rast_n_tris;
   const bool same = sp.valid && sp.whole_draw == (whole_draw ? 1 : 0) && sp.W == cam->width && sp.H == cam->height &&
                     sp.row0 == row_begin && sp.row1 == row_end && sp.ts == ctx->opt_rast_tile_log2 &&
-                    sp.fast == ctx->opt_rast_path && sp.n_list == n_list &&
+                    sp.fast == ctx->opt_rast_path && sp.n_list == n_list && sp.cull == ctx->opt_rast_band_cull &&
                     (!whole_draw || (sp.n_room == ctx->rast_n_room && sp.n_boxes == ctx->rast_n_boxes));
   const bool spec = allow_spec && same;
   sp.valid = 0;
   sp.whole_draw = whole_draw ? 1 : 0; sp.W = cam->width; sp.H = cam->height; sp.row0 = row_begin; sp.row1 = row_end;
-  sp.ts = ctx->opt_rast_tile_log2; sp.fast = ctx->opt_rast_path; sp.n_list = n_list;
+  sp.ts = ctx->opt_rast_tile_log2; sp.fast = ctx->opt_rast_path; sp.n_list = n_list; sp.cull = ctx->opt_rast_band_cull;
   sp.n_room = ctx->rast_n_room; sp.n_boxes = ctx->rast_n_boxes;
   b200_ctx::RastInflight &f = ctx->rast_inflight;
   f.active = 0;
@@ -534,7 +538,8 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
   ctx->tl_n = 0;
   tl_mark(ctx, "frame start");
   rast_light_t lc = *light;
-  ctx->rast_clear_ptr = nullptr; ctx->rast_keys_cleared = 0;
+  ctx->rast_clear_ptr = nullptr; ctx->rast_keys_cleared = 0; ctx->rast_cull_on = 0;
+  if (!whole_draw) ctx->rast_culled = 0;   // the caller's own list
   if (whole_draw) {
     if (spec && (ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow))) {
       // the frame is bound for the scatter path: its geometry kernel clears the key rows on the way
@@ -544,6 +549,13 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
       if (fb1 > fb0) {
         ctx->rast_clear_ptr = (unsigned long long *)ctx->rast_keys.p + (size_t)fb0 * W;
         ctx->rast_clear_bytes = (size_t)(fb1 - fb0) * W * sizeof(unsigned long long);
+      }
+      // ... and, asked to, keeps only the triangles that reach the band's rows.  (Not when the entry
+      // value of the indirect light is in play: its one fragment is found on the complete list.)
+      const float steady = 0.2f * 1.0f;
+      const bool quirk = memcmp(&light->indirect[0], &steady, 4) || memcmp(&light->indirect[1], &steady, 4) || memcmp(&light->indirect[2], &steady, 4);
+      if (ctx->opt_rast_band_cull && !quirk && (fb0 > 0 || fb1 < cam->height)) {
+        ctx->rast_cull_on = 1; ctx->rast_cull0 = fb0; ctx->rast_cull1 = fb1;
       }
     }
     if (int rc = rast_geometry(ctx, cam, light, &lc, spec)) return rc;

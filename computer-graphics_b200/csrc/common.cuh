@@ -114,6 +114,10 @@ struct b200_ctx {
   int rast_n_tris = 0;
   DevBuf rast_setup, rast_rowsA, rast_rowsB, rast_bins, rast_tile_count, rast_tmp, rast_tile_bits;
   DevBuf rast_keys;      // fast path: 64-bit (zinv, triangle) key per pixel
+  int opt_rast_band_cull = 0;        // B200_OPT_RAST_BAND_CULL
+  int rast_cull_on = 0, rast_cull0 = 0, rast_cull1 = 0;   // this frame's geometry stage should keep only rows [cull0, cull1) ...
+  int rast_culled = 0;               // ... and did: rast_src is the band's list, rast_orig its indices in the complete list
+  DevBuf rast_orig;
   void *rast_clear_ptr = nullptr;    // key rows the single-pass geometry kernel should clear (set per frame by rast_frame)
   size_t rast_clear_bytes = 0;
   int rast_keys_cleared = 0;         // ... and whether it did (rast_launch then skips its memset)
@@ -134,7 +138,7 @@ struct b200_ctx {
   // guess is re-rendered synchronously before anything is handed out.
   int opt_rast_pipelined = 0;
   struct RastSpec {
-    int valid = 0, has_shadow = 0, n_room = 0, n_boxes = 0, n_list = 0, W = 0, H = 0, row0 = 0, row1 = 0, fast = 0, ts = 0, whole_draw = 0;
+    int valid = 0, has_shadow = 0, n_room = 0, n_boxes = 0, n_list = 0, W = 0, H = 0, row0 = 0, row1 = 0, fast = 0, ts = 0, whole_draw = 0, cull = 0;
     unsigned long long tris = 0, chunks = 0, rows = 0, bins = 0, big = 0;
   } rast_spec;
   struct RastInflight {

@@ -187,7 +187,10 @@ int b200_init_multi(int n_gpus, b200_ctx **out) {
   for (int i = 0; i < n_gpus && rc == B200_OK; ++i) {
     b200_ctx *c = nullptr;
     rc = b200_init(i, &c);
-    if (rc == B200_OK) mc->child.push_back(c);
+    if (rc == B200_OK) {
+      mc->child.push_back(c);
+      b200_set_option(c, B200_OPT_RAST_BAND_CULL, 1);   // every device's geometry stage keeps its band's triangles only
+    }
   }
   // peer access between every pair (NVLink / NVSwitch): the rasteriser's scene all-gather
   mc->peer_ok = rc == B200_OK ? 1 : 0;

@@ -460,5 +460,8 @@ __global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __gr
   if (!in_x) return;
   if (p.out_argb) p.out_argb[q] = interior ? put_pixel_argb(out[0], out[1], out[2]) : 0u;
   if (p.out_depth) p.out_depth[q] = zinv_s[c0];
-  if (p.out_index) p.out_index[q] = owner[c0] >> 5;                  // -1 >> 5 = -1
+  if (p.out_index) {
+    const int t = owner[c0] >> 5;                                    // -1 >> 5 = -1
+    p.out_index[q] = (t >= 0 && p.orig) ? __ldg(p.orig + t) : t;
+  }
 }

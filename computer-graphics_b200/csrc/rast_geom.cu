@@ -15,6 +15,7 @@
 // the far plane kept (:1607 tests v2.x instead of v2.w; :1615 divides by
 // (w1 - w0) instead of (w1 - w2)).
 #include "rast_geom.cuh"
+#include <limits.h>
 
 struct GeomParams {
   GeomXform x;
@@ -35,6 +36,11 @@ struct GeomParams {
   // (stores issued while their triangles are still on the way; saves a 66 MB memset launch at 4K)
   uint4 *clear;
   size_t clear_n;              // 16-byte units
+  // single-pass mode, band culling (B200_OPT_RAST_BAND_CULL): only the triangles whose vertex rows
+  // (VertexShader :513, truncated like :516) meet [cull0, cull1) are written, in list order, and
+  // orig[] receives their indices in the complete list (what the owner-index output reports)
+  int cull, cull0, cull1;
+  int *orig;
 };
 
 // MODE 0: count the triangles each pre-clip triangle turns into; MODE 1: write them at the
@@ -46,7 +52,7 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
   constexpr bool WRITE = MODE != 0;
   constexpr int GT = 128, TW = sizeof(rast_triangle) / 4;
   __shared__ uint32_t stage[GT * TW];   // coalesced word streams in and out of the 84-byte records
-  __shared__ unsigned s_bid, s_warp[4], s_prefix;
+  __shared__ unsigned s_bid, s_warp[4], s_prefix, s_prefix_all;
   if (MODE == 2) {
     if (threadIdx.x == 0) s_bid = atomicAdd(p.ticket, 1u);
     __syncthreads();
@@ -92,11 +98,31 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
     if (j < n_pre) p.counts[j] = (unsigned)n_cur;
     return;
   }
-  unsigned my_off = 0;   // where this thread's first output goes
+  // ---- single pass: which descendants are kept, where they go ----
+  // kept: bit i set when descendant i is written (all of them unless the band is culled)
+  unsigned kept = n_cur >= 32 ? 0xffffffffu : ((1u << n_cur) - 1u);
+  if (MODE == 2 && p.cull) {
+    kept = 0;
+    for (int i = 0; i < n_cur; ++i) {
+      int ymin = INT_MAX, ymax = INT_MIN;
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const GV &v = cur[i].v[k];
+        const float y = xadd(xmul(p.x.focal, xdiv(v.y, v.z)), (float)(p.x.H / 2));   // :513
+        ok = ok && fabsf(y) < 8.0e6f;                       // not convertible: the triangle loop drops it
+        const int yi = ok ? (int)y : 0;                     // :516 static_cast<int>
+        ymin = min(ymin, yi); ymax = max(ymax, yi);
+      }
+      if (ok && ymax >= p.cull0 && ymin < p.cull1) kept |= 1u << i;
+    }
+  }
+  if (j >= n_pre) kept = 0;
+  unsigned my_off = 0, my_all = 0;   // first kept output of this thread in the written list / first descendant in the complete list
+  const unsigned cnt_all = j < n_pre ? (unsigned)n_cur : 0u, cnt_kept = (unsigned)__popc(kept);
   if (MODE == 2) {
-    const unsigned cnt = j < n_pre ? (unsigned)n_cur : 0u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned incl = cnt;
+    unsigned incl = cnt_all | (cnt_kept << 16);   // both counts in one scan: at most 32 each per thread, 4096 per block
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -107,12 +133,14 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
     unsigned before = 0, block_sum = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) { before += w < warp ? s_warp[w] : 0u; block_sum += s_warp[w]; }
+    const unsigned long long block_val = (unsigned long long)(block_sum & 0xffffu) | ((unsigned long long)(block_sum >> 16) << 31);
     if (warp == 0) {
       // Decoupled look-back by the whole warp: lane l inspects the block l places back; the
       // window moves 32 blocks at a time until it contains a block whose inclusive prefix is known.
-      // Every block before this one already holds its ticket, so it will publish.
+      // Every block before this one already holds its ticket, so it will publish.  The value carries
+      // two sums: complete list (low 31 bits) and written list (next 31 bits).
       const unsigned long long VAL = (1ull << 62) - 1;
-      if (lane == 0 && bid > 0) atomicExch(p.desc + bid, (1ull << 62) | block_sum);
+      if (lane == 0 && bid > 0) atomicExch(p.desc + bid, (1ull << 62) | block_val);
       unsigned long long prefix = 0;
       for (int base = bid - 1;;) {
         const int k = base - lane;
@@ -130,36 +158,46 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
         base -= 32;
       }
       if (lane == 0) {
-        atomicExch(p.desc + bid, (2ull << 62) | (prefix + block_sum));
-        if (bid == (int)gridDim.x - 1) *p.total = prefix + block_sum;
-        s_prefix = (unsigned)prefix;
+        atomicExch(p.desc + bid, (2ull << 62) | (prefix + block_val));
+        if (bid == (int)gridDim.x - 1) *p.total = (prefix + block_val) >> 31;   // length of the written list
+        s_prefix = (unsigned)(prefix >> 31);
+        s_prefix_all = (unsigned)(prefix & 0x7fffffffull);
       }
     }
     __syncthreads();
-    my_off = s_prefix + before + incl - cnt;
+    const unsigned ex = before + incl - (cnt_all | (cnt_kept << 16));   // exclusive, both halves (no carry: sums < 65536)
+    my_off = s_prefix + (ex >> 16);
+    my_all = s_prefix_all + (ex & 0xffffu);
   }
-  // Common case: the whole block is unclipped (one output each, contiguous in the
-  // list): write the records through shared memory as one coalesced stream.
+  // Common case: no triangle of the block is clipped (at most one output each): the kept records
+  // go through shared memory, compacted, and leave as one coalesced stream.
   if (__syncthreads_and(staged_in && n_cur == 1)) {
-    float *o = reinterpret_cast<float *>(stage) + threadIdx.x * TW;
-    const GTri &g = cur[0];
-    o[0] = g.v[0].x; o[1] = g.v[0].y; o[2] = g.v[0].z; o[3] = g.v[0].w;
-    o[4] = g.v[1].x; o[5] = g.v[1].y; o[6] = g.v[1].z; o[7] = g.v[1].w;
-    o[8] = g.v[2].x; o[9] = g.v[2].y; o[10] = g.v[2].z; o[11] = g.v[2].w;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) o[12 + k] = attr[k];
-    __syncthreads();
     const unsigned off0 = MODE == 2 ? s_prefix : p.offs[j0];
+    const unsigned slot = MODE == 2 ? my_off - off0 : threadIdx.x;   // position among the block's kept records
+    __syncthreads();   // (every thread has read its input record from `stage`)
+    if (kept) {
+      float *o = reinterpret_cast<float *>(stage) + slot * TW;
+      const GTri &g = cur[0];
+      o[0] = g.v[0].x; o[1] = g.v[0].y; o[2] = g.v[0].z; o[3] = g.v[0].w;
+      o[4] = g.v[1].x; o[5] = g.v[1].y; o[6] = g.v[1].z; o[7] = g.v[1].w;
+      o[8] = g.v[2].x; o[9] = g.v[2].y; o[10] = g.v[2].z; o[11] = g.v[2].w;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) o[12 + k] = attr[k];
+      if (MODE == 2 && p.orig && my_off < p.out_cap) p.orig[my_off] = (int)my_all;
+    }
+    const unsigned n_out = MODE == 2 ? (s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3]) >> 16 : (unsigned)GT;
+    __syncthreads();
     uint32_t *dst = reinterpret_cast<uint32_t *>(p.out + off0);
-    if (off0 + GT <= p.out_cap)
-      for (int i = threadIdx.x; i < GT * TW; i += GT) dst[i] = stage[i];
+    if (off0 + n_out <= p.out_cap)
+      for (int i = threadIdx.x; i < (int)n_out * TW; i += GT) dst[i] = stage[i];
     return;
   }
   if (j >= n_pre) return;
-  const unsigned off = MODE == 2 ? my_off : p.offs[j];
+  unsigned off = MODE == 2 ? my_off : p.offs[j];
   for (int i = 0; i < n_cur; ++i) {
-    if (off + i >= p.out_cap) break;
-    rast_triangle *o = p.out + off + i;
+    if (!((kept >> i) & 1u)) continue;
+    if (off >= p.out_cap) break;
+    rast_triangle *o = p.out + off;
     const GTri &g = cur[i];
     o->v0[0] = g.v[0].x; o->v0[1] = g.v[0].y; o->v0[2] = g.v[0].z; o->v0[3] = g.v[0].w;
     o->v1[0] = g.v[1].x; o->v1[1] = g.v[1].y; o->v1[2] = g.v[1].z; o->v1[3] = g.v[1].w;
@@ -170,6 +208,8 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
     for (int k = 0; k < 3; ++k) o->color[k] = attr[4 + k];
     o->texture = __float_as_int(attr[7]);
     o->index = __float_as_int(attr[8]);
+    if (MODE == 2 && p.orig) p.orig[off] = (int)(my_all + i);
+    ++off;
   }
 }
 
@@ -318,6 +358,13 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
     p.out = (rast_triangle *)ctx->rast_src.p;
     p.out_cap = (unsigned)cap;
     CU_CHECK(ctx, cudaMemsetAsync(p.ticket, 0, 16 + sizeof(unsigned long long) * (size_t)n_blocks, ctx->stream));
+    ctx->rast_culled = 0;
+    if (ctx->rast_cull_on) {
+      if (int rc = ensure(ctx, ctx->rast_orig, sizeof(int) * (size_t)cap)) return rc;
+      p.cull = 1; p.cull0 = ctx->rast_cull0; p.cull1 = ctx->rast_cull1;
+      p.orig = (int *)ctx->rast_orig.p;
+      ctx->rast_culled = 1;
+    }
     if (ctx->rast_clear_ptr && ((size_t)ctx->rast_clear_ptr & 15) == 0 && (ctx->rast_clear_bytes & 15) == 0) {
       p.clear = (uint4 *)ctx->rast_clear_ptr;
       p.clear_n = ctx->rast_clear_bytes / 16;
@@ -331,6 +378,7 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
     return B200_OK;
   }
   unsigned total = 0;
+  ctx->rast_culled = 0;
   if (n_pre > 0) {
     rast_geom_kernel<0><<<(n_pre + 127) / 128, 128, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;

@@ -80,6 +80,7 @@ struct RastParams {
   float4 *srowsB;    // fast path, small triangles: row records at triangle * S2_ROWS + y mod S2_ROWS
   int *srowsL;
   int2 *trimeta;     // fast path: per triangle, index of its first stored row and that row's y
+  const int *orig;   // band-culled list: index of every triangle in the complete list (null: the list is complete)
   int *big_list;     // fast path: triangles too large for rast_scatter2_kernel's shared-memory row table
   unsigned big_cap;
   int *chunk_owner;  // triangle (fast path: big-list position) owning each RAST_CHUNK-row chunk
@@ -871,6 +872,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     p.keys = (unsigned long long *)ctx->rast_keys.p;
     if (int rc = ensure(ctx, ctx->rast_trimeta, sizeof(int2) * (size_t)(n ? n : 1))) return rc;
     p.trimeta = (int2 *)ctx->rast_trimeta.p;
+    p.orig = ctx->rast_culled ? (const int *)ctx->rast_orig.p : nullptr;
     // small triangles: S2_ROWS record places each, addressed by the key (only the rows drawn are touched)
     if (int rc = ensure(ctx, ctx->rast_srowsB, sizeof(float4) * S2_ROWS * (size_t)(n ? n : 1))) return rc;
     if (int rc = ensure(ctx, ctx->rast_srowsL, sizeof(int) * S2_ROWS * (size_t)(n ? n : 1))) return rc;

