@@ -12,12 +12,16 @@ default the same line carries, as nested objects with the same keys,
     "rt_tess100k"  BASELINE config 5: Mrays/s of the 100 800-triangle Cornell box at 3840x2160
 
 A "step" is one frame.  `value` times the device-resident path (scene already in HBM)
-with CUDA events on the launching stream; `e2e` times the host-pointer C-ABI call (H2D
-of the scene from pinned memory, render, D2H of the packed framebuffer into pinned
-memory).  N > 1: one process per GPU (torchrun); every rank stores its share of the frame
-straight into rank 0's frame over NVLink (or, --gather nccl, an NCCL gather) inside the
-timed region; afterwards rank 0 renders the whole frame alone and bit-compares it with
-the assembled one ("parity").
+with CUDA events on the launching stream: every rank writes the float planes of its rows
+(RGB + depth) locally and the packed 0x80RRGGBB pixels -- what Draw(screen*) leaves in
+screen->buffer -- into the frame assembled on rank 0.  N > 1: one process per GPU
+(torchrun); the packed rows are stored straight into rank 0's frame over NVLink by the
+render kernels' epilogue (or, --gather nccl, an NCCL gather) inside the timed region;
+afterwards rank 0 renders the whole frame alone and bit-compares it with the assembled one
+("parity").  `e2e` times the host-pointer C-ABI call (H2D of the scene from pinned memory,
+render, D2H of the packed framebuffer into pinned memory): at N = 1 draw_*_band on the
+rank's context, at N > 1 ONE caller (rank 0) with a multi-GPU context (b200_init_multi),
+which is what a user of the reference's Draw(screen*) would hold.
 
 `cpu_baseline` (N = 1) runs the unmodified reference (oracle/_ref) on one core over a
 bounded sample of the same frame and bit-compares what it rendered with the GPU's pixels.
@@ -399,44 +403,48 @@ def run_b200_one(args, workload):
     #   "nccl"       each rank renders into a local band, then an NCCL gather to rank 0.
     # The device entry points address outputs as full frames (pixel (x, y) at y*W + x).
     gather, gather_note, symm_handles = "none", None, []
-    band_rgb = band_depth = full_rgb = full_depth = frame_rgb = frame_depth = None
+    # Every rank writes the float planes of its own rows (RGB + depth, 16 B per pixel: the
+    # algorithmic output of SURVEY 8(d)) into LOCAL memory, and the packed 0x80RRGGBB pixels --
+    # what Draw(screen*) leaves in screen->buffer -- into the frame that is assembled on rank 0.
+    interleaved_rt = world > 1 and kind == "rt" and args.gather == "p2p"
+    if interleaved_rt:          # blocks spread over the whole frame: full-size local planes
+        loc_rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+        loc_depth = torch.empty((H, W), dtype=torch.float32, device="cuda")
+        p_rgb, p_depth = loc_rgb.data_ptr(), loc_depth.data_ptr()
+    else:
+        loc_rgb = torch.empty((rows, W, 3), dtype=torch.float32, device="cuda")
+        loc_depth = torch.empty((rows, W), dtype=torch.float32, device="cuda")
+        p_rgb = loc_rgb.data_ptr() - row0 * W * 12       # frame origin above the band
+        p_depth = loc_depth.data_ptr() - row0 * W * 4
+    band_argb = full_argb = frame_argb = None
     if world > 1 and args.gather == "p2p":
         try:
             import torch.distributed._symmetric_memory as symm
-            frame_rgb = symm.empty((H, W, 3), dtype=torch.float32, device="cuda")
-            frame_depth = symm.empty((H, W), dtype=torch.float32, device="cuda")
-            h_rgb = symm.rendezvous(frame_rgb, dist.group.WORLD)
-            h_depth = symm.rendezvous(frame_depth, dist.group.WORLD)
-            p_rgb, p_depth = int(h_rgb.buffer_ptrs[0]), int(h_depth.buffer_ptrs[0])
-            symm_handles = [h_rgb, h_depth, frame_rgb, frame_depth]
+            frame_argb = symm.empty((H, W), dtype=torch.int32, device="cuda")
+            h_argb = symm.rendezvous(frame_argb, dist.group.WORLD)
+            p_argb = int(h_argb.buffer_ptrs[0])
+            symm_handles = [h_argb, frame_argb]
             gather = "p2p_store"
         except Exception as e:                      # both branches are GPU paths; say which one ran
             gather_note = f"symmetric memory unavailable ({type(e).__name__}: {e}); NCCL gather used"
     if gather != "p2p_store":
-        band_rgb = torch.empty((rows, W, 3), dtype=torch.float32, device="cuda")
-        band_depth = torch.empty((rows, W), dtype=torch.float32, device="cuda")
-        p_rgb = band_rgb.data_ptr() - row0 * W * 12     # frame origin above the band
-        p_depth = band_depth.data_ptr() - row0 * W * 4
+        interleaved_rt = False
+        band_argb = torch.empty((rows, W), dtype=torch.int32, device="cuda")
+        p_argb = band_argb.data_ptr() - row0 * W * 4
         if world > 1:
             gather = "nccl_gather"
             if rank == 0:
-                full_rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
-                full_depth = torch.empty((H, W), dtype=torch.float32, device="cuda")
+                full_argb = torch.empty((H, W), dtype=torch.int32, device="cuda")
 
     def exchange():
         if gather == "p2p_store":
             symm_handles[0].barrier(channel=0)      # every rank's rows have landed in rank 0's frame
         elif gather == "nccl_gather":
-            dist.gather(band_rgb, list(full_rgb.view(world, rows, W, 3).unbind(0)) if rank == 0 else None, dst=0)
-            dist.gather(band_depth, list(full_depth.view(world, rows, W).unbind(0)) if rank == 0 else None, dst=0)
+            dist.gather(band_argb, list(full_argb.view(world, rows, W).unbind(0)) if rank == 0 else None, dst=0)
 
     def assembled():
-        """rank 0: the frame the exchange left behind."""
-        if gather == "p2p_store":
-            return frame_rgb, frame_depth
-        if gather == "nccl_gather":
-            return full_rgb, full_depth
-        return band_rgb, band_depth
+        """rank 0: the packed frame the exchange left behind."""
+        return frame_argb if gather == "p2p_store" else (full_argb if gather == "nccl_gather" else band_argb)
 
     result = {}
     pinned = torch.empty(rows * W, dtype=torch.int32).pin_memory()
@@ -448,21 +456,21 @@ def run_b200_one(args, workload):
 
         # N > 1 with the peer-mapped frame: the ranks share the frame by interleaved 16-row blocks
         # (better balanced than contiguous bands); each stores its blocks straight into rank 0's frame
-        interleaved = world > 1 and gather == "p2p_store"
+        interleaved = interleaved_rt and gather == "p2p_store"
         if interleaved:
             r.set_option(b200.OPT_RT_INTERLEAVE_N, world)
             r.set_option(b200.OPT_RT_INTERLEAVE_R, rank)
 
         def step():
             if interleaved:
-                r.rt_render_device(cam, RT_LIGHTS, 0, H, p_rgb, p_depth)
+                r.rt_render_device(cam, RT_LIGHTS, 0, H, p_rgb, p_depth, None, p_argb)
             else:
-                r.rt_render_device(cam, RT_LIGHTS, row0, row1, p_rgb, p_depth)
+                r.rt_render_device(cam, RT_LIGHTS, row0, row1, p_rgb, p_depth, None, p_argb)
             exchange()
 
-        def render_alone(d_rgb, d_depth):
+        def render_alone(d_argb):
             r.set_option(b200.OPT_RT_INTERLEAVE_N, 1)
-            r.rt_render_device(cam, RT_LIGHTS, 0, H, d_rgb, d_depth)
+            r.rt_render_device(cam, RT_LIGHTS, 0, H, None, None, None, d_argb)
             r.synchronize()
 
         tris_pin = torch.from_numpy(tris.view(np.uint8).copy()).pin_memory()
@@ -484,15 +492,22 @@ def run_b200_one(args, workload):
         # verification (b200_synchronize) is part of the step, so a frame that had to be
         # rendered twice would be timed twice
         r.set_option(b200.OPT_RAST_PIPELINED, 0 if args.rast_sync else 1)
+        r.set_option(b200.OPT_RAST_BAND_CULL, 1)     # N > 1: every rank's geometry stage keeps its band's triangles only
         respec0 = r.stats()["respeculated"]
 
-        def step():
-            r.rast_draw_device(cam, L, row0, row1, p_rgb, p_depth)
-            r.synchronize()
-            exchange()
+        respec_seen = [respec0]
 
-        def render_alone(d_rgb, d_depth):
-            r.rast_draw_device(cam, L, 0, H, d_rgb, d_depth)
+        def step():
+            r.rast_draw_device(cam, L, row0, row1, p_rgb, p_depth, None, p_argb)
+            exchange()                           # enqueued behind the frame: no host round trip in between
+            r.synchronize()                      # verifies the pipelined frame (renders it again if it outgrew its sizes)
+            now = r.stats()["respeculated"]
+            if world > 1 and now != respec_seen[0]:
+                respec_seen[0] = now
+                exchange()                       # ... in which case the rows were stored again
+
+        def render_alone(d_argb):
+            r.rast_draw_device(cam, L, 0, H, None, None, None, d_argb)
             r.synchronize()
 
         room_pin = torch.from_numpy(room.view(np.uint8).copy()).pin_memory()
@@ -517,6 +532,8 @@ def run_b200_one(args, workload):
         wall0 = time.perf_counter()
         for _ in range(steps):
             flush.fill_(1)                       # L2 flush between timed iterations (not timed)
+            if world > 1:
+                dist.barrier()                   # the ranks enter the step together (not timed): no host skew in the exchange
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             fn()
@@ -547,27 +564,61 @@ def run_b200_one(args, workload):
 
     # ---- N > 1: the assembled frame against rank 0 rendering the whole frame alone ----------
     parity = None
+    own_argb = None
     if world > 1:
         step()                                   # one more exchange whose result is inspected
         barrier()
         if rank == 0:
-            a_rgb, a_depth = assembled()
-            own_rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
-            own_depth = torch.empty((H, W), dtype=torch.float32, device="cuda")
-            render_alone(own_rgb.data_ptr(), own_depth.data_ptr())
+            a_argb = assembled()
+            own_argb = torch.empty((H, W), dtype=torch.int32, device="cuda")
+            render_alone(own_argb.data_ptr())
             torch.cuda.synchronize()
-            bad_rgb = int((a_rgb.view(torch.int32) != own_rgb.view(torch.int32)).any(dim=-1).sum().item())
-            bad_depth = int((a_depth.view(torch.int32) != own_depth.view(torch.int32)).sum().item())
-            parity = {"assembled_frame_vs_single_gpu": "bit-exact" if bad_rgb + bad_depth == 0 else "MISMATCH",
-                      "pixels_checked": W * H, "rgb_mismatches": bad_rgb, "depth_mismatches": bad_depth,
+            bad = int((a_argb != own_argb).sum().item())
+            parity = {"assembled_frame_vs_single_gpu": "bit-exact" if bad == 0 else "MISMATCH",
+                      "pixels_checked": W * H, "argb_mismatches": bad,
                       "mode": ("interleaved 16-row blocks, " if interleaved else "row bands, ") + gather}
-            del own_rgb, own_depth
         barrier()
         if interleaved:
             r.set_option(b200.OPT_RT_INTERLEAVE_N, world)
             r.set_option(b200.OPT_RT_INTERLEAVE_R, rank)
 
-    ms_e2e, _, _, _, _ = timed(step_e2e, max(2, args.steps // 2), 3)
+    # ---- end to end: the call a user of the reference makes, host buffers in and out ---------
+    # N = 1: draw_*_band on this context.  N > 1: ONE caller -- rank 0 -- with a multi-GPU context
+    # (b200_init_multi: the library shares the frame among the N devices and returns when the
+    # assembled frame is in the caller's pinned buffer); the other ranks wait on the host.
+    e2e_note = None
+    if world == 1:
+        ms_e2e, _, _, _, _ = timed(step_e2e, max(2, args.steps // 2), 3)
+    else:
+        host_group = dist.new_group(backend="gloo")
+        ms_e2e = float("inf")                    # only rank 0 measures (and prints) it
+        dist.barrier(group=host_group)
+        if rank == 0:
+            m = b200.Renderer(n_gpus=world)
+            whole = torch.empty(H * W, dtype=torch.int32).pin_memory()
+
+            def whole_frame():
+                if kind == "rt":
+                    m.draw_raytrace_band(tris_h, sph_h, cam, RT_LIGHTS, 0, H, whole.data_ptr())
+                else:
+                    m.draw_raster_band(room_h, boxes_h, cam, L, 0, H, whole.data_ptr())
+
+            for _ in range(4):                   # warm-up: buffers, pipelined sizes, adaptive bands
+                whole_frame()
+            k = max(2, args.steps // 2)
+            t0 = time.perf_counter()
+            for _ in range(k):
+                whole_frame()
+            ms_e2e = (time.perf_counter() - t0) * 1e3 / k
+            bad = int((whole.view(H, W).cuda() != own_argb).sum().item())
+            parity["library_multi_frame_vs_single_gpu"] = "bit-exact" if bad == 0 else "MISMATCH"
+            parity["library_multi_mismatches"] = bad
+            m.close()
+            e2e_note = (f"one caller (rank 0), b200_init_multi({world}): host wall clock of {k} blocking whole-frame calls; "
+                        "the other ranks idle on a host barrier")
+        dist.barrier(group=host_group)
+        del own_argb
+
 
     config = workload_config(workload, world)
     detail = {"gather": gather, "gather_note": gather_note,
@@ -632,9 +683,10 @@ def run_b200_one(args, workload):
                   "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                   "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "detail": detail,
                   "clocks": clocks,
-                  "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d) * world,
-                          "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": ms_e2e,
-                          "call": "draw_raytrace_band" if kind == "rt" else "draw_raster_band"},
+                  "e2e": {"value": e2e_value, "unit": unit,
+                          "h2d_bytes_per_step": int(h2d) * (world if kind == "rt" else 1),   # RT: scene to every device; RAST: one slice each
+                          "d2h_bytes_per_step": H * W * 4, "ms_per_step": ms_e2e,
+                          "call": "draw_raytrace_band" if kind == "rt" else "draw_raster_band", "note": e2e_note},
                   "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
     r.set_stream(None)
     r.close()

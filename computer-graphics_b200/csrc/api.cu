@@ -17,12 +17,16 @@ int ctx_fail(b200_ctx *ctx, int code, const char *what, cudaError_t e) {
 
 int ensure(b200_ctx *ctx, DevBuf &b, size_t bytes) {
   if (bytes <= b.cap && b.p) return B200_OK;
+  size_t cap = bytes < 256 ? 256 : bytes;
   if (b.p) {
+    // a buffer that has to grow grows by a quarter more than asked: frame-sized buffers (cell lists,
+    // row tables, bands whose edges move) would otherwise be freed and allocated again -- ~1.5 ms
+    // with its implicit synchronisation -- every time a frame needs a little more than the last
+    cap += cap / 4;
     cudaStreamSynchronize(ctx->stream);
     cudaFree(b.p);
     b.p = nullptr; b.cap = 0;
   }
-  size_t cap = bytes < 256 ? 256 : bytes;
   cudaError_t e = cudaMalloc(&b.p, cap);
   if (e != cudaSuccess) { b.p = nullptr; return ctx_fail(ctx, B200_ENOMEM, "cudaMalloc", e); }
   b.cap = cap;
@@ -73,7 +77,7 @@ int b200_init(int device, b200_ctx **out) {
   for (int i = 0; i < B200_SLICES; ++i)
     if (cudaEventCreateWithFlags(&ctx->ev_slice[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return B200_ECUDA; }
   ctx->stream = ctx->own_stream;
-  if (ensure(ctx, ctx->counters, 32 * sizeof(unsigned long long)) != B200_OK || ensure_pinned(ctx, 512) != B200_OK) {
+  if (ensure(ctx, ctx->counters, 32 * sizeof(unsigned long long)) != B200_OK || ensure_pinned(ctx, 1024) != B200_OK) {
     delete ctx;
     return B200_ENOMEM;
   }
@@ -90,7 +94,7 @@ void b200_destroy(b200_ctx *ctx) {
   if (ctx->multi) { multi_destroy(ctx); delete ctx; return; }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rt_dtcam, &ctx->rt_cells, &ctx->rt_cell_rec, &ctx->rt_cell_idx, &ctx->rast_src,
+  DevBuf *bufs[] = {&ctx->rt_src, &ctx->rt_geom, &ctx->rt_spheres, &ctx->rt_planes, &ctx->rt_dtcam, &ctx->rt_bounds, &ctx->rt_cells, &ctx->rt_cell_rec, &ctx->rt_cell_idx, &ctx->rast_src,
                     &ctx->rast_setup, &ctx->rast_rowsA, &ctx->rast_rowsB, &ctx->rast_bins, &ctx->rast_tile_count, &ctx->rast_tile_bits,
                     &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_trimeta, &ctx->rast_big, &ctx->rast_orig, &ctx->rast_srowsB, &ctx->rast_srowsL, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
                     &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
@@ -206,15 +210,18 @@ int rt_upload_scene(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt
                                                cudaMemcpyHostToDevice, ctx->stream));
   ctx->rt_n_tris = n_tris;
   ctx->rt_n_spheres = n_spheres;
-  // bound of |coordinate| over the scene, for the shadow filter's error budget
+  // bound of |coordinate| over the scene, for the shadow filter's error budget: small scenes on the
+  // host (no synchronisation), large ones inside the preparation kernel (one 8-byte read-back)
   float m = 0.f, nm = 1.f;
-  for (int i = 0; i < n_tris; ++i)
-    for (int k = 0; k < 3; ++k) {
-      nm = fabsf(tris[i].normal[k]) <= 1e30f ? fmaxf(nm, fabsf(tris[i].normal[k])) : 1e30f;   // NaN / inf: widest margins
-      m = fmaxf(m, fabsf(tris[i].v0[k]));
-      m = fmaxf(m, fabsf(tris[i].v1[k]));
-      m = fmaxf(m, fabsf(tris[i].v2[k]));
-    }
+  ctx->rt_bounds_on_device = n_tris > 4096;
+  if (!ctx->rt_bounds_on_device)
+    for (int i = 0; i < n_tris; ++i)
+      for (int k = 0; k < 3; ++k) {
+        nm = fabsf(tris[i].normal[k]) <= 1e30f ? fmaxf(nm, fabsf(tris[i].normal[k])) : 1e30f;   // NaN / inf: widest margins
+        m = fmaxf(m, fabsf(tris[i].v0[k]));
+        m = fmaxf(m, fabsf(tris[i].v1[k]));
+        m = fmaxf(m, fabsf(tris[i].v2[k]));
+      }
   for (int i = 0; i < n_spheres; ++i)
     for (int k = 0; k < 3; ++k) m = fmaxf(m, fabsf(spheres[i].centre[k]) + fabsf(spheres[i].radius));
   ctx->rt_world_abs = m;

@@ -98,6 +98,8 @@ struct b200_ctx {
   DevBuf rt_spheres;  // rt_sphere[n]
   DevBuf rt_planes;   // float4[..]: per-origin edge-function planes for the filter
   DevBuf rt_dtcam;    // float[n]: per-frame numerator of t for primary rays
+  DevBuf rt_bounds;   // two words: coordinate / normal bounds of a large scene, reduced on the device
+  int rt_bounds_on_device = 0;
   DevBuf rt_cells;    // direction grids: per-cell counts, cursors, padded counts, offsets, scan scratch
   DevBuf rt_cell_rec, rt_cell_idx;   // the cells' lists: plane records and triangle indices
   size_t rt_n_cells = 0, rt_n_cam_cells = 0;   // of the last gridded frame (diagnostics)

@@ -130,6 +130,11 @@ void multi_band_edges(const std::vector<int> &prev_edges, const std::vector<floa
   if (!usable) {
     for (int i = 1; i < n; ++i) out[i] = (int)((long long)H * i / n);
   } else {
+    // Hysteresis: a split within 6 % of balance stays as it is (a rasteriser band whose shape
+    // changes cannot be pipelined from its predecessor, and timing noise must not move edges).
+    float worst = 0.f;
+    for (int i = 0; i < n; ++i) worst = prev_cost[i] > worst ? prev_cost[i] : worst;
+    if (worst * n <= 1.06 * total) { out = prev_edges; return; }
     int band = 0;
     double before = 0;   // cost of the bands in front of `band`
     for (int k = 1; k < n; ++k) {
@@ -137,7 +142,9 @@ void multi_band_edges(const std::vector<int> &prev_edges, const std::vector<floa
       while (band < n - 1 && before + prev_cost[band] < want) before += prev_cost[band++];
       const double rows = prev_edges[band + 1] - prev_edges[band];
       const double y = prev_edges[band] + (want - before) / prev_cost[band] * rows;
-      out[k] = (int)(y + 0.5);
+      // damped: a frame's cost also carries what does not scale with its rows (allocations of a
+      // new band shape, per-frame grids), so the edges move 60 % of the way
+      out[k] = (int)(prev_edges[k] + 0.6 * (y - prev_edges[k]) + 0.5);
     }
   }
   for (int k = 1; k < n; ++k) {
@@ -350,5 +357,25 @@ int multi_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const ras
   if (rc != B200_OK) return rc;
   multi_note_cost(mc, 1, edges, rows);
   multi_sum_stats(ctx);
+  return B200_OK;
+}
+
+// Band edges and per-device cost (ms) of the last frame of `kind` (0 RT, 1 RAST): diagnostics.
+extern "C" int b200_debug_multi_bands(b200_ctx *ctx, int kind, int *edges_out, float *cost_out, int cap) {
+  if (!ctx || !ctx->multi || kind < 0 || kind > 1) return B200_EINVAL;
+  const b200_multi *mc = ctx->multi;
+  const int n = (int)mc->cost[kind].size();
+  for (int i = 0; i < n && i < cap; ++i) { edges_out[i] = mc->edges[kind][i + 1]; cost_out[i] = mc->cost[kind][i]; }
+  return n;
+}
+
+// The band-split rule itself, callable without a device (host logic; CPU tests).
+extern "C" int b200_debug_band_edges(const int *prev_edges, const float *prev_cost, int n_prev, int H, int n, int align, int *out) {
+  if (!out || n <= 0 || H < 0) return B200_EINVAL;
+  std::vector<int> pe, o;
+  std::vector<float> pc;
+  if (prev_edges && prev_cost && n_prev == n) { pe.assign(prev_edges, prev_edges + n + 1); pc.assign(prev_cost, prev_cost + n); }
+  multi_band_edges(pe, pc, H, n, align, o);
+  for (int i = 0; i <= n; ++i) out[i] = o[i];
   return B200_OK;
 }

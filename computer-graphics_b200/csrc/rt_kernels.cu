@@ -14,22 +14,47 @@
 // ------------------------------------------------------------------------------
 // scene preparation: v0 / e1 / e2 per triangle (skeleton.cpp:283-284)
 // ------------------------------------------------------------------------------
-__global__ void rt_prep_geom_kernel(const rt_triangle *__restrict__ src, int n, float4 *__restrict__ geom) {
+// bounds (optional): [0] max |vertex coordinate|, [1] max |normal component| capped at 1e30 (NaN / inf
+// count as 1e30), as bit patterns of non-negative floats -- what rt_upload_scene's host loop computes
+// for small scenes, here for large ones (100 800 triangles took 2.8 ms on the host per upload).
+__global__ void rt_prep_geom_kernel(const rt_triangle *__restrict__ src, int n, float4 *__restrict__ geom,
+                                    unsigned *__restrict__ bounds) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const rt_triangle t = src[i];
-  float4 g0, g1, g2;
-  g0.x = t.v0[0]; g0.y = t.v0[1]; g0.z = t.v0[2];
-  g0.w = xsub(t.v1[0], t.v0[0]);
-  g1.x = xsub(t.v1[1], t.v0[1]);
-  g1.y = xsub(t.v1[2], t.v0[2]);
-  g1.z = xsub(t.v2[0], t.v0[0]);
-  g1.w = xsub(t.v2[1], t.v0[1]);
-  g2.x = xsub(t.v2[2], t.v0[2]);
-  g2.y = g2.z = g2.w = 0.f;
-  geom[3 * i + 0] = g0;
-  geom[3 * i + 1] = g1;
-  geom[3 * i + 2] = g2;
+  float m = 0.f, nm = 0.f;
+  if (i < n) {
+    const rt_triangle t = src[i];
+    float4 g0, g1, g2;
+    g0.x = t.v0[0]; g0.y = t.v0[1]; g0.z = t.v0[2];
+    g0.w = xsub(t.v1[0], t.v0[0]);
+    g1.x = xsub(t.v1[1], t.v0[1]);
+    g1.y = xsub(t.v1[2], t.v0[2]);
+    g1.z = xsub(t.v2[0], t.v0[0]);
+    g1.w = xsub(t.v2[1], t.v0[1]);
+    g2.x = xsub(t.v2[2], t.v0[2]);
+    g2.y = g2.z = g2.w = 0.f;
+    geom[3 * i + 0] = g0;
+    geom[3 * i + 1] = g1;
+    geom[3 * i + 2] = g2;
+    if (bounds) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        m = fmaxf(m, fmaxf(fabsf(t.v0[k]), fmaxf(fabsf(t.v1[k]), fabsf(t.v2[k]))));   // fmaxf drops NaN, like the host's
+        const float a = fabsf(t.normal[k]);
+        nm = fmaxf(nm, a <= 1e30f ? a : 1e30f);
+      }
+    }
+  }
+  if (bounds) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      nm = fmaxf(nm, __shfl_xor_sync(0xffffffffu, nm, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(bounds, __float_as_uint(m));
+      atomicMax(bounds + 1, __float_as_uint(nm));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------
@@ -112,10 +137,23 @@ int rt_prepare_scene(b200_ctx *ctx) {
   const int n = ctx->rt_n_tris;
   if (int rc = ensure(ctx, ctx->rt_geom, sizeof(float4) * 3 * (size_t)(n > 0 ? n : 1))) return rc;
   if (n > 0) {
+    unsigned *bounds = nullptr;
+    if (ctx->rt_bounds_on_device) {
+      if (int rc = ensure(ctx, ctx->rt_bounds, 2 * sizeof(unsigned))) return rc;
+      bounds = (unsigned *)ctx->rt_bounds.p;
+      CU_CHECK(ctx, cudaMemsetAsync(bounds, 0, 2 * sizeof(unsigned), ctx->stream));
+    }
     rt_prep_geom_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const rt_triangle *)ctx->rt_src.p, n,
-                                                                  (float4 *)ctx->rt_geom.p);
+                                                                  (float4 *)ctx->rt_geom.p, bounds);
     ctx->stats.kernel_launches++;
     CU_CHECK(ctx, cudaGetLastError());
+    if (bounds) {
+      float *hb = (float *)((char *)ctx->pinned + 512);   // past both counter blocks of the pinned scratch
+      CU_CHECK(ctx, cudaMemcpyAsync(hb, bounds, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->rt_world_abs = fmaxf(ctx->rt_world_abs, hb[0]);
+      ctx->rt_normal_abs = fmaxf(ctx->rt_normal_abs, hb[1]);
+    }
   }
   return B200_OK;
 }

@@ -222,3 +222,35 @@ def test_bench_window_trick_is_exact():
     win = h.oracle_rt_render(w, hh, f, h.f32(0, 0, -3, 1), bench.window_R(W, H, x0, y0, w, hh), L, tris, sph)
     assert np.array_equal(win["rgb"].view(np.uint32), full["rgb"][y0:y0 + hh, x0:x0 + w].view(np.uint32))
     assert np.array_equal(win["index"], full["index"][y0:y0 + hh, x0:x0 + w])
+
+
+def test_multi_gpu_band_split_rule(b200):
+    """Host logic of b200_init_multi's adaptive row bands (csrc/multi.cu): equal rows first, then
+    towards the edges that would have balanced the previous frame's measured cost -- damped,
+    aligned, monotone, and left alone once the split is within 6 % of balance."""
+    import ctypes
+    lib = b200.load_library()
+
+    def edges(prev_e, prev_c, H, n, align):
+        out = (ctypes.c_int * (n + 1))()
+        pe = (ctypes.c_int * (n + 1))(*prev_e) if prev_e else None
+        pc = (ctypes.c_float * n)(*prev_c) if prev_c else None
+        assert lib.b200_debug_band_edges(pe, pc, n if prev_e else 0, H, n, align, out) == 0
+        return list(out)
+
+    for n in (1, 2, 3, 4, 8):
+        e = edges(None, None, 2160, n, 16)
+        assert e[0] == 0 and e[-1] == 2160 and all(b >= a for a, b in zip(e, e[1:]))
+        assert all(x % 16 == 0 for x in e[1:-1])
+        assert max(b - a for a, b in zip(e, e[1:])) - min(b - a for a, b in zip(e, e[1:])) <= 32
+    # a frame three times as expensive per row in its lower half: the edge moves up, and converges
+    e = edges(None, None, 2160, 2, 16)
+    for _ in range(12):
+        cost = [sum((1.0 if y < 1080 else 3.0) for y in range(a, b)) for a, b in zip(e, e[1:])]
+        e = edges(e, cost, 2160, 2, 16)
+    cost = [sum((1.0 if y < 1080 else 3.0) for y in range(a, b)) for a, b in zip(e, e[1:])]
+    assert e[1] > 1080 and max(cost) / (sum(cost) / 2) < 1.07, (e, cost)
+    # balanced within the hysteresis: untouched
+    assert edges([0, 1000, 2160], [1.00, 1.03], 2160, 2, 8) == [0, 1000, 2160]
+    # unusable history (other frame height): equal split
+    assert edges([0, 500, 1000], [1.0, 2.0], 2160, 2, 8)[1] == 1080
