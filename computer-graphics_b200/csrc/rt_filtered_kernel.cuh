@@ -316,6 +316,10 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
 #else
 #define RT_PC(i)
 #endif
+#ifdef RT_PROFILE_CLOCK   // diagnostic build: where the long-running warps are and why (profiles/rt_block_cycles.py)
+  const long long prof_t0 = clock64();
+  unsigned prof_recs = 0, prof_cells = 0, prof_l1 = 0, prof_l2 = 0, prof_ex0 = 0;
+#endif
 
   // ============================ primary rays ============================
   {
@@ -456,6 +460,9 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
     if (p.index) p.index[pid] = hit4 ? HI(4) : INT32_MIN;
   }
 
+#ifdef RT_PROFILE_CLOCK
+  prof_ex0 = n_exact;
+#endif
   // ============================ shadow rays ============================
   constexpr int NL = MULTI ? B200_MAX_LIGHTS : 1;
   float dl[MULTI ? NL * 27 : 1];
@@ -588,6 +595,9 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
       if (s_ncells <= RT_GRID_MAX_CELLS) cursor = rt_cursor_cells(s_cells, s_ncells);
       else if (!warp_active) cursor = rt_cursor_cells(s_cells, 0);
       dedupe = s_ncells > 1 && s_ncells <= RT_GRID_MAX_CELLS;
+#ifdef RT_PROFILE_CLOCK
+      prof_cells += (unsigned)s_ncells;
+#endif
 #ifdef RT_PROFILE_COUNTERS
       if (lane == 0) {
         if (s_ncells > RT_GRID_MAX_CELLS) atomicAdd(p.counters + 10, 1ull);
@@ -614,6 +624,9 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
       const int cnt = warp_active ? item.cnt : 0;
 #ifdef RT_PROFILE_COUNTERS
       if (issuer) atomicAdd(p.counters + 13, (unsigned long long)item.cnt);
+#endif
+#ifdef RT_PROFILE_CLOCK
+      prof_recs += (unsigned)cnt;
 #endif
       item = next_item;
       have = have_next;
@@ -664,7 +677,13 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
           const float mN = (cu + cv + cw) + (hu + hv + hw);
           if (active) RT_PC(3);
           if ((active & ~occluded) && !((m3 < -Eg) || (mN + Eg < q2.z))) mine |= 1u << j;
+#ifdef RT_PROFILE_CLOCK
+          ++prof_l1;
+#endif
         }
+#ifdef RT_PROFILE_CLOCK
+        prof_l2 += (unsigned)__popc(mine);
+#endif
         // ---- L2 / EX: each lane walks its own candidates ----
         while (mine) {
           const int j = __ffs(mine) - 1;
@@ -749,6 +768,13 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
   // diagnostic build only: the depth plane carries this pixel's shadow L1 test count, the index plane its exact evaluations
   if (live && p.depth) p.depth[pid] = (float)prof_cnt[3];
   if (live && p.index) p.index[pid] = (int)n_exact;
+#endif
+#ifdef RT_PROFILE_CLOCK
+  // depth plane: cycles of this warp; index plane: records its shadow phases streamed (low 20 bits), cells walked (high bits);
+  // rgb plane: shadow-phase L0 survivors this lane tested, candidates it kept, exact evaluations
+  if (live && p.depth) p.depth[pid] = (float)(clock64() - prof_t0);
+  if (live && p.index) p.index[pid] = (int)(min(prof_recs, 0xfffffu) | (min(prof_cells, 2047u) << 20));
+  if (live && p.rgb) { p.rgb[3 * pid] = (float)prof_l1; p.rgb[3 * pid + 1] = (float)prof_l2; p.rgb[3 * pid + 2] = (float)(n_exact - prof_ex0); }
 #endif
 }
 
