@@ -10,6 +10,7 @@ metric Mrays/s = (primary + shadow rays) / s, whole job.  With --workload left a
 default the same line carries, as nested objects with the same keys,
     "raster"       BASELINE config 4: frames/s of the 1M-triangle soup at 3840x2160
     "rt_tess100k"  BASELINE config 5: Mrays/s of the 100 800-triangle Cornell box at 3840x2160
+    "rt_cornell_default" / "rast_cornell_default"   BASELINE configs 1 and 2 (320x256 / 900x720), N = 1 only
 
 A "step" is one frame.  `value` times the device-resident path (scene already in HBM)
 with CUDA events on the launching stream: every rank writes the float planes of its rows
@@ -60,7 +61,10 @@ WORKLOADS = {
     "rast_cornell_default": ("rast", 900, 720, 512.0),
 }
 DEFAULT_WORKLOADS = ["rt_cornell_4k", "rast_soup_4k", "rt_tess100k_4k"]
-NESTED_KEY = {"rast_soup_4k": "raster", "rt_tess100k_4k": "rt_tess100k"}
+# BASELINE configs 1 and 2 (the reference's own resolutions): single-GPU frames, carried at N = 1 only
+DEFAULT_WORKLOADS_1GPU = ["rt_cornell_default", "rast_cornell_default"]
+NESTED_KEY = {"rast_soup_4k": "raster", "rt_tess100k_4k": "rt_tess100k", "rt_cornell_default": "rt_cornell_default",
+              "rast_cornell_default": "rast_cornell_default"}
 RT_CAM = (0.0, 0.0, -3.0, 1.0)
 RT_LIGHTS = [((0.0, -0.5, -0.7, 1.0), (14.0, 14.0, 14.0))]
 RAST_CAM = (0.0, 0.0, -3.001, 1.0)
@@ -711,6 +715,8 @@ def main():
     # default: the headline raytracer line (BASELINE config 3) carrying the rasteriser figure
     # (config 4) and the large raytracer scene (config 5) as nested objects
     workloads = DEFAULT_WORKLOADS if args.workload == "default" else [args.workload]
+    if args.workload == "default" and args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        workloads = workloads + DEFAULT_WORKLOADS_1GPU
     if args.impl == "reference":
         lines = [run_reference(args, w) for w in workloads]
     else:

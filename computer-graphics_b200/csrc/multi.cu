@@ -183,6 +183,7 @@ int b200_init_multi(int n_gpus, b200_ctx **out) {
   if (cudaGetDeviceCount(&have) != cudaSuccess || have <= 0) return B200_ENODEV;
   if (n_gpus <= 0) n_gpus = have;
   if (n_gpus > have) return B200_EINVAL;
+  if (n_gpus == 1) return b200_init(0, out);   // one device: an ordinary context, no threads in between
   b200_ctx *ctx = new b200_ctx();
   b200_multi *mc = new b200_multi();
   ctx->multi = mc;

@@ -596,6 +596,8 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
   __shared__ int list[RAST_LIST_CAP];
   __shared__ float4 recA[RAST_BATCH][TS];
   __shared__ int recFlags[RAST_BATCH];
+  __shared__ unsigned triRows[RAST_BATCH];   // per staged triangle: the tile rows in which its span meets the tile's columns
+  __shared__ unsigned rowTris[TS];           // the transpose: per tile row, the staged triangles a pixel of that row has to look at
   __shared__ unsigned scratch[NT + 2];
 
   const int tile_x = blockIdx.x, tile_y = p.ty0 + blockIdx.y;
@@ -676,17 +678,33 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
       const RastSetup *s = p.setup + t;
       const int row0 = s->row0, nrows = s->nrows;
       if (lane == 0) recFlags[b] = s->flags;
+      bool meets = false;
       if (lane < TS) {
         const int yy = (tile_y << TS_LOG2) + lane;
         const int r = yy - row0;
         float4 A = make_float4(__int_as_float(0), __int_as_float(0), 0.f, 0.f);
         if (r >= 0 && r < nrows) A = p.rowsA[s->row_off + r];
         recA[b][lane] = A;
+        // fragments of this row are x = lx .. rx-1: any of them in the tile's columns?
+        const int lx = __float_as_int(A.x), rx = __float_as_int(A.y), tx0 = tile_x << TS_LOG2;
+        meets = rx > lx && rx > tx0 && lx < tx0 + TS;
       }
+      const unsigned m = __ballot_sync(0xffffffffu, meets);
+      if (lane == 0) triRows[b] = m;
+    }
+    __syncthreads();
+    // The lists come from bounding boxes: most (triangle, tile row) pairs of a long thin triangle --
+    // every shadow-volume side -- hold no fragment of this tile.  Transposed, each row walks only
+    // the triangles that do reach it (the fold was ~1000 instructions per pixel on the Cornell box).
+    if (threadIdx.x < TS) {
+      unsigned mask = 0;
+      for (int b = 0; b < nb; ++b) mask |= ((triRows[b] >> threadIdx.x) & 1u) << b;
+      rowTris[threadIdx.x] = mask;
     }
     __syncthreads();
     if (on_screen) {
-      for (int b = 0; b < nb; ++b) {
+      for (unsigned mine = rowTris[ly_]; mine; mine &= mine - 1) {
+        const int b = __ffs(mine) - 1;
         const float4 A = recA[b][ly_];
         const int lx = __float_as_int(A.x), rx = __float_as_int(A.y);
         // fragments x = lx .. rx-1 (right end excluded, :504); (:573) bounds hold by construction
