@@ -123,6 +123,7 @@ struct b200_ctx {
   void *rast_clear_ptr = nullptr;    // key rows the single-pass geometry kernel should clear (set per frame by rast_frame)
   size_t rast_clear_bytes = 0;
   int rast_keys_cleared = 0;         // ... and whether it did (rast_launch then skips its memset)
+  DevBuf rast_shadow8;               // ordered path, fused: shadowBuffer as one byte per pixel
   DevBuf rast_srowsB, rast_srowsL;   // fast path: row records of the small triangles
   DevBuf rast_trimeta, rast_big;   // fast path: per-triangle row-table origin; list of the triangles too big for the small-triangle kernel
   int rast_has_shadow = 0;   // the uploaded list can contain shadow-volume triangles

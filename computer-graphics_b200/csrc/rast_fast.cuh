@@ -329,7 +329,13 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
 
 constexpr int RS_W = 32, RS_H = 8, RS_HW = RS_W + 2, RS_HH = RS_H + 2, RS_N = RS_HW * RS_HH;   // 34 x 10 = 340
 constexpr int RS_HALO = 2 * RS_HW + 2 * RS_H;                                                   // 84 halo positions
+constexpr int RS_FW = RS_W + 4, RS_FH = RS_H + 4;                                               // shadow flags: 2-pixel halo
 
+// ORDERED = false: the scatter path's keys (row record named by the key).  ORDERED = true: the
+// ordered-tile path's per-pixel result (rast_fill_kernel with p.fused: depth bits << 32 | winner + 1,
+// and a shadow flag per pixel) -- the same pass then also does the shadow softening of the post pass
+// (:286-303), so that path keeps no colour buffers in HBM either.
+template <bool ORDERED>
 __global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __grid_constant__ RastParams p) {
   __shared__ float col[9][RS_N];            // [screen rgb, low rgb, high rgb][position]: conflict-free taps
   __shared__ float zinv_s[RS_N];            // the winner's zinv (:665); 0 = empty
@@ -337,12 +343,19 @@ __global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __gr
   __shared__ unsigned short work[RS_N];
   __shared__ int n_work;
   __shared__ __align__(16) float out_stage[RS_H][3 * RS_W];   // one row of RGB per warp, for 128-bit stores
+  __shared__ unsigned char flag[ORDERED ? RS_FH * RS_FW : 1];   // shadowBuffer of the tile + 2-pixel halo
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int tx = tid % RS_W, ty = tid / RS_W;                                   // a warp is one row of the tile
   const int x0 = blockIdx.x * RS_W - 1, y0 = p.row0 + blockIdx.y * RS_H - 1;   // halo origin
 
   if (tid == 0) n_work = 0;
+  if (ORDERED) {
+    for (int i = tid; i < RS_FH * RS_FW; i += RS_W * RS_H) {
+      const int gx = x0 - 1 + i % RS_FW, gy = y0 - 1 + i / RS_FW;
+      flag[i] = (gx >= 0 && gx < p.W && gy >= p.fb0 && gy < p.fb1) ? p.shadow8[(size_t)gy * p.W + gx] : (unsigned char)0;
+    }
+  }
   __syncthreads();
 
   // ---- the winners of the tile (every thread its own pixel) and of the 1-pixel halo (the first 84
@@ -352,9 +365,9 @@ __global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __gr
     const int gx = x0 + hx, gy = y0 + hy;
     unsigned long long key = 0;
     if (active && gx >= 0 && gx < p.W && gy >= p.fb0 && gy < p.fb1) key = __ldcs(p.keys + (size_t)gy * p.W + gx);   // read once
-    const bool covered = key != 0;
+    const bool covered = (ORDERED ? (unsigned)(key & 0xffffffffull) : (unsigned)(key != 0)) != 0;
     if (active) {
-      owner[pos] = (int)(unsigned)(key & 0xffffffffull) - 1;             // triangle << 5 | code, or -1
+      owner[pos] = (int)(unsigned)(key & 0xffffffffull) - 1;             // scatter: triangle << 5 | code; ordered: triangle; or -1
       zinv_s[pos] = __uint_as_float((unsigned)(key >> 32));
       if (!covered) {
 #pragma unroll
@@ -386,22 +399,31 @@ __global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __gr
   for (int k = tid; k < nw; k += RS_W * RS_H) {
     const int pos = work[k];
     const int gx = x0 + pos % RS_HW, gy = y0 + pos / RS_HW;
-    const unsigned low = (unsigned)owner[pos], code = low & 31u;
-    const int t = (int)(low >> 5);
+    int t;
     float4 B;
     int lx;
-    if (code < (unsigned)S2_ROWS) {                                 // small triangle: the record's place is in the key
-      const size_t rr = (size_t)t * S2_ROWS + code;
-      B = __ldg(p.srowsB + rr);
-      lx = __ldg(p.srowsL + rr);
-    } else {
-      const int2 m = __ldg(p.trimeta + t);
-      const unsigned rr = (unsigned)m.x + (unsigned)(gy - m.y);
+    if (ORDERED) {
+      t = owner[pos];
+      const RastSetup *su = p.setup + t;
+      const unsigned rr = su->row_off + (unsigned)(gy - su->row0);
       B = __ldg(p.rowsB + rr);
-      lx = __ldg(p.rowsL + rr);
+      lx = __float_as_int(__ldg(&p.rowsA[rr].x));
+    } else {
+      const unsigned low = (unsigned)owner[pos], code = low & 31u;
+      t = (int)(low >> 5);
+      if (code < (unsigned)S2_ROWS) {                                 // small triangle: the record's place is in the key
+        const size_t rr = (size_t)t * S2_ROWS + code;
+        B = __ldg(p.srowsB + rr);
+        lx = __ldg(p.srowsL + rr);
+      } else {
+        const int2 m = __ldg(p.trimeta + t);
+        const unsigned rr = (unsigned)m.x + (unsigned)(gy - m.y);
+        B = __ldg(p.rowsB + rr);
+        lx = __ldg(p.rowsL + rr);
+      }
     }
     const float fi = (float)(gx - lx);
-    const float zinv = zinv_s[pos];                                 // as the scatter computed it (:543)
+    const float zinv = zinv_s[pos];                                 // as the scatter / fold computed it (:543)
     const float pz = xdiv(1.0f, zinv);                              // :546
     const float px = xdiv(xadd(B.x, xmul(B.y, fi)), zinv);          // :547
     const float py = xdiv(xadd(B.z, xmul(B.w, fi)), zinv);          // :548
@@ -426,8 +448,25 @@ __global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __gr
   const size_t q = (size_t)y * p.W + x;
   float out[3] = {0.f, 0.f, 0.f};
   const bool interior = y >= 1 && y <= p.H - 2 && x >= 1 && x <= p.W - 2;
-  // five empty taps average to +0 exactly: nothing to compute (most pixels of a sparse scene)
-  const bool any = (owner[c0] & owner[c0 - RS_HW] & owner[c0 + RS_HW] & owner[c0 - 1] & owner[c0 + 1]) >= 0;
+  // The reference darkens screenBuffer in place while scanning row-major (:286-303): the cross at
+  // (y,x) sees darkened (y,x), (y-1,x), (y,x-1) and original (y+1,x), (y,x+1); the amount depends on
+  // the final shadow mask only (surroundingShadowSum :1725-1733: [y+1][x-1] twice, [y+1][x+1] never).
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  if (ORDERED) {
+    auto sub = [&](int yy, int xx) -> float {   // (yy, xx) relative to the pixel: flags of pixel (y + yy, x + xx)
+      const int gy = y + yy, gx = x + xx;
+      if (gy < 1 || gy > p.H - 2 || gx < 1 || gx > p.W - 2) return 0.f;   // never visited by the loop
+      const unsigned char *f = flag + (ty + 2 + yy) * RS_FW + (tx + 2 + xx);
+      if (f[0] != 1) return 0.f;
+      const int sum = f[0] + f[-RS_FW] + f[-RS_FW - 1] + f[-RS_FW + 1] + f[RS_FW - 1] + f[RS_FW] + f[RS_FW - 1] + f[-1] + f[1];
+      const double d = (double)xdiv((float)sum, 9.0f);
+      return d < 0.6 ? 0.05f : d < 0.7 ? 0.08f : d < 0.8 ? 0.1f : d < 0.9 ? 0.12f : 0.3f;
+    };
+    s0 = sub(0, 0); s1 = sub(-1, 0); s2 = sub(0, -1);
+  }
+  // five empty, undarkened taps average to +0 exactly: nothing to compute (most pixels of a sparse scene)
+  const bool any = (owner[c0] & owner[c0 - RS_HW] & owner[c0 + RS_HW] & owner[c0 - 1] & owner[c0 + 1]) >= 0 ||
+                   s0 != 0.f || s1 != 0.f || s2 != 0.f;
   if (in_x && interior && any) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -435,9 +474,15 @@ __global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __gr
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
         const float *cb = col[3 * b + c];
-        float a = xadd(cb[c0], cb[c0 - RS_HW]);
+        float v0 = cb[c0], v1 = cb[c0 - RS_HW], v2 = cb[c0 - 1];
+        if (ORDERED && b == 0) {   // the reference only subtracts where the flag is set; x - 0 == x keeps that exact
+          if (s0 != 0.f) v0 = xsub(v0, s0);
+          if (s1 != 0.f) v1 = xsub(v1, s1);
+          if (s2 != 0.f) v2 = xsub(v2, s2);
+        }
+        float a = xadd(v0, v1);
         a = xadd(a, cb[c0 + RS_HW]);
-        a = xadd(a, cb[c0 - 1]);
+        a = xadd(a, v2);
         a = xadd(a, cb[c0 + 1]);
         acc[b] = xdiv_const<5>(a);
       }
@@ -461,7 +506,7 @@ __global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __gr
   if (p.out_argb) p.out_argb[q] = interior ? put_pixel_argb(out[0], out[1], out[2]) : 0u;
   if (p.out_depth) p.out_depth[q] = zinv_s[c0];
   if (p.out_index) {
-    const int t = owner[c0] >> 5;                                    // -1 >> 5 = -1
+    const int t = ORDERED ? owner[c0] : owner[c0] >> 5;              // -1 >> 5 = -1
     p.out_index[q] = (t >= 0 && p.orig) ? __ldg(p.orig + t) : t;
   }
 }

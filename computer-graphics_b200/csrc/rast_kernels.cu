@@ -98,6 +98,10 @@ struct RastParams {
   unsigned bin_cap;
   float *depth, *screen, *low, *high;
   int *shadow, *index;
+  // ordered path, fused (the default): the fold leaves one word per pixel in `keys` (depth bits << 32 |
+  // winner + 1) and a shadow flag per pixel; rast_resolve_kernel<true> shades and post-processes from those
+  int fused;
+  unsigned char *shadow8;
   float *out_rgb;
   float *out_depth;
   int *out_index;
@@ -723,7 +727,11 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
   }
 
   // ---- deferred PixelShader of the winning fragment (:575-586) ----
-  if (on_screen && y >= p.fb0 && y < p.fb1) {
+  if (on_screen && y >= p.fb0 && y < p.fb1 && p.fused) {
+    const size_t q = (size_t)y * p.W + x;
+    p.keys[q] = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned)(win + 1);
+    p.shadow8[q] = (unsigned char)shadow;
+  } else if (on_screen && y >= p.fb0 && y < p.fb1) {
     const size_t q = (size_t)y * p.W + x;
     float sc[3] = {0.f, 0.f, 0.f}, lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
     if (win >= 0) {
@@ -969,7 +977,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
       p.row1 = band_slice_edge(row0, row1 - row0, i + 1, k, RS_H);
       if (p.row1 <= p.row0) continue;
       dim3 rg((W + RS_W - 1) / RS_W, (p.row1 - p.row0 + RS_H - 1) / RS_H);
-      rast_resolve_kernel<<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
+      rast_resolve_kernel<false><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
       tl_mark(ctx, "rast_resolve_kernel");
       CU_CHECK(ctx, cudaGetLastError());
@@ -988,13 +996,25 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(float4) * row_cap)) return rc;
   if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * row_cap)) return rc;
   if (int rc = ensure(ctx, ctx->rast_tile_count, sizeof(unsigned) * (size_t)(n_tiles + 1) * 3)) return rc;
-  if (int rc = ensure(ctx, ctx->rast_screen, npix * 3 * sizeof(float))) return rc;
-  if (int rc = ensure(ctx, ctx->rast_low, npix * 3 * sizeof(float))) return rc;
-  if (int rc = ensure(ctx, ctx->rast_high, npix * 3 * sizeof(float))) return rc;
-  if (int rc = ensure(ctx, ctx->rast_shadow, npix * sizeof(int))) return rc;
-  if (int rc = ensure(ctx, ctx->rast_depth, npix * sizeof(float))) return rc;
-  if (int rc = ensure(ctx, ctx->rast_index, npix * sizeof(int))) return rc;
-  ctx->rast_w = W; ctx->rast_h = H;
+  // Automatic strategy: fused -- the fold leaves 9 bytes per pixel and the resolve kernel does the
+  // rest.  B200_OPT_RAST_PATH = 1 keeps the reference's six intermediate buffers (raster_read_buffers).
+  const bool fused = ctx->opt_rast_path == 0;
+  p.fused = fused ? 1 : 0;
+  if (fused) {
+    if (int rc = ensure(ctx, ctx->rast_keys, npix * sizeof(unsigned long long))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_shadow8, npix)) return rc;
+    p.keys = (unsigned long long *)ctx->rast_keys.p;
+    p.shadow8 = (unsigned char *)ctx->rast_shadow8.p;
+    ctx->rast_w = 0; ctx->rast_h = 0;
+  } else {
+    if (int rc = ensure(ctx, ctx->rast_screen, npix * 3 * sizeof(float))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_low, npix * 3 * sizeof(float))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_high, npix * 3 * sizeof(float))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_shadow, npix * sizeof(int))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_depth, npix * sizeof(float))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_index, npix * sizeof(int))) return rc;
+    ctx->rast_w = W; ctx->rast_h = H;
+  }
   p.rowsA = (float4 *)ctx->rast_rowsA.p;
   p.rowsB = (float4 *)ctx->rast_rowsB.p;
   p.row_cap = (unsigned)(row_cap > 0xffffffffull ? 0xffffffffull : row_cap);
@@ -1064,9 +1084,10 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     p.row1 = band_slice_edge(row0, row1 - row0, i + 1, k, 8);
     if (p.row1 <= p.row0) continue;
     dim3 pb(32, 8), pg((W + 31) / 32, (p.row1 - p.row0 + 7) / 8);
-    rast_post_kernel<<<pg, pb, 0, ctx->stream>>>(p);
+    if (fused) rast_resolve_kernel<true><<<pg, RS_W * RS_H, 0, ctx->stream>>>(p);
+    else rast_post_kernel<<<pg, pb, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
-    tl_mark(ctx, "rast_post_kernel");
+    tl_mark(ctx, fused ? "rast_resolve_kernel<ordered>" : "rast_post_kernel");
     CU_CHECK(ctx, cudaGetLastError());
     if (int rc = band_slice_done(ctx, p.row0, p.row1)) return rc;
   }

@@ -220,15 +220,17 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
         }
       }
     q.dmax = dmax * 1.001f + 1.0f;
+    // world_S bounds |start - v0|inf of SHADOW rays (the camera's own plane records use the exact
+    // |camera - v0|): their starts are hit points, which lie on the scene's geometry, so the camera
+    // position does not enter (it tripled S, and with it the filter's margin, on the Cornell box)
     float m = ctx->rt_world_abs;
-    for (int k = 0; k < 3; ++k) m = fmaxf(m, fabsf(f.cam[k]));
     q.n_lights = f.n_lights;
     for (int l = 0; l < f.n_lights; ++l)
       for (int k = 0; k < 3; ++k) {
         q.lights[l][k] = f.lights[l][k];
         m = fmaxf(m, fabsf(f.lights[l][k]));
       }
-    q.world_S = 2.0f * m * 1.001f + 1e-4f;
+    q.world_S = 2.0f * m * 1.001f + 1e-3f;
     q.n_scale = ctx->rt_normal_abs;
     q.planes = (float4 *)ctx->rt_planes.p;
     q.origin_stride_f4 = origin_stride;
