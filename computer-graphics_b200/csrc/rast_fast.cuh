@@ -327,8 +327,8 @@ __global__ void rast_scatter_kernel(const __grid_constant__ RastParams p) {
   if ((threadIdx.x & 31) == 0 && n_frag) atomicAdd(p.counters + 16, n_frag);
 }
 
-constexpr int RS_W = 32, RS_H = 8, RS_HW = RS_W + 2, RS_HH = RS_H + 2, RS_N = RS_HW * RS_HH;   // 34 x 10 = 340
-constexpr int RS_HALO = 2 * RS_HW + 2 * RS_H;                                                   // 84 halo positions
+constexpr int RS_W = 32, RS_H = 8, RS_HW = RS_W + 2, RS_HH = RS_H + 2, RS_N = RS_HW * RS_HH;   // tile + 1-pixel halo
+constexpr int RS_HALO = 2 * RS_HW + 2 * RS_H;                                                   // halo positions
 constexpr int RS_FW = RS_W + 4, RS_FH = RS_H + 4;                                               // shadow flags: 2-pixel halo
 
 // ORDERED = false: the scatter path's keys (row record named by the key).  ORDERED = true: the
@@ -336,7 +336,7 @@ constexpr int RS_FW = RS_W + 4, RS_FH = RS_H + 4;                               
 // and a shadow flag per pixel) -- the same pass then also does the shadow softening of the post pass
 // (:286-303), so that path keeps no colour buffers in HBM either.
 template <bool ORDERED>
-__global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __grid_constant__ RastParams p) {
+__global__ void __launch_bounds__(RS_W * RS_H, 2048 / (RS_W * RS_H)) rast_resolve_kernel(const __grid_constant__ RastParams p) {
   __shared__ float col[9][RS_N];            // [screen rgb, low rgb, high rgb][position]: conflict-free taps
   __shared__ float zinv_s[RS_N];            // the winner's zinv (:665); 0 = empty
   __shared__ int owner[RS_N];
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(RS_W * RS_H, 8) rast_resolve_kernel(const __gr
     }
   };
   take(true, tx + 1, ty + 1);
-  if (tid < 96) {   // warps 0..2, whole warps
+  if (tid < (RS_HALO + 31) / 32 * 32) {   // whole warps
     const int h = tid;
     int hx, hy;
     if (h < RS_HW) { hx = h; hy = 0; }

@@ -1080,11 +1080,12 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   CU_CHECK(ctx, cudaGetLastError());
   const int k = (ctx->slice_host && (size_t)(row1 - row0) * W >= ((size_t)1 << 20)) ? B200_SLICES : 1;
   for (int i = 0; i < k; ++i) {
-    p.row0 = band_slice_edge(row0, row1 - row0, i, k, 8);
-    p.row1 = band_slice_edge(row0, row1 - row0, i + 1, k, 8);
+    p.row0 = band_slice_edge(row0, row1 - row0, i, k, fused ? RS_H : 8);
+    p.row1 = band_slice_edge(row0, row1 - row0, i + 1, k, fused ? RS_H : 8);
     if (p.row1 <= p.row0) continue;
     dim3 pb(32, 8), pg((W + 31) / 32, (p.row1 - p.row0 + 7) / 8);
-    if (fused) rast_resolve_kernel<true><<<pg, RS_W * RS_H, 0, ctx->stream>>>(p);
+    const dim3 rg((W + RS_W - 1) / RS_W, (p.row1 - p.row0 + RS_H - 1) / RS_H);
+    if (fused) rast_resolve_kernel<true><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
     else rast_post_kernel<<<pg, pb, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     tl_mark(ctx, fused ? "rast_resolve_kernel<ordered>" : "rast_post_kernel");
