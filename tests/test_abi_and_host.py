@@ -38,6 +38,8 @@ def test_no_cpu_fallback(b200):
         pytest.skip("a GPU is present")
     with pytest.raises(b200.B200Error):
         b200.Renderer(0)
+    with pytest.raises(b200.B200Error):
+        b200.Renderer(n_gpus=2)          # b200_init_multi: B200_ENODEV as well
 
 
 def test_product_does_not_touch_the_oracle():
