@@ -69,6 +69,9 @@ int b200_init(int device, b200_ctx **out) {
   ctx->timeline = getenv("B200_TIMELINE") != nullptr;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     delete ctx;
@@ -76,6 +79,9 @@ int b200_init(int device, b200_ctx **out) {
   }
   for (int i = 0; i < B200_SLICES; ++i)
     if (cudaEventCreateWithFlags(&ctx->ev_slice[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return B200_ECUDA; }
+  for (int i = 0; i < RAST_UP_CHUNKS; ++i)
+    if (cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return B200_ECUDA; }
   ctx->stream = ctx->own_stream;
   if (ensure(ctx, ctx->counters, 32 * sizeof(unsigned long long)) != B200_OK || ensure_pinned(ctx, 1024) != B200_OK) {
     delete ctx;
@@ -106,6 +112,10 @@ void b200_destroy(b200_ctx *ctx) {
   cudaEventDestroy(ctx->ev_copied);
   for (int i = 0; i < B200_SLICES; ++i) cudaEventDestroy(ctx->ev_slice[i]);
   for (int i = 0; i < 64; ++i) if (ctx->tl_ev[i]) cudaEventDestroy(ctx->tl_ev[i]);
+  for (int i = 0; i < RAST_UP_CHUNKS; ++i) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_chunk[i]); }
+  cudaEventDestroy(ctx->ev_join);
+  cudaEventDestroy(ctx->ev_main);
+  cudaStreamDestroy(ctx->aux_stream);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -545,7 +555,16 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
   ctx->tl_n = 0;
   tl_mark(ctx, "frame start");
   rast_light_t lc = *light;
-  ctx->rast_clear_ptr = nullptr; ctx->rast_keys_cleared = 0; ctx->rast_cull_on = 0;
+  ctx->rast_clear_ptr = nullptr; ctx->rast_keys_cleared = 0; ctx->rast_cull_on = 0; ctx->rast_geom_chunks = 1;
+  const bool to_scatter = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow);
+  if (ctx->rast_up_chunks > 1) {
+    if (spec && whole_draw && to_scatter) {
+      ctx->rast_geom_chunks = ctx->rast_up_chunks;   // the frame consumes the upload chunk by chunk
+    } else {                                        // any other frame: the whole scene first
+      CU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[ctx->rast_up_chunks - 1], 0));
+    }
+    ctx->rast_up_chunks = 1;
+  }
   if (!whole_draw) ctx->rast_culled = 0;   // the caller's own list
   if (whole_draw) {
     if (spec && (ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow))) {
@@ -641,8 +660,25 @@ int rast_upload_scene(b200_ctx *ctx, const rast_triangle *room, int n_room, cons
   const size_t n = (size_t)n_room + (size_t)n_boxes;
   if (int rc = ensure(ctx, ctx->rast_world, sizeof(rast_triangle) * (n ? n : 1))) return rc;
   rast_triangle *d = (rast_triangle *)ctx->rast_world.p;
-  if (n_room) CU_CHECK(ctx, cudaMemcpyAsync(d, room, sizeof(rast_triangle) * (size_t)n_room, cudaMemcpyHostToDevice, ctx->stream));
-  if (n_boxes) CU_CHECK(ctx, cudaMemcpyAsync(d + n_room, boxes, sizeof(rast_triangle) * (size_t)n_boxes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->rast_up_chunks = 1;
+  if (ctx->rast_chunk_next_upload && n_boxes == 0 && (size_t)n_room * sizeof(rast_triangle) >= ((size_t)16 << 20)) {
+    // a frame follows at once (host-pointer entries): the list travels in chunks on the copy stream,
+    // and that frame's geometry / scatter work on chunk k while chunk k + 1 is on the link
+    CU_CHECK(ctx, cudaEventRecord(ctx->ev_main, ctx->stream));
+    CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_main, 0));
+    for (int c = 0; c <= RAST_UP_CHUNKS; ++c)
+      ctx->rast_up_edge[c] = c == RAST_UP_CHUNKS ? n_room : (int)((long long)n_room * c / RAST_UP_CHUNKS) / 128 * 128;
+    for (int c = 0; c < RAST_UP_CHUNKS; ++c) {
+      const size_t a = (size_t)ctx->rast_up_edge[c], b = (size_t)ctx->rast_up_edge[c + 1];
+      if (b > a) CU_CHECK(ctx, cudaMemcpyAsync(d + a, room + a, sizeof(rast_triangle) * (b - a), cudaMemcpyHostToDevice, ctx->copy_stream));
+      CU_CHECK(ctx, cudaEventRecord(ctx->ev_up[c], ctx->copy_stream));
+    }
+    ctx->rast_up_chunks = RAST_UP_CHUNKS;
+  } else {
+    if (n_room) CU_CHECK(ctx, cudaMemcpyAsync(d, room, sizeof(rast_triangle) * (size_t)n_room, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_boxes) CU_CHECK(ctx, cudaMemcpyAsync(d + n_room, boxes, sizeof(rast_triangle) * (size_t)n_boxes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->rast_chunk_next_upload = 0;
   ctx->rast_n_room = n_room;
   ctx->rast_n_boxes = n_boxes;
   return B200_OK;
@@ -695,6 +731,7 @@ int render_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room, con
   if (ctx->multi)
     return multi_raster(ctx, room, n_room, boxes, n_boxes, cam, light, row_begin, row_end, rgb_out, depth_out, index_out, nullptr);
   if (int rc = check_camera(ctx, cam)) return rc;
+  ctx->rast_chunk_next_upload = 1;
   if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
   return rast_band_resident(ctx, cam, light, row_begin, row_end, rgb_out, depth_out, index_out, nullptr);
 }
@@ -715,6 +752,7 @@ int draw_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room, const
   if (ctx->multi)
     return multi_raster(ctx, room, n_room, boxes, n_boxes, cam, light, row_begin, row_end, nullptr, nullptr, nullptr, argb_out);
   if (int rc = check_camera(ctx, cam)) return rc;
+  ctx->rast_chunk_next_upload = 1;
   if (int rc = rast_upload_scene(ctx, room, n_room, boxes, n_boxes)) return rc;
   return rast_band_resident(ctx, cam, light, row_begin, row_end, nullptr, nullptr, nullptr, argb_out);
 }

@@ -67,6 +67,7 @@ __host__ __device__ __forceinline__ uint32_t put_pixel_argb(float r, float g, fl
 
 // ---- context -------------------------------------------------------------------
 #define B200_SLICES 4
+constexpr int RAST_UP_CHUNKS = 4;   // a large raster scene travels to the device in this many chunks (draw_raster_band)
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
@@ -83,6 +84,14 @@ struct b200_ctx {
   // slice i + 1, slice i travels to the host on a second stream (band_begin .. band_slice_done).
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_slice[B200_SLICES] = {}, ev_copied = nullptr;
+  // Chunked scene upload of the host-pointer raster entries: chunk k is copied on copy_stream, the
+  // single-pass geometry kernel runs per chunk behind its copy, and the scatter of chunk k runs on
+  // aux_stream while chunk k + 1 is still on the link.
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_up[RAST_UP_CHUNKS] = {}, ev_chunk[RAST_UP_CHUNKS] = {}, ev_join = nullptr, ev_main = nullptr;
+  int rast_chunk_next_upload = 0;   // set by the host-pointer entries: the next rast_upload_scene may travel in chunks
+  int rast_up_chunks = 1, rast_up_edge[RAST_UP_CHUNKS + 1] = {};   // chunks of the upload in flight; their first triangles (multiples of 128)
+  int rast_geom_chunks = 1, rast_geom_chunk_tris[RAST_UP_CHUNKS] = {};   // of the frame being enqueued
   uint32_t *slice_host = nullptr;       // destination of row `slice_row0`; null = no sliced copy in progress
   const uint32_t *slice_dev = nullptr;  // device frame (full-frame addressing)
   int slice_row0 = 0, slice_w = 0, slice_n = 0;

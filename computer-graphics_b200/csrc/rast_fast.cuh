@@ -86,8 +86,13 @@ __global__ void __launch_bounds__(S2_THREADS) rast_scatter2_kernel(const __grid_
   float *epar = reinterpret_cast<float *>(stage);            // [edge * 6 + k][thread]: a.zinv, sz, a.px*a.zinv, spx, a.py*a.zinv, spy
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t0 = blockIdx.x * S2_THREADS, t = t0 + tid;
-  const int n_tris = rast_count_tris(p);
+  // (a launch for one geometry chunk works on the list range that chunk wrote; if the launch turns
+  // out too small for it -- clipping added more than 3 % -- the frame is flagged and rendered again)
+  const int lo = p.range_lo ? (int)*p.range_lo : 0;
+  const int n_tris = p.range_hi ? (int)min((unsigned long long)p.n_tris, *p.range_hi) : rast_count_tris(p);
+  if (p.range_hi && blockIdx.x == 0 && threadIdx.x == 0 && (long long)n_tris - lo > (long long)gridDim.x * S2_THREADS)
+    atomicExch(p.counters + 5, 1ull);
+  const int t0 = lo + blockIdx.x * S2_THREADS, t = t0 + tid;
   if (t0 >= n_tris) return;   // pipelined launches are sized by a bound on the list length
   const int n_here = min(S2_THREADS, n_tris - t0);
   {

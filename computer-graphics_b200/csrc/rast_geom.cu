@@ -41,6 +41,12 @@ struct GeomParams {
   // orig[] receives their indices in the complete list (what the owner-index output reports)
   int cull, cull0, cull1;
   int *orig;
+  // single-pass mode launched in several chunks of blocks (a large scene still arriving from the
+  // host: chunk k is transformed, clipped and scattered while chunk k + 1 is on the PCIe link):
+  // blocks of the whole list, last block of this launch, where that block leaves the length of the
+  // list written so far
+  int n_blocks_total, chunk_last_bid;
+  unsigned long long *chunk_hi;
 };
 
 // MODE 0: count the triangles each pre-clip triangle turns into; MODE 1: write them at the
@@ -58,7 +64,7 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
     __syncthreads();
   }
   const int bid = MODE == 2 ? (int)s_bid : (int)blockIdx.x;
-  if (MODE == 2 && p.clear_n) {
+  if (MODE == 2 && p.clear_n) {   // (set for the first chunk's launch only: its block ids start at 0)
     const size_t per = (p.clear_n + gridDim.x - 1) / gridDim.x;
     const size_t a = (size_t)bid * per, b = a + per < p.clear_n ? a + per : p.clear_n;
     for (size_t i = a + threadIdx.x; i < b; i += GT) p.clear[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -159,7 +165,8 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
       }
       if (lane == 0) {
         atomicExch(p.desc + bid, (2ull << 62) | (prefix + block_val));
-        if (bid == (int)gridDim.x - 1) *p.total = (prefix + block_val) >> 31;   // length of the written list
+        if (bid == p.n_blocks_total - 1) *p.total = (prefix + block_val) >> 31;   // length of the written list
+        if (bid == p.chunk_last_bid && p.chunk_hi) *p.chunk_hi = (prefix + block_val) >> 31;
         s_prefix = (unsigned)(prefix >> 31);
         s_prefix_all = (unsigned)(prefix & 0x7fffffffull);
       }
@@ -365,13 +372,26 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
       p.orig = (int *)ctx->rast_orig.p;
       ctx->rast_culled = 1;
     }
-    if (ctx->rast_clear_ptr && ((size_t)ctx->rast_clear_ptr & 15) == 0 && (ctx->rast_clear_bytes & 15) == 0) {
-      p.clear = (uint4 *)ctx->rast_clear_ptr;
-      p.clear_n = ctx->rast_clear_bytes / 16;
-      ctx->rast_keys_cleared = 1;
+    const bool clear = ctx->rast_clear_ptr && ((size_t)ctx->rast_clear_ptr & 15) == 0 && (ctx->rast_clear_bytes & 15) == 0;
+    if (clear) ctx->rast_keys_cleared = 1;
+    // A scene that is still arriving from the host in chunks (draw_raster_band on a large list): one
+    // launch per chunk, each behind its chunk's copy; rast_launch scatters chunk k on the second
+    // stream while chunk k + 1 is on the link.
+    const int chunks = ctx->rast_geom_chunks;
+    p.n_blocks_total = n_blocks;
+    for (int c = 0; c < chunks; ++c) {
+      const int b0 = chunks > 1 ? ctx->rast_up_edge[c] / 128 : 0;
+      const int b1 = (chunks > 1 && c + 1 < chunks) ? ctx->rast_up_edge[c + 1] / 128 : n_blocks;
+      p.clear = (clear && c == 0) ? (uint4 *)ctx->rast_clear_ptr : nullptr;
+      p.clear_n = (clear && c == 0) ? ctx->rast_clear_bytes / 16 : 0;
+      p.chunk_last_bid = b1 - 1;
+      p.chunk_hi = chunks > 1 ? (unsigned long long *)ctx->counters.p + 12 + c : nullptr;
+      ctx->rast_geom_chunk_tris[c] = (b1 - b0) * 128;
+      if (chunks > 1) CU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[c], 0));
+      if (b1 > b0) rast_geom_kernel<2><<<b1 - b0, 128, 0, ctx->stream>>>(p);
+      if (chunks > 1) CU_CHECK(ctx, cudaEventRecord(ctx->ev_chunk[c], ctx->stream));
     }
-    rast_geom_kernel<2><<<n_blocks, 128, 0, ctx->stream>>>(p);
-    ctx->stats.kernel_launches++;
+    ctx->stats.kernel_launches += chunks;
     tl_mark(ctx, "rast_geom_kernel<2>");
     CU_CHECK(ctx, cudaGetLastError());
     ctx->rast_n_tris = (int)cap;

@@ -80,6 +80,8 @@ struct RastParams {
   float4 *srowsB;    // fast path, small triangles: row records at triangle * S2_ROWS + y mod S2_ROWS
   int *srowsL;
   int2 *trimeta;     // fast path: per triangle, index of its first stored row and that row's y
+  // scatter of one geometry chunk: the list range [*range_lo, *range_hi) (null: the whole list)
+  const unsigned long long *range_lo, *range_hi;
   const int *orig;   // band-culled list: index of every triangle in the complete list (null: the list is complete)
   int *big_list;     // fast path: triangles too large for rast_scatter2_kernel's shared-memory row table
   unsigned big_cap;
@@ -954,8 +956,25 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     }
     ctx->rast_keys_cleared = 0;
     if (n > 0) {
-      rast_scatter2_kernel<false><<<s2_blocks, S2_THREADS, 0, ctx->stream>>>(p);
-      ctx->stats.kernel_launches++;
+      if (spec && ctx->rast_geom_chunks > 1) {
+        // chunk k of the list is scattered on the second stream as soon as the geometry kernel's
+        // k-th launch is done, while chunk k + 1 of the scene is still on the link; the frame goes on
+        // when all are in
+        for (int c = 0; c < ctx->rast_geom_chunks; ++c) {
+          RastParams pc = p;
+          pc.range_lo = c ? p.counters + 12 + (c - 1) : nullptr;
+          pc.range_hi = p.counters + 12 + c;
+          const int bound = ctx->rast_geom_chunk_tris[c] + ctx->rast_geom_chunk_tris[c] / 32 + 1024;   // + 3 %: clipping can add triangles
+          CU_CHECK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_chunk[c], 0));
+          rast_scatter2_kernel<false><<<(bound + S2_THREADS - 1) / S2_THREADS, S2_THREADS, 0, ctx->aux_stream>>>(pc);
+          ctx->stats.kernel_launches++;
+        }
+        CU_CHECK(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+        CU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+      } else {
+        rast_scatter2_kernel<false><<<s2_blocks, S2_THREADS, 0, ctx->stream>>>(p);
+        ctx->stats.kernel_launches++;
+      }
       tl_mark(ctx, "rast_scatter2_kernel");
       if (big_cap > 0) {
         rast_setup_big_kernel<<<(int)((big_cap + 127) / 128), 128, 0, ctx->stream>>>(p);
