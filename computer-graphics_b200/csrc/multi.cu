@@ -30,26 +30,35 @@
 #include <mutex>
 #include <thread>
 
+// Hand-offs between the calling thread and the device threads are short and frequent (a frame is a
+// fraction of a millisecond): both sides spin for a while before they go to sleep on the condition
+// variable (a wake-up through the kernel costs 20-50 us, several times per frame).
+static int MULTI_SPIN = 20000;   // iterations; B200_MULTI_SPIN overrides (0: sleep at once)
+
 struct MultiWorker {
   std::thread th;
   std::mutex m;
   std::condition_variable cv;
   std::function<int()> job;
-  bool has_job = false, done = true, quit = false;
+  std::atomic<int> has_job{0}, done{1};
+  bool quit = false;
   int rc = 0;
 };
 
 // Reusable barrier of the worker threads (phases of one frame: buffers exist -> slices pushed).
 struct MultiBarrier {
-  std::mutex m;
-  std::condition_variable cv;
-  int n = 0, waiting = 0;
-  unsigned long long gen = 0;
+  std::atomic<int> waiting{0};
+  std::atomic<unsigned long long> gen{0};
+  int n = 0;
   void wait() {
-    std::unique_lock<std::mutex> lk(m);
-    const unsigned long long g = gen;
-    if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); return; }
-    cv.wait(lk, [&] { return gen != g; });
+    const unsigned long long g = gen.load(std::memory_order_acquire);
+    if (waiting.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+      waiting.store(0, std::memory_order_relaxed);
+      gen.fetch_add(1, std::memory_order_release);
+      return;
+    }
+    for (long long spins = 0; gen.load(std::memory_order_acquire) == g; ++spins)
+      if (spins > MULTI_SPIN) std::this_thread::yield();
   }
 };
 
@@ -70,19 +79,17 @@ struct b200_multi {
 static void worker_main(MultiWorker *w, int device) {
   cudaSetDevice(device);
   for (;;) {
-    std::function<int()> job;
-    {
+    for (int spins = 0; spins < MULTI_SPIN && !w->has_job.load(std::memory_order_acquire); ++spins) {}
+    if (!w->has_job.load(std::memory_order_acquire)) {
       std::unique_lock<std::mutex> lk(w->m);
-      w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+      w->cv.wait(lk, [&] { return w->has_job.load(std::memory_order_acquire) || w->quit; });
       if (w->quit) return;
-      job = w->job;
-      w->has_job = false;
     }
-    const int rc = job();
+    w->has_job.store(0, std::memory_order_relaxed);
+    w->rc = w->job();
     {
-      std::lock_guard<std::mutex> lk(w->m);
-      w->rc = rc;
-      w->done = true;
+      std::lock_guard<std::mutex> lk(w->m);   // pairs with the caller's wait below
+      w->done.store(1, std::memory_order_release);
     }
     w->cv.notify_all();
   }
@@ -95,16 +102,20 @@ static int multi_run(b200_ctx *ctx, const std::function<int(int)> &job) {
     MultiWorker *w = mc->worker[i];
     {
       std::lock_guard<std::mutex> lk(w->m);
-      w->job = [job, i] { return job(i); };
-      w->has_job = true; w->done = false;
+      w->job = [&job, i] { return job(i); };
+      w->done.store(0, std::memory_order_relaxed);
+      w->has_job.store(1, std::memory_order_release);
     }
     w->cv.notify_all();
   }
   int rc = B200_OK;
   for (int i = 0; i < mc->n; ++i) {
     MultiWorker *w = mc->worker[i];
-    std::unique_lock<std::mutex> lk(w->m);
-    w->cv.wait(lk, [&] { return w->done; });
+    for (int spins = 0; spins < MULTI_SPIN && !w->done.load(std::memory_order_acquire); ++spins) {}
+    if (!w->done.load(std::memory_order_acquire)) {
+      std::unique_lock<std::mutex> lk(w->m);
+      w->cv.wait(lk, [&] { return w->done.load(std::memory_order_acquire) != 0; });
+    }
     if (w->rc != B200_OK && rc == B200_OK) {
       rc = w->rc;
       ctx->err = "device " + std::to_string(i) + ": " + mc->child[i]->err;
@@ -184,6 +195,7 @@ int b200_init_multi(int n_gpus, b200_ctx **out) {
   if (n_gpus <= 0) n_gpus = have;
   if (n_gpus > have) return B200_EINVAL;
   if (n_gpus == 1) return b200_init(0, out);   // one device: an ordinary context, no threads in between
+  if (const char *e = getenv("B200_MULTI_SPIN")) MULTI_SPIN = atoi(e);
   b200_ctx *ctx = new b200_ctx();
   b200_multi *mc = new b200_multi();
   ctx->multi = mc;
