@@ -454,3 +454,28 @@ def test_band_culling_in_the_geometry_stage(b200, renderer):
     finally:
         renderer.set_option(b200.OPT_RAST_BAND_CULL, 0)
         renderer.set_option(b200.OPT_RAST_PIPELINED, 0)
+
+
+def test_chunked_scene_upload_pipeline(b200, renderer):
+    """draw_raster / render_raster on a list of 16 MB or more: from the second call on the scene
+    travels in chunks and the frame's geometry + scatter work on chunk k while chunk k + 1 is on
+    the link (second stream, per-chunk list ranges).  Same pixels as the oracle, call after call."""
+    W, H, f = 480, 270, 192.0
+    cam_pos = h.f32(0, 0, -3.001, 1)
+    cam = b200.make_camera(cam_pos, f, h.identity_R(), W, H)
+    light = h.DEFAULT_RAST_LIGHT
+    L = b200.make_rast_light(light["pos"], light["power"], light["indirect"])
+    soup = b200.scene_soup_rast(210_000, edge=0.02)          # 17.6 MB
+    none = np.zeros(0, h.RAST_TRI)
+    want = h.oracle_rast_draw(W, H, f, cam_pos, h.identity_R(), light, soup, none)
+    for call in range(4):
+        assert np.array_equal(renderer.draw_raster(soup, none, cam, L), want["argb"]), call
+    got = renderer.render_raster(soup, none, cam, L)
+    assert np.array_equal(bits(got["rgb"]), bits(want["rgb"])) and np.array_equal(got["index"], want["index"])
+    # a camera that clips part of the list (the chunk's list range is no longer its input range)
+    cam_pos2 = h.f32(0.4, 0.1, -1.4, 1)
+    cam2 = b200.make_camera(cam_pos2, f, h.identity_R(), W, H)
+    want2 = h.oracle_rast_draw(W, H, f, cam_pos2, h.identity_R(), light, soup, none)
+    for call in range(3):
+        assert np.array_equal(renderer.draw_raster(soup, none, cam2, L), want2["argb"]), call
+    assert np.array_equal(renderer.draw_raster(soup, none, cam, L), want["argb"])
