@@ -122,25 +122,183 @@ static void illumination_D(const o_frame *f, const float *pos, const float *norm
   for (int k = 0; k < 3; ++k) D[k] = (f->power[k] * m) / den;
 }
 
-/* PixelShader :559-672, untextured colour-mode-0 branch. */
+/* ---- texture state (:63-75, built by main() :133-169) and the view globals findU / findV read ----
+ * An image is what cv::Mat holds: rows x step bytes, at<T>(r, c) = *(T *)(data + r * step + c * sizeof(T)).
+ * which: 0 marble, 1 metalGrill, 2 metalGrillOpacity (thresholded), 3 metalGrillNormalMap, 4 woven,
+ * 5 woven_ambientOcclusion, 6 woven_opacity (thresholded), 7 wovenNormal. */
+typedef struct { const uint8_t *data; int rows, cols, step; } o_image;
+static o_image g_img[8];
+static const float *g_noise;      /* normalMap_marble, vec4 per entry (:157-168) */
+static long long g_noise_len;
+static int g_tex_on;              /* 0: every triangle is drawn as texture == 0 (no images) */
+static float g_cam[4], g_Rinv[16];
+static int g_yaw_nonzero;
+
+void oracle_rast_set_image(int which, const uint8_t *data, int rows, int cols, int step) {
+  if (which < 0 || which > 7) return;
+  g_img[which].data = data; g_img[which].rows = rows; g_img[which].cols = cols; g_img[which].step = step;
+}
+void oracle_rast_set_marble_noise(const float *noise4, long long n) { g_noise = noise4; g_noise_len = n; }
+void oracle_rast_enable_textures(int on) { g_tex_on = on; }
+
+/* glm::inverse(mat4), glm 0.9.7.2 detail/type_mat4x4.inl:37-92; m and out column-major, m[4 * c + r] */
+static void mat4_inverse(const float *m_, float *out) {
+#define M(c, r) m_[4 * (c) + (r)]
+  float Coef00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3);
+  float Coef02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3);
+  float Coef03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
+  float Coef04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3);
+  float Coef06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3);
+  float Coef07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+  float Coef08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2);
+  float Coef10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2);
+  float Coef11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2);
+  float Coef12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3);
+  float Coef14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3);
+  float Coef15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+  float Coef16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2);
+  float Coef18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2);
+  float Coef19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2);
+  float Coef20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1);
+  float Coef22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1);
+  float Coef23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+  float Fac0[4] = {Coef00, Coef00, Coef02, Coef03}, Fac1[4] = {Coef04, Coef04, Coef06, Coef07};
+  float Fac2[4] = {Coef08, Coef08, Coef10, Coef11}, Fac3[4] = {Coef12, Coef12, Coef14, Coef15};
+  float Fac4[4] = {Coef16, Coef16, Coef18, Coef19}, Fac5[4] = {Coef20, Coef20, Coef22, Coef23};
+  float Vec0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)}, Vec1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)};
+  float Vec2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)}, Vec3[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+  static const float SignA[4] = {+1, -1, +1, -1}, SignB[4] = {-1, +1, -1, +1};
+  float Inv[16];
+  for (int k = 0; k < 4; ++k) {
+    Inv[0 + k] = ((Vec1[k] * Fac0[k] - Vec2[k] * Fac1[k]) + Vec3[k] * Fac2[k]) * SignA[k];
+    Inv[4 + k] = ((Vec0[k] * Fac0[k] - Vec2[k] * Fac3[k]) + Vec3[k] * Fac4[k]) * SignB[k];
+    Inv[8 + k] = ((Vec0[k] * Fac1[k] - Vec1[k] * Fac3[k]) + Vec3[k] * Fac5[k]) * SignA[k];
+    Inv[12 + k] = ((Vec0[k] * Fac2[k] - Vec1[k] * Fac4[k]) + Vec2[k] * Fac5[k]) * SignB[k];
+  }
+  float Dot0[4] = {M(0, 0) * Inv[0], M(0, 1) * Inv[4], M(0, 2) * Inv[8], M(0, 3) * Inv[12]};
+  float Dot1 = (Dot0[0] + Dot0[1]) + (Dot0[2] + Dot0[3]);
+  float OneOverDeterminant = 1.0f / Dot1;
+  for (int k = 0; k < 16; ++k) out[k] = Inv[k] * OneOverDeterminant;
+#undef M
+}
+
+/* cameraPos, R and "yaw != 0" as findU / findV see them (:1761-1769) */
+void oracle_rast_set_view(const float *cam4, const float *R16, int yaw_nonzero) {
+  memcpy(g_cam, cam4, sizeof g_cam);
+  mat4_inverse(R16, g_Rinv);
+  g_yaw_nonzero = yaw_nonzero;
+}
+void oracle_rast_inverse(const float *R16, float *out16) { mat4_inverse(R16, out16); }
+
+/* the common head of findU / findV :1759-1769 */
+static void object_space(const float *pos, float *o) {
+  if (g_yaw_nonzero) {
+    /* glm mat4 * vec4: (m[0] * x + m[1] * y) + (m[2] * z + m[3] * w) */
+    for (int r = 0; r < 4; ++r)
+      o[r] = (g_Rinv[r] * pos[0] + g_Rinv[4 + r] * pos[1]) + (g_Rinv[8 + r] * pos[2] + g_Rinv[12 + r] * pos[3]);
+    for (int r = 0; r < 4; ++r) o[r] = o[r] + g_cam[r];
+  } else {
+    for (int r = 0; r < 4; ++r) o[r] = pos[r] + g_cam[r];
+  }
+  o[3] = 1.0f;
+}
+/* float -> int as the reference build does it (cvttss2si: out-of-range and NaN give INT_MIN) */
+static int to_int(float v) {
+  if (!(v > -2147483904.0f && v < 2147483648.0f)) return INT_MIN;
+  return (int)v;
+}
+/* findU :1756-1791: int * float + int, truncated; C's % keeps the sign of u */
+static int find_u(const float *pos, int size, int index) {
+  float o[4];
+  object_space(pos, o);
+  int u = 0;
+  if (index == 3) u = to_int((float)(-size / 2) * o[1] + (float)(size / 2));
+  else if (index == 1) u = to_int((float)(-size / 2) * o[0] + (float)(size / 2));
+  else if (index == 4) u = to_int((float)(-size / 2) * o[1] + (float)(size / 2));
+  else if (index == 2) u = to_int((float)(-size / 2) * o[0] + (float)(size / 2));
+  else if (index == 0) u = to_int((float)(-size / 2) * o[0] + (float)(size / 2));
+  return u % size;
+}
+/* findV :1793-1825 */
+static int find_v(const float *pos, int size, int index) {
+  float o[4];
+  object_space(pos, o);
+  int v = 0;
+  if (index == 3) v = to_int((float)(size / 2) * o[2] + (float)(size / 2));
+  else if (index == 1) v = to_int((float)(-size / 2) * o[2] + (float)(size / 2));
+  else if (index == 4) v = to_int((float)(-size / 2) * o[2] + (float)(size / 2));
+  else if (index == 2) v = to_int((float)(-size / 2) * o[2] + (float)(size / 2));
+  else if (index == 0) v = to_int((float)(-size / 2) * o[1] + (float)(size / 2));
+  return v % size;
+}
+/* Mat::at.  A negative coordinate (a point outside the unit box the textures are laid over) reads out of
+ * bounds in the reference -- undefined; here, and in the product, it wraps into the image. */
+static const uint8_t *texel(const o_image *im, int u, int v, int size, int elem) {
+  if (u < 0) u += size;
+  if (v < 0) v += size;
+  return im->data + (size_t)u * im->step + (size_t)v * elem;
+}
+/* glm::normalize(vec4(x, y, z, 1)) (:603, :629) = v * (1 / sqrt(dot(v, v))), dot = (xx + yy) + (zz + ww) */
+static void normal_from_map(const uint8_t *t, float *n) {
+  float v[4] = {(float)t[0] / 255.0f, (float)t[1] / 255.0f, (float)t[2] / 255.0f, 1.0f};
+  float d = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+  float inv = 1.0f / sqrtf(d);
+  for (int k = 0; k < 3; ++k) n[k] = v[k] * inv;
+}
+
+/* PixelShader :559-672, colour mode 0: texture == 0 (:578-586), marble (:588-599), metal grill (:601-621),
+ * woven wood (:623-645).  Colour modes 1 and 2 (:647-662) draw from rand() and are not restated. */
 static void pixel_shader(o_frame *f, const o_pixel *p, const o_rtri *t, int tri_index) {
   int x = p->x, y = p->y;
   if (x >= 0 && x < f->W && y >= 0 && y < f->H) {
     size_t q = (size_t)y * f->W + x;
     f->fragments++;
     if (p->zinv >= f->depth[q] && t->color[0] >= 0) {
-      float D[3];
-      illumination_D(f, p->pos, t->normal, D);
-      for (int k = 0; k < 3; ++k) {
-        f->screen[3 * q + k] = t->color[k] * (D[k] + f->indirect[k]);   /* :580, the global as it stands */
-        f->low[3 * q + k] = t->color[k] * (D[k] + 0.0f);
-        f->high[3 * q + k] = t->color[k] * (D[k] + 0.4f);
+      const int tex = g_tex_on ? t->texture : 0;
+      float zinv = p->zinv;
+      float colour[3] = {t->color[0], t->color[1], t->color[2]};
+      float normal[3] = {t->normal[0], t->normal[1], t->normal[2]};
+      float occlusion = 1.0f;
+      int shade = tex >= 0 && tex <= 3;   /* any other value: no branch of :578-645 runs, only :665 */
+      if (tex == 1) {
+        const uint8_t *c = texel(&g_img[0], find_u(p->pos, 2000, t->index), find_v(p->pos, 2000, t->index), 2000, 3);
+        colour[0] = (float)c[2] / 255.0f; colour[1] = (float)c[1] / 255.0f; colour[2] = (float)c[0] / 255.0f;
+        long long ni = (long long)p->y * g_img[0].rows + p->x;   /* :593 */
+        if (ni >= g_noise_len) ni = g_noise_len - 1;             /* out of bounds in the reference: clamped */
+        for (int k = 0; k < 3; ++k) normal[k] = normal[k] + g_noise[4 * ni + k];
+      } else if (tex == 2 || tex == 3) {
+        const int u = find_u(p->pos, 1024, t->index), v = find_v(p->pos, 1024, t->index);
+        const o_image *op = &g_img[tex == 2 ? 2 : 6], *nm = &g_img[tex == 2 ? 3 : 7], *base = &g_img[tex == 2 ? 1 : 4];
+        if (*texel(op, u, v, 1024, 1) == 255) {
+          if (tex == 3) { occlusion = (float)*texel(&g_img[5], u, v, 1024, 1); occlusion /= 255.0f; }
+          normal_from_map(texel(nm, u, v, 1024, 3), normal);
+          const uint8_t *c = texel(base, u, v, 1024, 3);
+          colour[0] = (float)c[2] / 255.0f; colour[1] = (float)c[1] / 255.0f; colour[2] = (float)c[0] / 255.0f;
+        } else {
+          zinv = 0;        /* :619, :643: a hole -- the colours stay, the depth goes back to "empty" */
+          shade = 0;
+        }
       }
-      /* :585 leaves the GLOBAL indirectLightPowerPerArea at 0.2f * vec3(1): only the first
-       * shaded fragment of a Draw ever sees the value the global had on entry */
-      f->indirect[0] = f->indirect[1] = f->indirect[2] = 0.2f * 1.0f;
-      f->depth[q] = p->zinv;
-      if (f->index) f->index[q] = tri_index;
+      if (shade) {
+        float D[3];
+        illumination_D(f, p->pos, normal, D);
+        for (int k = 0; k < 3; ++k) {
+          if (tex == 3) {   /* :634-638: textureColour * (illumination * occlusion) */
+            f->screen[3 * q + k] = colour[k] * ((D[k] + f->indirect[k]) * occlusion);
+            f->low[3 * q + k] = colour[k] * ((D[k] + 0.0f) * occlusion);
+            f->high[3 * q + k] = colour[k] * ((D[k] + 0.4f) * occlusion);
+          } else {
+            f->screen[3 * q + k] = colour[k] * (D[k] + f->indirect[k]);   /* :580, the global as it stands */
+            f->low[3 * q + k] = colour[k] * (D[k] + 0.0f);
+            f->high[3 * q + k] = colour[k] * (D[k] + 0.4f);
+          }
+        }
+        /* :585 leaves the GLOBAL indirectLightPowerPerArea at 0.2f * vec3(1): only the first
+         * shaded fragment of a Draw ever sees the value the global had on entry */
+        f->indirect[0] = f->indirect[1] = f->indirect[2] = 0.2f * 1.0f;
+        if (f->index) f->index[q] = tri_index;
+      }
+      f->depth[q] = zinv;   /* :665 */
     } else if (p->zinv > f->depth[q] && t->color[0] < 0) {
       f->shadow[q] = 1;
     }

@@ -279,6 +279,65 @@ def oracle_rast_draw_clipped(W, H, focal, light_cam, light, clipped):
     return out
 
 
+# ---- textures (rasteriser/Source/skeleton.cpp:63-75, 133-169): synthetic images, see oracle/refbuild/stubs/cv_stub.hpp ----
+TEX_IMAGES = ("marble", "grill", "grill_opacity", "grill_normal", "woven", "woven_occlusion", "woven_opacity", "woven_normal")
+
+
+def synthetic_textures(seed=7, noise_amp=0.01):
+    """Random decoded images of the sizes findU / findV are called with (2000 for the marble, 1024 for the
+    rest): three channels, except the two opacity maps, which are what cv::threshold leaves (one channel,
+    0 / 255, in blocks so that holes have edges).  marble_noise is normalMap_marble (vec4 per entry)."""
+    rng = np.random.default_rng(seed)
+    t = {}
+    for name in TEX_IMAGES:
+        n = 2000 if name == "marble" else 1024
+        if name.endswith("opacity"):
+            blocks = rng.uniform(0, 1, (n // 16, n // 16)) < 0.7
+            t[name] = np.ascontiguousarray(np.kron(blocks, np.ones((16, 16), bool)).astype(np.uint8) * np.uint8(255)).reshape(n, n, 1)
+        else:
+            t[name] = rng.integers(0, 256, (n, n, 3), dtype=np.uint8)
+    noise = rng.uniform(-noise_amp, noise_amp, (2000 * 2000, 4)).astype(np.float32)
+    noise[:, 3] = 0.0
+    t["marble_noise"] = noise
+    return t
+
+
+def ref_rast_set_textures(W, H, tex, cam, R, yaw):
+    lib = ref_lib(ref_rast_name(W, H))
+    for i, name in enumerate(TEX_IMAGES):
+        im = tex[name]
+        assert lib.ref_rast_set_image(c_i(i), ptr(im), c_i(im.shape[0]), c_i(im.shape[1]), c_i(im.shape[2])) == 0
+    lib.ref_rast_set_marble_noise(ptr(tex["marble_noise"]), ctypes.c_longlong(len(tex["marble_noise"])))
+    lib.ref_rast_set_view(ptr(np.asarray(cam, np.float32)), ptr(np.asarray(R, np.float32)), c_f(yaw))
+
+
+_oracle_tex_keep = None
+
+
+def oracle_rast_set_textures(tex, cam=None, R=None, yaw=0.0):
+    """tex = None switches the oracle back to the untextured reading of every triangle."""
+    global _oracle_tex_keep
+    lib = oracle()
+    _oracle_tex_keep = tex          # the oracle keeps pointers into these arrays
+    lib.oracle_rast_enable_textures(c_i(0 if tex is None else 1))
+    if tex is None:
+        return
+    for i, name in enumerate(TEX_IMAGES):
+        im = tex[name]
+        lib.oracle_rast_set_image(c_i(i), ptr(im), c_i(im.shape[0]), c_i(im.shape[1]), c_i(im.shape[1] * im.shape[2]))
+    lib.oracle_rast_set_marble_noise(ptr(tex["marble_noise"]), ctypes.c_longlong(len(tex["marble_noise"])))
+    lib.oracle_rast_set_view(ptr(np.asarray(cam, np.float32)), ptr(np.asarray(R, np.float32)), c_i(1 if yaw != 0 else 0))
+
+
+def ref_rast_testmodel_tex(setting, setting_boxes, W=64, H=48):
+    lib = ref_lib(ref_rast_name(W, H))
+    room, boxes = np.zeros(16, RAST_TRI), np.zeros(32, RAST_TRI)
+    a, b = c_i(0), c_i(0)
+    assert lib.ref_rast_load_testmodel_tex(c_i(setting), c_i(setting_boxes), ptr(room), 16, ptr(boxes), 32,
+                                           ctypes.byref(a), ctypes.byref(b)) == 0
+    return room[:a.value].copy(), boxes[:b.value].copy()
+
+
 def rows_call(fn, focal, verts, cap=1 << 14, dims=None):
     y0, n = c_i(0), c_i(0)
     rows = np.zeros((cap, 8), np.float32)
