@@ -53,6 +53,18 @@ class RastLight(ctypes.Structure):
                 ("indirect", ctypes.c_float * 3)]
 
 
+class RastImage(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("step", ctypes.c_int32)]
+
+
+class RastTextures(ctypes.Structure):
+    """rast_textures_t (include/b200render.h): the decoded images of the reference's texture globals."""
+    _fields_ = [("marble", RastImage), ("marble_noise", ctypes.c_void_p), ("marble_noise_len", ctypes.c_int64),
+                ("grill", RastImage), ("grill_opacity", RastImage), ("grill_normal", RastImage),
+                ("woven", RastImage), ("woven_occlusion", RastImage), ("woven_opacity", RastImage),
+                ("woven_normal", RastImage)]
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("primary_rays", ctypes.c_uint64), ("shadow_rays", ctypes.c_uint64),
                 ("prim_tests", ctypes.c_uint64), ("exact_evals", ctypes.c_uint64),
@@ -74,7 +86,7 @@ ABI_SYMBOLS = [
     "b200_measure_fp32_peak", "rt_upload_scene", "rt_render_device",
     "render_raster_clipped", "render_raster", "render_raster_band", "draw_raster", "raster_read_buffers",
     "raster_read_clipped", "rast_upload_clipped", "rast_render_device", "draw_raster_band",
-    "rast_upload_scene", "rast_draw_device",
+    "rast_upload_scene", "rast_draw_device", "rast_set_textures",
     "b200_quantise", "b200_save_bmp",
 ]
 
@@ -285,6 +297,24 @@ class Renderer:
         self._check(self.lib.raster_read_clipped(self.ctx, _ptr(out), len(out), ctypes.byref(n)),
                     "raster_read_clipped")
         return out
+
+    def set_textures(self, tex):
+        """tex: dict of (rows, cols, channels) uint8 arrays named like rast_textures_t's images plus
+        'marble_noise' ((n, 4) float32), or None to switch textures off (rast_set_textures)."""
+        if tex is None:
+            self._check(self.lib.rast_set_textures(self.ctx, None), "rast_set_textures")
+            return
+        t = RastTextures()
+        keep = []
+        for name in ("marble", "grill", "grill_opacity", "grill_normal", "woven", "woven_occlusion", "woven_opacity",
+                     "woven_normal"):
+            im = np.ascontiguousarray(tex[name], np.uint8)
+            keep.append(im)
+            setattr(t, name, RastImage(im.ctypes.data, im.shape[0], im.shape[1], im.shape[1] * (im.shape[2] if im.ndim == 3 else 1)))
+        noise = np.ascontiguousarray(tex["marble_noise"], np.float32).reshape(-1, 4)
+        t.marble_noise = noise.ctypes.data
+        t.marble_noise_len = len(noise)
+        self._check(self.lib.rast_set_textures(self.ctx, ctypes.byref(t)), "rast_set_textures")
 
     def rast_upload_clipped(self, clipped):
         self._check(self.lib.rast_upload_clipped(self.ctx, _ptr(clipped), len(clipped)), "rast_upload_clipped")

@@ -504,6 +504,42 @@ int b200_measure_fp32_peak(b200_ctx *ctx, float *tflops_out) {
 
 // ---- RAST -------------------------------------------------------------------------------
 
+int rast_set_textures(b200_ctx *ctx, const rast_textures_t *tex) {
+  if (!ctx) return B200_EINVAL;
+  if (ctx->multi) return multi_rast_set_textures(ctx, tex);
+  cudaSetDevice(ctx->device);
+  if (ctx->pending == 2 || ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // a frame in flight reads the old images
+  ctx->rast_spec.valid = 0;
+  if (!tex) { ctx->rast_tex_on = 0; return B200_OK; }
+  // order of RastTex::img (rast_tex.cuh): bytes read per pixel, smallest edge
+  const rast_image_t *im[8] = {&tex->marble, &tex->grill, &tex->grill_opacity, &tex->grill_normal,
+                               &tex->woven, &tex->woven_occlusion, &tex->woven_opacity, &tex->woven_normal};
+  const int elem[8] = {3, 3, 1, 3, 3, 1, 1, 3}, edge[8] = {2000, 1024, 1024, 1024, 1024, 1024, 1024, 1024};
+  size_t off[8], total = 0;
+  for (int k = 0; k < 8; ++k) {
+    if (!im[k]->data || im[k]->rows < edge[k] || im[k]->cols < edge[k] || (long long)im[k]->step < (long long)im[k]->cols * elem[k])
+      return ctx_fail(ctx, B200_EINVAL, "texture image missing, smaller than findU / findV address (2000 marble, 1024 others) or step < cols * element");
+    off[k] = total;
+    total += ((size_t)im[k]->rows * (size_t)im[k]->step + 255) & ~(size_t)255;
+  }
+  if (!tex->marble_noise || tex->marble_noise_len < 1) return ctx_fail(ctx, B200_EINVAL, "marble_noise missing");
+  if (int rc = ensure(ctx, ctx->rast_tex_images, total)) return rc;
+  if (int rc = ensure(ctx, ctx->rast_tex_noise, (size_t)tex->marble_noise_len * sizeof(float4))) return rc;
+  RastTex &t = ctx->rast_tex;
+  for (int k = 0; k < 8; ++k) {
+    t.img[k] = (const unsigned char *)ctx->rast_tex_images.p + off[k];
+    t.step[k] = im[k]->step;
+    CU_CHECK(ctx, cudaMemcpyAsync((void *)t.img[k], im[k]->data, (size_t)im[k]->rows * (size_t)im[k]->step, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  t.marble_rows = tex->marble.rows;
+  t.noise = (const float4 *)ctx->rast_tex_noise.p;
+  t.noise_len = tex->marble_noise_len;
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->rast_tex_noise.p, tex->marble_noise, (size_t)tex->marble_noise_len * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the caller's arrays are free again on return
+  ctx->rast_tex_on = 1;
+  return B200_OK;
+}
+
 int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris) {
   if (!ctx) return B200_EINVAL;
   SINGLE_ONLY(ctx);
@@ -512,7 +548,8 @@ int rast_upload_clipped(b200_ctx *ctx, const rast_triangle *clipped, int n_tris)
   if (ctx->rast_inflight.active) if (int rc = finish_stats(ctx)) return rc;   // a re-render must see its own scene
   int has_shadow = 0;
   for (int i = 0; i < n_tris; ++i) {
-    if (clipped[i].texture != 0) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+    if (clipped[i].texture != 0 && !ctx->rast_tex_on) return ctx_fail(ctx, B200_EINVAL, "texture != 0 needs rast_set_textures");
+    if (clipped[i].texture < 0 || clipped[i].texture > 3) return ctx_fail(ctx, B200_EINVAL, "texture must be 0..3");
     has_shadow |= !(clipped[i].color[0] >= 0);
   }
   ctx->rast_has_shadow = has_shadow;
@@ -556,7 +593,7 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
   tl_mark(ctx, "frame start");
   rast_light_t lc = *light;
   ctx->rast_clear_ptr = nullptr; ctx->rast_keys_cleared = 0; ctx->rast_cull_on = 0; ctx->rast_geom_chunks = 1;
-  const bool to_scatter = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow);
+  const bool to_scatter = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow && !ctx->rast_tex_on);
   if (ctx->rast_up_chunks > 1) {
     if (spec && whole_draw && to_scatter) {
       ctx->rast_geom_chunks = ctx->rast_up_chunks;   // the frame consumes the upload chunk by chunk
@@ -567,7 +604,7 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
   }
   if (!whole_draw) ctx->rast_culled = 0;   // the caller's own list
   if (whole_draw) {
-    if (spec && (ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow))) {
+    if (spec && to_scatter) {
       // the frame is bound for the scatter path: its geometry kernel clears the key rows on the way
       const size_t W = (size_t)cam->width;
       const int fb0 = row_begin - 2 > 0 ? row_begin - 2 : 0, fb1 = row_end + 2 < cam->height ? row_end + 2 : cam->height;

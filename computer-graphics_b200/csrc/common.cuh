@@ -74,6 +74,18 @@ struct DevBuf {
 };
 
 struct b200_multi;   // multi.cu
+// Texture state of the rasteriser (rast_set_textures; device pointers; see rast_tex.cuh)
+struct RastTex {
+  const unsigned char *img[8];
+  int step[8];
+  int marble_rows;             // normalMap_marble is indexed y * marble.rows + x (:593)
+  const float4 *noise;
+  long long noise_len;
+  float cam[4];                // cameraPos
+  float Rinv[16];              // glm::inverse(R), column-major
+  int use_rinv;                // the reference's "yaw != 0" (:1761): R is not the identity
+};
+
 struct b200_ctx {
   b200_multi *multi = nullptr;        // set on a context made by b200_init_multi: it only fans out to one ordinary context per device
   int device = 0;
@@ -136,6 +148,9 @@ struct b200_ctx {
   DevBuf rast_srowsB, rast_srowsL;   // fast path: row records of the small triangles
   DevBuf rast_trimeta, rast_big;   // fast path: per-triangle row-table origin; list of the triangles too big for the small-triangle kernel
   int rast_has_shadow = 0;   // the uploaded list can contain shadow-volume triangles
+  int rast_tex_on = 0;       // rast_set_textures: texture / index fields are honoured, frames take the ordered path
+  RastTex rast_tex{};
+  DevBuf rast_tex_images, rast_tex_noise;
   int opt_rast_path = 0;     // 0 auto, 1 ordered tiles, 2 scatter (shadow-free lists only)
   DevBuf rast_chunks;    // owner triangle of each 8-row chunk of the row tables
   DevBuf rast_world;     // tier 2: world-space room then boxes, as uploaded
@@ -229,6 +244,7 @@ int rt_launch(b200_ctx *ctx, const RtFrame &f, float *d_rgb, float *d_depth, int
 void multi_destroy(b200_ctx *ctx);
 int multi_synchronize(b200_ctx *ctx);
 int multi_set_option(b200_ctx *ctx, int option, int value);
+int multi_rast_set_textures(b200_ctx *ctx, const rast_textures_t *tex);
 int multi_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_sphere *spheres, int n_spheres,
                    const camera_t *cam, const light_t *lights, int n_lights, int row_begin, int row_end,
                    float *rgb_out, float *depth_out, int32_t *index_out, uint32_t *argb_out);

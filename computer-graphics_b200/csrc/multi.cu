@@ -302,6 +302,11 @@ int multi_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_
 }
 
 // ---- rasteriser -------------------------------------------------------------------------
+// Every device keeps its own copy of the images (each over its own PCIe link).
+int multi_rast_set_textures(b200_ctx *ctx, const rast_textures_t *tex) {
+  return multi_run(ctx, [&](int i) -> int { return rast_set_textures(ctx->multi->child[i], tex); });
+}
+
 int rast_band_resident(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row_begin, int row_end,
                        float *rgb_out, float *depth_out, int32_t *index_out, uint32_t *argb_out);   // api.cu
 

@@ -340,8 +340,11 @@ constexpr int RS_FW = RS_W + 4, RS_FH = RS_H + 4;                               
 // ordered-tile path's per-pixel result (rast_fill_kernel with p.fused: depth bits << 32 | winner + 1,
 // and a shadow flag per pixel) -- the same pass then also does the shadow softening of the post pass
 // (:286-303), so that path keeps no colour buffers in HBM either.
-template <bool ORDERED>
+// TEX (ordered path only): the winners' texture / index fields are honoured (rast_tex.cuh); the depth
+// word is then not the winner's zinv (holes, :619 / :643), which is recomputed from the row record.
+template <bool ORDERED, bool TEX>
 __global__ void __launch_bounds__(RS_W * RS_H, 2048 / (RS_W * RS_H)) rast_resolve_kernel(const __grid_constant__ RastParams p) {
+  static_assert(ORDERED || !TEX, "textures are drawn by the ordered path");
   __shared__ float col[9][RS_N];            // [screen rgb, low rgb, high rgb][position]: conflict-free taps
   __shared__ float zinv_s[RS_N];            // the winner's zinv (:665); 0 = empty
   __shared__ int owner[RS_N];
@@ -407,12 +410,19 @@ __global__ void __launch_bounds__(RS_W * RS_H, 2048 / (RS_W * RS_H)) rast_resolv
     int t;
     float4 B;
     int lx;
+    float zinv_tex = 0.f;
     if (ORDERED) {
       t = owner[pos];
       const RastSetup *su = p.setup + t;
       const unsigned rr = su->row_off + (unsigned)(gy - su->row0);
       B = __ldg(p.rowsB + rr);
-      lx = __float_as_int(__ldg(&p.rowsA[rr].x));
+      if (TEX) {
+        const float4 A = __ldg(p.rowsA + rr);
+        lx = __float_as_int(A.x);
+        zinv_tex = xadd(A.z, xmul(A.w, (float)(gx - lx)));          // :543 again: a later hole may have cleared the depth
+      } else {
+        lx = __float_as_int(__ldg(&p.rowsA[rr].x));
+      }
     } else {
       const unsigned low = (unsigned)owner[pos], code = low & 31u;
       t = (int)(low >> 5);
@@ -428,20 +438,11 @@ __global__ void __launch_bounds__(RS_W * RS_H, 2048 / (RS_W * RS_H)) rast_resolv
       }
     }
     const float fi = (float)(gx - lx);
-    const float zinv = zinv_s[pos];                                 // as the scatter / fold computed it (:543)
+    const float zinv = TEX ? zinv_tex : zinv_s[pos];                // as the scatter / fold computed it (:543)
     const float pz = xdiv(1.0f, zinv);                              // :546
     const float px = xdiv(xadd(B.x, xmul(B.y, fi)), zinv);          // :547
     const float py = xdiv(xadd(B.z, xmul(B.w, fi)), zinv);          // :548
-    const float *tr = reinterpret_cast<const float *>(p.src + t);   // normal at words 12..14, colour at 16..18
-    float D[3];
-    rast_illum_D(p, px, py, pz, __ldg(tr + 12), __ldg(tr + 13), __ldg(tr + 14), D);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float cc = __ldg(tr + 16 + c);
-      col[c][pos] = xmul(cc, xadd(D[c], rast_indirect(p, c, t, (size_t)gy * p.W + gx)));   // :580
-      col[3 + c][pos] = xmul(cc, xadd(D[c], 0.0f));                 // :581-582
-      col[6 + c][pos] = xmul(cc, xadd(D[c], 0.4f));                 // :583-584
-    }
+    rast_shade<TEX>(p, t, gx, gy, px, py, pz, &col[0][pos], RS_N);  // :575-586 (TEX: :588-645)
   }
   __syncthreads();
 

@@ -27,7 +27,8 @@ struct GeomParams {
   unsigned *offs;       // [n_pre + 1] exclusive scan, total at [n_pre]
   rast_triangle *out;
   unsigned out_cap;
-  unsigned long long *flags;   // bit0: a triangle with texture != 0, bit1: a shadow-coloured input triangle
+  unsigned long long *flags;   // bit0: a triangle whose texture field cannot be drawn (see tex_on), bit1: a shadow-coloured input triangle
+  int tex_on;                  // rast_set_textures: texture 1..3 are drawn; otherwise only 0 is accepted
   // single-pass mode (pipelined frames): chained scan over the blocks
   unsigned *ticket;            // hands out block ids in scheduling order (forward progress of the look-back)
   unsigned long long *desc;    // per block: state << 62 | value; state 1 = block sum, 2 = inclusive prefix
@@ -97,7 +98,8 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
   cur[0] = t;
   if (!all_in) n_cur = clip_six_planes(p.x.W, p.x.H, p.x.focal, cur);
   if (MODE != 1 && j < n_pre) {
-    if (__float_as_int(attr[7]) != 0) atomicOr(p.flags, 1ull);
+    const int texture = __float_as_int(attr[7]);
+    if (texture != 0 && (!p.tex_on || texture < 0 || texture > 3)) atomicOr(p.flags, 1ull);
     if (s == 0 && !(attr[4] >= 0.0f)) atomicOr(p.flags, 2ull);
   }
   if (MODE == 0) {
@@ -351,6 +353,7 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
   const size_t chain_off = (tmp_words * sizeof(unsigned) + 15) / 16 * 16;        // then: ticket (16 B), block descriptors
   if (int rc = ensure(ctx, ctx->rast_geom_tmp, chain_off + 16 + sizeof(unsigned long long) * (size_t)(n_blocks + 1))) return rc;
   p.flags = (unsigned long long *)ctx->counters.p + 7;
+  p.tex_on = ctx->rast_tex_on;
   p.counts = (unsigned *)ctx->rast_geom_tmp.p;
   p.offs = p.counts + (n_pre + 1);
   p.ticket = (unsigned *)((char *)ctx->rast_geom_tmp.p + chain_off);
@@ -413,7 +416,7 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
       CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
       const unsigned long long flags = hc[7];
       total = (unsigned)hc[24];
-      if (flags & 1ull) return ctx_fail(ctx, B200_EINVAL, "only texture == 0 is supported");
+      if (flags & 1ull) return ctx_fail(ctx, B200_EINVAL, "texture != 0 needs rast_set_textures and must be 1..3");
       ctx->rast_has_shadow = (n_boxes > 0 || (flags & 2ull)) ? 1 : 0;
     }
   }

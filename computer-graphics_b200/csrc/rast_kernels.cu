@@ -29,6 +29,7 @@
 //   rast_post_kernel   shadow softening + 5-tap AA + "HDR" mean (:283-307)
 #include "common.cuh"
 #include <limits.h>
+#include "rast_tex.cuh"
 
 constexpr int RAST_LIST_CAP = 2048;   // tile list entries sorted in shared memory
 constexpr int RAST_BATCH = 32;        // triangles per shared-memory row batch
@@ -108,6 +109,8 @@ struct RastParams {
   float *out_depth;
   int *out_index;
   uint32_t *out_argb;
+  int tex_on;        // rast_set_textures: the triangles' texture / index fields are honoured (ordered path only)
+  RastTex tex;
   unsigned long long *counters;  // [3] bin entries, [4] rows, [5] overflow flag, [6] row chunks, [9] first shaded fragment, [10] big triangles, [11] their rows (counting pass), second cache line: [16] fragments (updated while [6] is read), [24] list length (read while [4]/[6] are updated)
 };
 
@@ -406,13 +409,22 @@ __global__ void rast_first_fragment_kernel(const __grid_constant__ RastParams p,
   const int xmin = min(s.v[0].x, min(s.v[1].x, s.v[2].x)) - 1, xmax = max(s.v[0].x, max(s.v[1].x, s.v[2].x));
   if (xmax <= 0 || xmin >= p.W || xmax <= xmin) return;
   s.ymin = ymin;
+  // textures: a hole of a metal-grill / woven-wood triangle is accepted but not shaded (:603, :625) and leaves
+  // the depth buffer clear (:619, :643), so the search goes on behind it
+  const int texture = p.tex_on ? __float_as_int(tr[19]) : 0, index = __float_as_int(tr[20]);
+  const bool holes = texture == 2 || texture == 3;
   for (int y = max(ymin, 0); y <= min(ymax, p.H - 1); ++y) {
     float4 A, B;
-    rast_row_record<false>(s, y, A, B);
+    if (holes) rast_row_record<true>(s, y, A, B);
+    else rast_row_record<false>(s, y, A, B);
     const int lx = __float_as_int(A.x), rx = __float_as_int(A.y);
     for (int x = max(lx, 0); x < min(rx, p.W); ++x) {
-      const float zinv = xadd(A.z, xmul(A.w, (float)(x - lx)));
+      const float fi = (float)(x - lx);
+      const float zinv = xadd(A.z, xmul(A.w, fi));
       if (zinv >= 0.0f) {
+        if (holes && rast_tex_hole(p.tex, texture, index, xdiv(xadd(B.x, xmul(B.y, fi)), zinv),
+                                   xdiv(xadd(B.z, xmul(B.w, fi)), zinv), xdiv(1.0f, zinv)))
+          continue;
         atomicMin(first, ((unsigned long long)(unsigned)t << 32) | (unsigned long long)((size_t)y * p.W + x));
         return;
       }
@@ -540,6 +552,42 @@ __device__ __forceinline__ void rast_illum_D(const RastParams &p, float x, float
   for (int k = 0; k < 3; ++k) D[k] = xdiv(xmul(p.power[k], m), den);
 }
 
+// ---- PixelShader's colour writes for the fragment of triangle t at pixel (gx, gy), position (px, py, pz):
+// screenBuffer / lowLightBuffer / highLightBuffer (:578-586; TEX: :588-645, see rast_tex.cuh) ----
+template <bool TEX>
+__device__ __forceinline__ void rast_shade(const RastParams &p, int t, int gx, int gy, float px, float py, float pz,
+                                           float *out, int stride) {   // out[(3 * b + c) * stride]: buffer b (screen, low, high), channel c
+  const float *tr = reinterpret_cast<const float *>(p.src + t);   // normal at words 12..14, colour at 16..18, texture 19, index 20
+  float colour[3], normal[3];
+  float occlusion = 1.0f;
+  int texture = 0;
+  float D[3];
+  if (TEX) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { colour[c] = __ldg(tr + 16 + c); normal[c] = __ldg(tr + 12 + c); }
+    texture = __float_as_int(__ldg(tr + 19));
+    if (texture != 0) rast_tex_material(p.tex, texture, __float_as_int(__ldg(tr + 20)), px, py, pz, gx, gy, colour, normal, occlusion);
+    rast_illum_D(p, px, py, pz, normal[0], normal[1], normal[2], D);
+  } else {
+    rast_illum_D(p, px, py, pz, __ldg(tr + 12), __ldg(tr + 13), __ldg(tr + 14), D);
+  }
+  const size_t q = (size_t)gy * p.W + gx;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float cc = TEX ? colour[c] : __ldg(tr + 16 + c);
+    const float a = xadd(D[c], rast_indirect(p, c, t, q)), b = xadd(D[c], 0.0f), h = xadd(D[c], 0.4f);   // :580-584
+    if (TEX && texture == 3) {   // :634-638: textureColour * (illumination * occlusion)
+      out[c * stride] = xmul(cc, xmul(a, occlusion));
+      out[(3 + c) * stride] = xmul(cc, xmul(b, occlusion));
+      out[(6 + c) * stride] = xmul(cc, xmul(h, occlusion));
+    } else {
+      out[c * stride] = xmul(cc, a);
+      out[(3 + c) * stride] = xmul(cc, b);
+      out[(6 + c) * stride] = xmul(cc, h);
+    }
+  }
+}
+
 // In-place ascending sort of a tile's list in global memory when it does not fit
 // in shared memory: LSD radix sort, one bit per pass (a stable split), by the
 // whole block.  Only pathological scenes (> RAST_LIST_CAP triangles over one
@@ -596,12 +644,16 @@ __device__ void rast_sort_global(int *a, int *tmp, int n, int max_key, unsigned 
 }
 
 // ---- per-tile fold + deferred shading -------------------------------------------------------
-template <int TS_LOG2>
+template <int TS_LOG2, bool TEX>
 __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __grid_constant__ RastParams p) {
   constexpr int TS = 1 << TS_LOG2, NT = TS * TS, NW = NT / 32;
   __shared__ int list[RAST_LIST_CAP];
   __shared__ float4 recA[RAST_BATCH][TS];
   __shared__ int recFlags[RAST_BATCH];
+  // TEX: texture | index << 8 of the staged triangles, and where their row records are (row_off - row0):
+  // a metal-grill / woven-wood fragment that passes the depth test needs its position for the opacity map
+  __shared__ int recTex[TEX ? RAST_BATCH : 1];
+  __shared__ unsigned recRowBase[TEX ? RAST_BATCH : 1];
   __shared__ unsigned triRows[RAST_BATCH];   // per staged triangle: the tile rows in which its span meets the tile's columns
   __shared__ unsigned rowTris[TS];           // the transpose: per tile row, the staged triangles a pixel of that row has to look at
   __shared__ unsigned scratch[NT + 2];
@@ -684,6 +736,10 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
       const RastSetup *s = p.setup + t;
       const int row0 = s->row0, nrows = s->nrows;
       if (lane == 0) recFlags[b] = s->flags;
+      if (TEX && lane == 0) {
+        recTex[b] = (p.src[t].texture & 0xff) | (p.src[t].index << 8);
+        recRowBase[b] = s->row_off - (unsigned)row0;
+      }
       bool meets = false;
       if (lane < TS) {
         const int yy = (tile_y << TS_LOG2) + lane;
@@ -720,8 +776,24 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
           if (recFlags[b] & 1) {
             if (zinv > depth) shadow = 1;                            // :668-670
           } else if (zinv >= depth) {                                // :574
-            depth = zinv;                                            // :665
-            win = sorted[b0 + b];
+            bool hole = false;
+            if (TEX) {
+              const int texture = recTex[b] & 0xff;
+              if (texture == 2 || texture == 3) {                    // :603, :625: the opacity map decides
+                const float4 B = __ldg(p.rowsB + (recRowBase[b] + (unsigned)y));
+                const float fi = (float)(x - lx);
+                const float pz = xdiv(1.0f, zinv);                              // :546
+                const float px = xdiv(xadd(B.x, xmul(B.y, fi)), zinv);          // :547
+                const float py = xdiv(xadd(B.z, xmul(B.w, fi)), zinv);          // :548
+                hole = rast_tex_hole(p.tex, texture, recTex[b] >> 8, px, py, pz);
+              }
+            }
+            if (hole) {
+              depth = 0.f;                                           // :619 / :643, then :665; the colours stay
+            } else {
+              depth = zinv;                                          // :665
+              win = sorted[b0 + b];
+            }
           }
         }
       }
@@ -745,16 +817,10 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
       const float pz = xdiv(1.0f, zinv);                              // :546
       const float px = xdiv(xadd(B.x, xmul(B.y, fi)), zinv);          // :547
       const float py = xdiv(xadd(B.z, xmul(B.w, fi)), zinv);          // :548
-      const rast_triangle *tr = p.src + win;
-      float D[3];
-      rast_illum_D(p, px, py, pz, tr->normal[0], tr->normal[1], tr->normal[2], D);
+      float o[9];
+      rast_shade<TEX>(p, win, x, y, px, py, pz, o, 1);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float c = tr->color[k];
-        sc[k] = xmul(c, xadd(D[k], rast_indirect(p, k, win, q)));   // :580
-        lo[k] = xmul(c, xadd(D[k], 0.0f));            // :581-582
-        hi[k] = xmul(c, xadd(D[k], 0.4f));            // :583-584
-      }
+      for (int k = 0; k < 3; ++k) { sc[k] = o[k]; lo[k] = o[3 + k]; hi[k] = o[6 + k]; }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { p.screen[3 * q + k] = sc[k]; p.low[3 * q + k] = lo[k]; p.high[3 * q + k] = hi[k]; }
@@ -830,6 +896,59 @@ __global__ void rast_post_kernel(const __grid_constant__ RastParams p) {
 #include "rast_fast.cuh"
 
 // ---- host side ---------------------------------------------------------------------------------
+// glm::inverse(R) as findU / findV compute it per fragment (glm 0.9.7.2 detail/type_mat4x4.inl:37-92; separately
+// rounded products and differences: the reference build has no FMA), and the reference's `yaw != 0` (:1761):
+// R is the identity exactly when yaw is 0 (:387-396).
+static void rast_tex_view(const float *m_, float *out, int *use_rinv) {
+  auto M = [&](int c, int r) -> float { return m_[4 * c + r]; };
+  auto sub2 = [](float a, float b, float c, float d) -> float {   // a * b - c * d, three roundings
+    volatile float x = a * b, y = c * d;
+    return x - y;
+  };
+  const float Coef00 = sub2(M(2, 2), M(3, 3), M(3, 2), M(2, 3)), Coef02 = sub2(M(1, 2), M(3, 3), M(3, 2), M(1, 3)),
+              Coef03 = sub2(M(1, 2), M(2, 3), M(2, 2), M(1, 3)), Coef04 = sub2(M(2, 1), M(3, 3), M(3, 1), M(2, 3)),
+              Coef06 = sub2(M(1, 1), M(3, 3), M(3, 1), M(1, 3)), Coef07 = sub2(M(1, 1), M(2, 3), M(2, 1), M(1, 3)),
+              Coef08 = sub2(M(2, 1), M(3, 2), M(3, 1), M(2, 2)), Coef10 = sub2(M(1, 1), M(3, 2), M(3, 1), M(1, 2)),
+              Coef11 = sub2(M(1, 1), M(2, 2), M(2, 1), M(1, 2)), Coef12 = sub2(M(2, 0), M(3, 3), M(3, 0), M(2, 3)),
+              Coef14 = sub2(M(1, 0), M(3, 3), M(3, 0), M(1, 3)), Coef15 = sub2(M(1, 0), M(2, 3), M(2, 0), M(1, 3)),
+              Coef16 = sub2(M(2, 0), M(3, 2), M(3, 0), M(2, 2)), Coef18 = sub2(M(1, 0), M(3, 2), M(3, 0), M(1, 2)),
+              Coef19 = sub2(M(1, 0), M(2, 2), M(2, 0), M(1, 2)), Coef20 = sub2(M(2, 0), M(3, 1), M(3, 0), M(2, 1)),
+              Coef22 = sub2(M(1, 0), M(3, 1), M(3, 0), M(1, 1)), Coef23 = sub2(M(1, 0), M(2, 1), M(2, 0), M(1, 1));
+  const float Fac0[4] = {Coef00, Coef00, Coef02, Coef03}, Fac1[4] = {Coef04, Coef04, Coef06, Coef07},
+              Fac2[4] = {Coef08, Coef08, Coef10, Coef11}, Fac3[4] = {Coef12, Coef12, Coef14, Coef15},
+              Fac4[4] = {Coef16, Coef16, Coef18, Coef19}, Fac5[4] = {Coef20, Coef20, Coef22, Coef23};
+  const float Vec0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)}, Vec1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)},
+              Vec2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)}, Vec3[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+  const float SignA[4] = {+1, -1, +1, -1}, SignB[4] = {-1, +1, -1, +1};
+  auto inv3 = [&](const float *a, const float *fa, const float *b, const float *fb, const float *c, const float *fc, int k) -> float {
+    volatile float t = sub2(a[k], fa[k], b[k], fb[k]), u = c[k] * fc[k];   // (a * fa - b * fb) + c * fc
+    return t + u;
+  };
+  float Inv[16];
+  for (int k = 0; k < 4; ++k) {
+    Inv[0 + k] = inv3(Vec1, Fac0, Vec2, Fac1, Vec3, Fac2, k) * SignA[k];
+    Inv[4 + k] = inv3(Vec0, Fac0, Vec2, Fac3, Vec3, Fac4, k) * SignB[k];
+    Inv[8 + k] = inv3(Vec0, Fac1, Vec1, Fac3, Vec3, Fac5, k) * SignA[k];
+    Inv[12 + k] = inv3(Vec0, Fac2, Vec1, Fac4, Vec2, Fac5, k) * SignB[k];
+  }
+  volatile float d0 = M(0, 0) * Inv[0], d1 = M(0, 1) * Inv[4], d2 = M(0, 2) * Inv[8], d3 = M(0, 3) * Inv[12];
+  volatile float s01 = d0 + d1, s23 = d2 + d3;
+  const float det = s01 + s23;
+  const float one_over = 1.0f / det;
+  for (int k = 0; k < 16; ++k) out[k] = Inv[k] * one_over;
+  *use_rinv = 0;
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r)
+      if (m_[4 * c + r] != (c == r ? 1.0f : 0.0f)) *use_rinv = 1;
+}
+
+// host logic, callable without a device (CPU tests compare it with the oracle's restatement)
+extern "C" int b200_debug_rast_inverse(const float *R16, float *out16, int *use_rinv) {
+  if (!R16 || !out16 || !use_rinv) return B200_EINVAL;
+  rast_tex_view(R16, out16, use_rinv);
+  return B200_OK;
+}
+
 int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row0, int row1,
                 float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb, bool spec) {
   // n is the list length, or in a pipelined whole-Draw frame the bound the geometry stage wrote under
@@ -858,7 +977,14 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (ctx->opt_rast_path == 2 && ctx->rast_has_shadow)
     return ctx_fail(ctx, B200_EINVAL, "the scatter path cannot draw shadow-volume triangles");
   if (ctx->opt_rast_path == 2 && n >= RAST_FAST_MAX_TRIS) return ctx_fail(ctx, B200_EINVAL, "too many triangles for the scatter path");
-  const bool fast = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow && n < RAST_FAST_MAX_TRIS);
+  if (ctx->opt_rast_path == 2 && ctx->rast_tex_on) return ctx_fail(ctx, B200_EINVAL, "the scatter path cannot draw textures (holes are order dependent)");
+  const bool fast = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow && !ctx->rast_tex_on && n < RAST_FAST_MAX_TRIS);
+  p.tex_on = ctx->rast_tex_on;
+  if (ctx->rast_tex_on) {
+    p.tex = ctx->rast_tex;
+    memcpy(p.tex.cam, cam->pos, sizeof p.tex.cam);
+    rast_tex_view(cam->R, p.tex.Rinv, &p.tex.use_rinv);
+  }
   p.fast = fast ? 1 : 0;
   p.out_rgb = d_rgb; p.out_depth = d_depth; p.out_index = d_index; p.out_argb = d_argb;
   p.counters = (unsigned long long *)ctx->counters.p;
@@ -996,7 +1122,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
       p.row1 = band_slice_edge(row0, row1 - row0, i + 1, k, RS_H);
       if (p.row1 <= p.row0) continue;
       dim3 rg((W + RS_W - 1) / RS_W, (p.row1 - p.row0 + RS_H - 1) / RS_H);
-      rast_resolve_kernel<false><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
+      rast_resolve_kernel<false, false><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
       ctx->stats.kernel_launches++;
       tl_mark(ctx, "rast_resolve_kernel");
       CU_CHECK(ctx, cudaGetLastError());
@@ -1089,10 +1215,18 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   }
   if (n > 0 && bin_cap > 0 && !bits) rast_spread_launch(ctx, p, 2);
   dim3 grid(p.tiles_x, p.tiles_y);
-  switch (ts) {
-    case 3: rast_fill_kernel<3><<<grid, 64, 0, ctx->stream>>>(p); break;
-    case 4: rast_fill_kernel<4><<<grid, 256, 0, ctx->stream>>>(p); break;
-    default: rast_fill_kernel<5><<<grid, 1024, 0, ctx->stream>>>(p); break;
+  if (p.tex_on) {
+    switch (ts) {
+      case 3: rast_fill_kernel<3, true><<<grid, 64, 0, ctx->stream>>>(p); break;
+      case 4: rast_fill_kernel<4, true><<<grid, 256, 0, ctx->stream>>>(p); break;
+      default: rast_fill_kernel<5, true><<<grid, 1024, 0, ctx->stream>>>(p); break;
+    }
+  } else {
+    switch (ts) {
+      case 3: rast_fill_kernel<3, false><<<grid, 64, 0, ctx->stream>>>(p); break;
+      case 4: rast_fill_kernel<4, false><<<grid, 256, 0, ctx->stream>>>(p); break;
+      default: rast_fill_kernel<5, false><<<grid, 1024, 0, ctx->stream>>>(p); break;
+    }
   }
   ctx->stats.kernel_launches++;
   tl_mark(ctx, "rast_fill_kernel");
@@ -1104,7 +1238,8 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     if (p.row1 <= p.row0) continue;
     dim3 pb(32, 8), pg((W + 31) / 32, (p.row1 - p.row0 + 7) / 8);
     const dim3 rg((W + RS_W - 1) / RS_W, (p.row1 - p.row0 + RS_H - 1) / RS_H);
-    if (fused) rast_resolve_kernel<true><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
+    if (fused && p.tex_on) rast_resolve_kernel<true, true><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
+    else if (fused) rast_resolve_kernel<true, false><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
     else rast_post_kernel<<<pg, pb, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     tl_mark(ctx, fused ? "rast_resolve_kernel<ordered>" : "rast_post_kernel");

@@ -65,8 +65,10 @@ typedef struct rast_triangle {
   float v0[4], v1[4], v2[4];
   float normal[4];
   float color[3];  /* color[0] < 0 marks a shadow-volume triangle (:1705)    */
-  int32_t texture; /* only 0 (untextured) is supported                       */
-  int32_t index;   /* only read by the reference's texture code              */
+  int32_t texture; /* 0 untextured, 1 marble, 2 metal grill, 3 woven wood
+                    * (TestModelH.h:21-22); non-zero needs rast_set_textures  */
+  int32_t index;   /* object the texture is laid over (TestModelH.h:23-24): 0
+                    * back, 1 ceiling, 2 floor, 3 left wall, 4 right wall     */
 } rast_triangle;
 
 /* RT globals cameraPos / focalLength / R (skeleton.cpp:56-60) and RAST globals
@@ -256,6 +258,43 @@ int render_raster_band(b200_ctx *ctx, const rast_triangle *room, int n_room,
                        const rast_triangle *boxes, int n_boxes, const camera_t *cam,
                        const rast_light_t *light, int row_begin, int row_end, float *rgb_out,
                        float *depth_out, int32_t *index_out);
+
+/* ---- RAST textures: PixelShader's texture branches (skeleton.cpp:588-645) --------------
+ * The reference's main() decodes eight image files with OpenCV into cv::Mat globals
+ * (:63-75, :133-155) and draws normalMap_marble from rand() (:157-168); PixelShader then
+ * reads pixels, at<T>(findU, findV).  The library takes exactly that state: DECODED images
+ * (decoding stays with the caller), addressed like cv::Mat -- `rows` x `step` bytes,
+ * at<T>(r, c) = *(T *)(data + r * step + c * sizeof(T)). */
+typedef struct rast_image_t {
+  const uint8_t *data; /* host memory; copied by rast_set_textures           */
+  int32_t rows, cols;
+  int32_t step;        /* bytes per row (cols * channels when continuous)    */
+} rast_image_t;
+typedef struct rast_textures_t {
+  rast_image_t marble;          /* `marble` :64, read as Vec3b (BGR) at (findU(p, 2000), findV(p, 2000)) */
+  const float *marble_noise;    /* `normalMap_marble` :75: vec4 per entry, added to the normal (:593)    */
+  int64_t marble_noise_len;     /* entries; indexed y * marble.rows + x of the SCREEN pixel              */
+  rast_image_t grill;           /* `metalGrill` :70 (Vec3b)                                               */
+  rast_image_t grill_opacity;   /* `metalGrillOpacity` after cv::threshold (:152): uchar, 255 = solid    */
+  rast_image_t grill_normal;    /* `metalGrillNormalMap` :72 (Vec3b)                                      */
+  rast_image_t woven;           /* `woven` :65 (Vec3b)                                                    */
+  rast_image_t woven_occlusion; /* `woven_ambientOcclusion` :66, read as uchar at byte column findV (:626) */
+  rast_image_t woven_opacity;   /* `woven_opacity` after cv::threshold (:155): uchar                      */
+  rast_image_t woven_normal;    /* `wovenNormal` :68 (Vec3b)                                              */
+} rast_textures_t;
+/* Copies the images to the device(s) of the context; from then on the `texture` / `index` fields
+ * of the triangles are honoured (without textures set, a list with texture != 0 is refused with
+ * B200_EINVAL) and every raster frame is drawn by the ordered path: a metal-grill / woven-wood
+ * fragment whose opacity is not 255 passes the depth test, keeps the pixel's colours and sets its
+ * depth back to 0 (:619, :643, :665), which only an in-order fold reproduces.  The marble must be
+ * at least 2000 x 2000 and the others 1024 x 1024 (the sizes findU / findV are called with).
+ * findU / findV use cam->pos and glm::inverse(cam->R) (the reference's `yaw != 0` branch is taken
+ * when cam->R is not the identity).  Where the reference reads outside an image (negative
+ * findU / findV, normalMap_marble on screens taller than the marble) the coordinate wraps /
+ * the index is clamped.  NULL switches textures off again.
+ * Colour modes 1 and 2 (randColourSelect, :647-662) draw three rand() values per accepted
+ * fragment in serial fragment order and are not provided. */
+int rast_set_textures(b200_ctx *ctx, const rast_textures_t *textures);
 
 /* screen->buffer of the whole rasteriser Draw. */
 int draw_raster(b200_ctx *ctx, const rast_triangle *room, int n_room,

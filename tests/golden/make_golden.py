@@ -90,6 +90,28 @@ def make_rast():
     print("rast goldens written")
 
 
+def make_rast_textured():
+    """The compiled reference's whole Draw with its texture branches (skeleton.cpp:588-645) on the
+    synthetic images of helpers.synthetic_textures(seed): the settings the reference ships with (2, 1)
+    straight on, and (3, 2) through the `yaw != 0` branch of findU / findV."""
+    W, H, f, seed = 64, 48, 30.0, 7
+    tex = h.synthetic_textures(seed)
+    for tag, setting, setting_boxes, cam, yaw in [("a", 2, 1, h.DEFAULT_RAST_CAM, 0.0),
+                                                  ("b", 3, 2, (0.1, -0.05, -2.6, 1.0), 0.174533)]:
+        R = h.yaw_R(yaw) if yaw else h.identity_R()
+        room, boxes = h.ref_rast_testmodel_tex(setting, setting_boxes, W, H)
+        h.ref_rast_set_textures(W, H, tex, cam, R, yaw)
+        r = h.ref_rast_draw(W, H, f, cam, R, h.DEFAULT_RAST_LIGHT, room, boxes)
+        np.savez_compressed(os.path.join(HERE, f"rast_ref_cornell_tex_{tag}_{W}x{H}.npz"), W=W, H=H, focal=f, seed=seed,
+                            cam=h.f32(*cam), R=R, yaw=yaw, room=room.view(np.uint8), boxes=boxes.view(np.uint8),
+                            **{k: r[k] for k in ("rgb", "argb", "depth", "low", "high", "shadow", "screen_post")})
+    print("textured rast goldens written")
+
+
 if __name__ == "__main__":
-    make_rt()
-    make_rast()
+    if "textured" in sys.argv[1:]:
+        make_rast_textured()
+    else:
+        make_rt()
+        make_rast()
+        make_rast_textured()

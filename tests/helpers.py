@@ -487,7 +487,7 @@ SDLK = {"UP": 0x40000052, "DOWN": 0x40000051, "LEFT": 0x40000050, "RIGHT": 0x400
         **{c: ord(c) for c in "wsadqenmiozxfg12"}}
 
 
-def prog_run(name, frames):
+def prog_run(name, frames, model=None):
     """Runs the reference program `name` (libprog_*.so under oracle/_ref): its own main() with a
     script of key presses, `frames` = one list of key names per frame drawn.  The library is
     loaded from a private copy so that every run starts from the program's initial globals.
@@ -502,6 +502,8 @@ def prog_run(name, frames):
         shutil.copyfile(src, path)
         try:
             lib = ctypes.CDLL(path)
+            if model is not None:   # (setting, settingBoxes) of TestModelH.h:9-10; the images are cv_stub.hpp's
+                lib.prog_set_model(c_i(model[0]), c_i(model[1]))
             keys = np.array([SDLK[k] for fr in frames for k in fr] + [0], np.int32)
             lens = np.array([len(fr) for fr in frames], np.int32)
             shot = np.zeros(3840 * 2160, np.uint32)

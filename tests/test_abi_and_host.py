@@ -256,3 +256,27 @@ def test_multi_gpu_band_split_rule(b200):
     assert edges([0, 1000, 2160], [1.00, 1.03], 2160, 2, 8) == [0, 1000, 2160]
     # unusable history (other frame height): equal split
     assert edges([0, 500, 1000], [1.0, 2.0], 2160, 2, 8)[1] == 1080
+
+
+def test_host_inverse_of_R_is_the_oracle_restatement_of_glm_inverse(b200):
+    """findU / findV multiply by glm::inverse(R) (rasteriser/Source/skeleton.cpp:1761-1763); the library
+    computes it once per frame on the host.  Bit-compared with the oracle's restatement (itself pinned on
+    the unmodified reference by tests/test_oracle_rast.py) on the reference's own rotations and on
+    arbitrary matrices."""
+    lib = b200.load_library()
+    o = h.oracle()
+    rng = np.random.default_rng(5)
+    mats = [h.identity_R()] + [h.yaw_R(np.float32(k) * np.float32(0.174533)) for k in range(-9, 10) if k]
+    mats += [rng.uniform(-2, 2, 16).astype(np.float32) for _ in range(200)]
+    for m in mats:
+        got, want = np.zeros(16, np.float32), np.zeros(16, np.float32)
+        flag = ctypes.c_int(-1)
+        assert lib.b200_debug_rast_inverse(h.ptr(m), h.ptr(got), ctypes.byref(flag)) == 0
+        o.oracle_rast_inverse(h.ptr(m), h.ptr(want))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert flag.value == (0 if np.array_equal(m, h.identity_R()) else 1)
+
+
+def test_texture_structs_match_the_header(b200):
+    assert ctypes.sizeof(b200.RastImage) == 24            # pointer, three int32, padded to 8
+    assert ctypes.sizeof(b200.RastTextures) == 8 * 24 + 16

@@ -156,3 +156,65 @@ def test_indirect_entry_value_reaches_only_the_first_shaded_fragment(entry):
     for key in ("rgb", "screen", "low", "high", "depth"):
         assert np.array_equal(bits(o[key]), bits(r[key])), key
     assert np.count_nonzero((bits(o["screen"]) != bits(s["screen"])).any(axis=-1)) == 1
+
+
+# ---- texture branches (rasteriser/Source/skeleton.cpp:588-645, findU / findV :1756-1825) ----
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_oracle_textures_match_committed_reference_outputs(tag):
+    """Whole textured Draw of the compiled reference (tests/golden/make_golden.py textured) on the
+    synthetic images of helpers.synthetic_textures(seed)."""
+    g = load_golden(f"rast_ref_cornell_tex_{tag}_64x48.npz")
+    W, H = int(g["W"]), int(g["H"])
+    tex = h.synthetic_textures(int(g["seed"]))
+    room, boxes = g["room"].view(h.RAST_TRI), g["boxes"].view(h.RAST_TRI)
+    assert set(np.unique(room["texture"])) | set(np.unique(boxes["texture"])) <= {1, 2, 3}
+    try:
+        h.oracle_rast_set_textures(tex, g["cam"], g["R"], float(g["yaw"]))
+        o = h.oracle_rast_draw(W, H, float(g["focal"]), g["cam"], g["R"], h.DEFAULT_RAST_LIGHT, room, boxes)
+    finally:
+        h.oracle_rast_set_textures(None)
+    for key in ("rgb", "depth", "low", "high", "screen_post"):
+        assert np.array_equal(bits(o[key]), bits(g[key])), key
+    assert np.array_equal(o["shadow"], g["shadow"])
+    assert np.array_equal(o["argb"], g["argb"])
+    assert np.count_nonzero(bits(g["rgb"])) > 1000
+
+
+@pytest.mark.parametrize("setting,setting_boxes,cam,yaw,indirect", [
+    (2, 1, h.DEFAULT_RAST_CAM, 0.0, 0.2), (1, 3, (0.1, -0.05, -2.6, 1.0), 0.174533, 0.2),
+    (3, 2, h.DEFAULT_RAST_CAM, -0.349066, 0.2), (3, 3, (0.0, 0.0, -1.5, 1.0), 0.0, 0.15), (2, 2, h.DEFAULT_RAST_CAM, 0.0, 0.15)])
+def test_oracle_textures_vs_compiled_reference(setting, setting_boxes, cam, yaw, indirect):
+    """Every texture on room and boxes, the `yaw != 0` branch (glm::inverse(R)), holes that clear the
+    depth (:619, :643) and the entry value of the indirect light behind holes, at 320x240."""
+    W, H, f = 320, 240, 120.0
+    if not h.have_ref(h.ref_rast_name(W, H)):
+        pytest.skip("oracle/_ref not built")
+    tex = h.synthetic_textures(11)
+    R = h.yaw_R(yaw) if yaw != 0 else h.identity_R()
+    room, boxes = h.ref_rast_testmodel_tex(setting, setting_boxes, W, H)
+    light = dict(h.DEFAULT_RAST_LIGHT, indirect=(indirect,) * 3)
+    h.ref_rast_set_textures(W, H, tex, cam, R, yaw)
+    ref = h.ref_rast_draw(W, H, f, cam, R, light, room, boxes)
+    try:
+        h.oracle_rast_set_textures(tex, cam, R, yaw)
+        o = h.oracle_rast_draw(W, H, f, cam, R, light, room, boxes)
+    finally:
+        h.oracle_rast_set_textures(None)
+    for key in ("depth", "low", "high", "rgb", "screen_post"):
+        assert np.array_equal(bits(ref[key]), bits(o[key])), key
+    assert np.array_equal(ref["shadow"], o["shadow"])
+    assert np.array_equal(ref["argb"], o["argb"])
+    if setting_boxes in (2, 3):
+        assert np.count_nonzero((o["depth"] == 0) & (o["index"] >= 0)) > 50   # colour kept under a cleared depth
+
+
+def test_oracle_inverse_is_glm_inverse_on_rotations():
+    """R stays a rotation about y (:387-396): inverse = transpose up to rounding; the restated cofactor
+    expansion must at least invert it to float accuracy (its bit pattern is pinned by the tests above)."""
+    lib = h.oracle()
+    for yaw in (0.174533, -0.349066, 1.0, 2.5):
+        R = h.yaw_R(yaw)
+        inv = np.zeros(16, np.float32)
+        lib.oracle_rast_inverse(h.ptr(R), h.ptr(inv))
+        prod = R.reshape(4, 4).T.astype(np.float64) @ inv.reshape(4, 4).T.astype(np.float64)
+        assert np.allclose(prod, np.eye(4), atol=1e-6)
