@@ -168,6 +168,11 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
       ctx->opt_rast_pipelined = value != 0;
       ctx->rast_spec.valid = 0;
       return B200_OK;
+    case B200_OPT_RAST_COLOUR_MODE:
+      if (value < 0 || value > 2) return ctx_fail(ctx, B200_EINVAL, "colour mode must be 0, 1 or 2");
+      ctx->opt_rast_colour = value;
+      ctx->rast_spec.valid = 0;
+      return B200_OK;
     case B200_OPT_RAST_BAND_CULL:
       ctx->opt_rast_band_cull = value != 0;
       ctx->rast_spec.valid = 0;
@@ -572,7 +577,7 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
                     sp.row0 == row_begin && sp.row1 == row_end && sp.ts == ctx->opt_rast_tile_log2 &&
                     sp.fast == ctx->opt_rast_path && sp.n_list == n_list && sp.cull == ctx->opt_rast_band_cull &&
                     (!whole_draw || (sp.n_room == ctx->rast_n_room && sp.n_boxes == ctx->rast_n_boxes));
-  const bool spec = allow_spec && same;
+  const bool spec = allow_spec && same && !ctx->opt_rast_colour;   // a colour-mode frame reads its fragment count back mid-frame
   sp.valid = 0;
   sp.whole_draw = whole_draw ? 1 : 0; sp.W = cam->width; sp.H = cam->height; sp.row0 = row_begin; sp.row1 = row_end;
   sp.ts = ctx->opt_rast_tile_log2; sp.fast = ctx->opt_rast_path; sp.n_list = n_list; sp.cull = ctx->opt_rast_band_cull;
@@ -593,7 +598,7 @@ static int rast_frame(b200_ctx *ctx, bool whole_draw, const camera_t *cam, const
   tl_mark(ctx, "frame start");
   rast_light_t lc = *light;
   ctx->rast_clear_ptr = nullptr; ctx->rast_keys_cleared = 0; ctx->rast_cull_on = 0; ctx->rast_geom_chunks = 1;
-  const bool to_scatter = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow && !ctx->rast_tex_on);
+  const bool to_scatter = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow && !ctx->rast_tex_on && !ctx->opt_rast_colour);
   if (ctx->rast_up_chunks > 1) {
     if (spec && whole_draw && to_scatter) {
       ctx->rast_geom_chunks = ctx->rast_up_chunks;   // the frame consumes the upload chunk by chunk

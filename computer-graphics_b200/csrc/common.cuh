@@ -151,6 +151,8 @@ struct b200_ctx {
   int rast_tex_on = 0;       // rast_set_textures: texture / index fields are honoured, frames take the ordered path
   RastTex rast_tex{};
   DevBuf rast_tex_images, rast_tex_noise;
+  int opt_rast_colour = 0;   // B200_OPT_RAST_COLOUR_MODE: randColourSelect (0, 1 random colours, 2 night vision)
+  DevBuf rast_colour_keys, rast_colour_rgb, rast_colour_tmp;
   int opt_rast_path = 0;     // 0 auto, 1 ordered tiles, 2 scatter (shadow-free lists only)
   DevBuf rast_chunks;    // owner triangle of each 8-row chunk of the row tables
   DevBuf rast_world;     // tier 2: world-space room then boxes, as uploaded
@@ -213,6 +215,7 @@ struct RtFrame {
 constexpr int RT_GRID_AUTO_TRIS = 1024;   // B200_OPT_RT_GRID = 0: scenes this large get direction grids
 
 // spec = true: pipelined (no host synchronisation; see b200_ctx::rast_spec)
+int rast_colour_sort(b200_ctx *ctx, const unsigned long long *in, unsigned long long *out, unsigned long long n, int end_bit);   // rast_colour.cu
 int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, int row0, int row1,
                 float *d_rgb, float *d_depth, int32_t *d_index, uint32_t *d_argb, bool spec);
 int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, rast_light_t *light_out,

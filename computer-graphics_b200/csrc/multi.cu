@@ -321,6 +321,8 @@ int multi_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const ras
   const int rows = row_end - row_begin, n = mc->n;
   std::vector<int> edges;
   multi_band_edges(mc->edges_h[1] == rows ? mc->edges[1] : std::vector<int>(), mc->cost[1], rows, n, 8, edges);
+  const bool colour = mc->child[0]->opt_rast_colour != 0;
+  if (colour) edges.assign(n + 1, rows), edges[0] = 0;   // colour modes number the fragments of the whole frame: one device draws it
   const size_t W = (size_t)cam->width;
   // slices of the room list: device i brings [s_i, s_i+1) over its own PCIe link
   const bool gather = mc->peer_ok && n > 1 && (size_t)n_room * sizeof(rast_triangle) >= ((size_t)1 << 20);
@@ -373,7 +375,7 @@ int multi_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const ras
                               index_out ? index_out + off : nullptr, argb_out ? argb_out + off : nullptr);
   });
   if (rc != B200_OK) return rc;
-  multi_note_cost(mc, 1, edges, rows);
+  if (!colour) multi_note_cost(mc, 1, edges, rows);
   multi_sum_stats(ctx);
   return B200_OK;
 }

@@ -29,6 +29,8 @@
 //   rast_post_kernel   shadow softening + 5-tap AA + "HDR" mean (:283-307)
 #include "common.cuh"
 #include <limits.h>
+#include <stdlib.h>
+#include <vector>
 #include "rast_tex.cuh"
 
 constexpr int RAST_LIST_CAP = 2048;   // tile list entries sorted in shared memory
@@ -111,6 +113,15 @@ struct RastParams {
   uint32_t *out_argb;
   int tex_on;        // rast_set_textures: the triangles' texture / index fields are honoured (ordered path only)
   RastTex tex;
+  // Colour modes 1 / 2 (randColourSelect, :647-662; B200_OPT_RAST_COLOUR_MODE): every ACCEPTED fragment draws three
+  // rand() values, in the serial order of the reference's loops (triangle, row, x).  The fold counts the accepted
+  // fragments ([17]), a second fold emits their keys (triangle << 24 | y << 12 | x), the sorted keys give every
+  // winner its ordinal and colour_rgb[ordinal] is the colour vector the host drew for it.
+  int colour_mode;
+  unsigned long long *colour_emit;          // emit pass: where the keys go (cursor: counters[18]); null otherwise
+  const unsigned long long *colour_sorted;  // resolve: the sorted keys
+  unsigned long long colour_n;
+  const float *colour_rgb;                  // 3 floats per ordinal
   unsigned long long *counters;  // [3] bin entries, [4] rows, [5] overflow flag, [6] row chunks, [9] first shaded fragment, [10] big triangles, [11] their rows (counting pass), second cache line: [16] fragments (updated while [6] is read), [24] list length (read while [4]/[6] are updated)
 };
 
@@ -562,6 +573,24 @@ __device__ __forceinline__ void rast_shade(const RastParams &p, int t, int gx, i
   float occlusion = 1.0f;
   int texture = 0;
   float D[3];
+  if (TEX && p.colour_mode) {
+    // :647-662: randColour / nightVision * calculateIllumination, screenBuffer only; the global indirect light
+    // is not reset in these modes, so every fragment sees the entry value
+    const unsigned long long key = ((unsigned long long)(unsigned)t << 24) | ((unsigned long long)gy << 12) | (unsigned long long)gx;
+    unsigned long long lo_i = 0, hi_i = p.colour_n;
+    while (lo_i < hi_i) {
+      const unsigned long long mid = (lo_i + hi_i) >> 1;
+      if (__ldg(p.colour_sorted + mid) < key) lo_i = mid + 1; else hi_i = mid;
+    }
+    rast_illum_D(p, px, py, pz, __ldg(tr + 12), __ldg(tr + 13), __ldg(tr + 14), D);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      out[c * stride] = xmul(__ldg(p.colour_rgb + 3 * lo_i + c), xadd(D[c], p.indirect[c]));
+      out[(3 + c) * stride] = 0.f;
+      out[(6 + c) * stride] = 0.f;
+    }
+    return;
+  }
   if (TEX) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { colour[c] = __ldg(tr + 16 + c); normal[c] = __ldg(tr + 12 + c); }
@@ -725,7 +754,7 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
   float depth = 0.f;       // depthBuffer cleared to 0 (:247)
   int win = -1;
   int shadow = 0;
-  unsigned n_frag = 0;
+  unsigned n_frag = 0, n_acc = 0;
   const bool on_screen = x < p.W && y < p.H;
   for (int b0 = 0; b0 < cnt; b0 += RAST_BATCH) {
     const int nb = min(RAST_BATCH, cnt - b0);
@@ -778,7 +807,7 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
           } else if (zinv >= depth) {                                // :574
             bool hole = false;
             if (TEX) {
-              const int texture = recTex[b] & 0xff;
+              const int texture = p.colour_mode ? 0 : recTex[b] & 0xff;   // the colour modes never look at it (:575)
               if (texture == 2 || texture == 3) {                    // :603, :625: the opacity map decides
                 const float4 B = __ldg(p.rowsB + (recRowBase[b] + (unsigned)y));
                 const float fi = (float)(x - lx);
@@ -794,10 +823,31 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
               depth = zinv;                                          // :665
               win = sorted[b0 + b];
             }
+            if (TEX && p.colour_mode && y >= p.fb0 && y < p.fb1) {
+              ++n_acc;
+              if (p.colour_emit) {
+                const unsigned m = __activemask();
+                const int leader = __ffs(m) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(p.counters + 18, (unsigned long long)__popc(m));
+                base = __shfl_sync(m, base, leader);
+                const unsigned long long at = base + __popc(m & ((1u << lane) - 1));
+                if (at < p.colour_n)
+                  p.colour_emit[at] = ((unsigned long long)(unsigned)win << 24) | ((unsigned long long)y << 12) | (unsigned long long)x;
+              }
+            }
           }
         }
       }
     }
+  }
+
+  if (TEX && p.colour_emit) return;   // emit pass of a colour-mode frame: the keys are out, the winners are already stored
+  if (TEX && p.colour_mode) {
+    unsigned long long na = n_acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) na += __shfl_xor_sync(0xffffffffu, na, o);
+    if (lane == 0 && na) atomicAdd(p.counters + 17, na);   // (colour-mode frames are always fused: shading needs the ordinals)
   }
 
   // ---- deferred PixelShader of the winning fragment (:575-586) ----
@@ -977,10 +1027,16 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (ctx->opt_rast_path == 2 && ctx->rast_has_shadow)
     return ctx_fail(ctx, B200_EINVAL, "the scatter path cannot draw shadow-volume triangles");
   if (ctx->opt_rast_path == 2 && n >= RAST_FAST_MAX_TRIS) return ctx_fail(ctx, B200_EINVAL, "too many triangles for the scatter path");
-  if (ctx->opt_rast_path == 2 && ctx->rast_tex_on) return ctx_fail(ctx, B200_EINVAL, "the scatter path cannot draw textures (holes are order dependent)");
-  const bool fast = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow && !ctx->rast_tex_on && n < RAST_FAST_MAX_TRIS);
-  p.tex_on = ctx->rast_tex_on;
-  if (ctx->rast_tex_on) {
+  const int colour = ctx->opt_rast_colour;
+  if (ctx->opt_rast_path == 2 && (ctx->rast_tex_on || colour))
+    return ctx_fail(ctx, B200_EINVAL, "the scatter path cannot draw textures or colour modes (both depend on the order of the fragments)");
+  if (colour && (row0 != 0 || row1 != H)) return ctx_fail(ctx, B200_EINVAL, "colour modes 1 / 2 number the fragments of the whole frame: no row bands");
+  if (colour && (W > 4096 || H > 4096)) return ctx_fail(ctx, B200_EINVAL, "colour modes 1 / 2: frames up to 4096 x 4096");
+  const bool fast = ctx->opt_rast_path == 2 || (ctx->opt_rast_path == 0 && !ctx->rast_has_shadow && !ctx->rast_tex_on && !colour && n < RAST_FAST_MAX_TRIS);
+  p.tex_on = ctx->rast_tex_on && !colour;   // the colour modes never look at the texture fields (:575)
+  p.colour_mode = colour;
+  const bool texk = p.tex_on || colour;     // the kernel variants that know about textures / colour modes
+  if (p.tex_on) {
     p.tex = ctx->rast_tex;
     memcpy(p.tex.cam, cam->pos, sizeof p.tex.cam);
     rast_tex_view(cam->R, p.tex.Rinv, &p.tex.use_rinv);
@@ -1009,7 +1065,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
 
   // the entry value of indirectLightPowerPerArea reaches the first shaded fragment only (:585)
   const float steady = 0.2f * 1.0f;
-  if (n > 0 && (memcmp(&light->indirect[0], &steady, 4) || memcmp(&light->indirect[1], &steady, 4) ||
+  if (n > 0 && !colour && (memcmp(&light->indirect[0], &steady, 4) || memcmp(&light->indirect[1], &steady, 4) ||
                 memcmp(&light->indirect[2], &steady, 4))) {
     unsigned long long *first = p.counters + 9;
     CU_CHECK(ctx, cudaMemsetAsync(first, 0xff, sizeof(unsigned long long), ctx->stream));
@@ -1143,7 +1199,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (int rc = ensure(ctx, ctx->rast_tile_count, sizeof(unsigned) * (size_t)(n_tiles + 1) * 3)) return rc;
   // Automatic strategy: fused -- the fold leaves 9 bytes per pixel and the resolve kernel does the
   // rest.  B200_OPT_RAST_PATH = 1 keeps the reference's six intermediate buffers (raster_read_buffers).
-  const bool fused = ctx->opt_rast_path == 0;
+  const bool fused = ctx->opt_rast_path == 0 || colour;
   p.fused = fused ? 1 : 0;
   if (fused) {
     if (int rc = ensure(ctx, ctx->rast_keys, npix * sizeof(unsigned long long))) return rc;
@@ -1215,12 +1271,15 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   }
   if (n > 0 && bin_cap > 0 && !bits) rast_spread_launch(ctx, p, 2);
   dim3 grid(p.tiles_x, p.tiles_y);
-  if (p.tex_on) {
+  auto fill_tex = [&](const RastParams &pp) {
     switch (ts) {
-      case 3: rast_fill_kernel<3, true><<<grid, 64, 0, ctx->stream>>>(p); break;
-      case 4: rast_fill_kernel<4, true><<<grid, 256, 0, ctx->stream>>>(p); break;
-      default: rast_fill_kernel<5, true><<<grid, 1024, 0, ctx->stream>>>(p); break;
+      case 3: rast_fill_kernel<3, true><<<grid, 64, 0, ctx->stream>>>(pp); break;
+      case 4: rast_fill_kernel<4, true><<<grid, 256, 0, ctx->stream>>>(pp); break;
+      default: rast_fill_kernel<5, true><<<grid, 1024, 0, ctx->stream>>>(pp); break;
     }
+  };
+  if (texk) {
+    fill_tex(p);
   } else {
     switch (ts) {
       case 3: rast_fill_kernel<3, false><<<grid, 64, 0, ctx->stream>>>(p); break;
@@ -1231,6 +1290,45 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   ctx->stats.kernel_launches++;
   tl_mark(ctx, "rast_fill_kernel");
   CU_CHECK(ctx, cudaGetLastError());
+  if (colour) {
+    // the accepted fragments in the reference's serial order: count, emit, sort; then the host draws
+    // three rand() values per fragment, exactly as PixelShader would have (:649-651, :657-659)
+    CU_CHECK(ctx, cudaMemcpyAsync(hc, ctx->counters.p, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned long long n_acc = hc[17];
+    if (n_acc > 0x3fffffffull) return ctx_fail(ctx, B200_ENOMEM, "colour modes 1 / 2: too many accepted fragments");
+    const size_t na = (size_t)(n_acc ? n_acc : 1);
+    if (int rc = ensure(ctx, ctx->rast_colour_keys, 2 * na * sizeof(unsigned long long))) return rc;
+    if (int rc = ensure(ctx, ctx->rast_colour_rgb, 3 * na * sizeof(float))) return rc;
+    unsigned long long *keys_a = (unsigned long long *)ctx->rast_colour_keys.p, *keys_b = keys_a + na;
+    if (n_acc) {
+      RastParams pe = p;
+      pe.colour_emit = keys_a;
+      pe.colour_n = n_acc;
+      fill_tex(pe);
+      ctx->stats.kernel_launches++;
+      tl_mark(ctx, "rast_fill_kernel<emit>");
+      CU_CHECK(ctx, cudaGetLastError());
+      int tri_bits = 1;
+      while (tri_bits < 31 && (1ll << tri_bits) < (long long)n) ++tri_bits;
+      if (int rc = rast_colour_sort(ctx, keys_a, keys_b, n_acc, 24 + tri_bits)) return rc;
+      std::vector<float> rgb(3 * (size_t)n_acc);
+      for (size_t i = 0; i < (size_t)n_acc; ++i) {
+        float LO = 0.2f;
+        float HI = 0.5f;
+        float r0 = LO + static_cast<float>(rand()) / (static_cast<float>(RAND_MAX / HI - LO));   // :649-651
+        float r1 = LO + static_cast<float>(rand()) / (static_cast<float>(RAND_MAX / HI - LO));
+        float r2 = LO + static_cast<float>(rand()) / (static_cast<float>(RAND_MAX / HI - LO));
+        if (colour == 1) { rgb[3 * i] = r0; rgb[3 * i + 1] = r1; rgb[3 * i + 2] = r2; }           // :652
+        else { rgb[3 * i] = r0 - 0.2f; rgb[3 * i + 1] = 1.0f; rgb[3 * i + 2] = r2 - 0.2f; }       // :660
+      }
+      CU_CHECK(ctx, cudaMemcpyAsync(ctx->rast_colour_rgb.p, rgb.data(), rgb.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // `rgb` leaves scope
+    }
+    p.colour_sorted = keys_b;
+    p.colour_n = n_acc;
+    p.colour_rgb = (const float *)ctx->rast_colour_rgb.p;
+  }
   const int k = (ctx->slice_host && (size_t)(row1 - row0) * W >= ((size_t)1 << 20)) ? B200_SLICES : 1;
   for (int i = 0; i < k; ++i) {
     p.row0 = band_slice_edge(row0, row1 - row0, i, k, fused ? RS_H : 8);
@@ -1238,7 +1336,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     if (p.row1 <= p.row0) continue;
     dim3 pb(32, 8), pg((W + 31) / 32, (p.row1 - p.row0 + 7) / 8);
     const dim3 rg((W + RS_W - 1) / RS_W, (p.row1 - p.row0 + RS_H - 1) / RS_H);
-    if (fused && p.tex_on) rast_resolve_kernel<true, true><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
+    if (fused && texk) rast_resolve_kernel<true, true><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
     else if (fused) rast_resolve_kernel<true, false><<<rg, RS_W * RS_H, 0, ctx->stream>>>(p);
     else rast_post_kernel<<<pg, pb, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;

@@ -166,6 +166,16 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
  * raster_read_clipped then returns the band's list.  Default 0; on in the per-device contexts
  * of b200_init_multi. */
 #define B200_OPT_RAST_BAND_CULL 8
+/* Rasteriser colour mode = the reference's randColourSelect (skeleton.cpp:81, toggled by SPACE :407):
+ * 0 (default) the shaded / textured colours; 1 random colours; 2 "night vision" (:647-662).  In modes 1
+ * and 2 every ACCEPTED fragment draws three values from the C library's rand(), in the serial order of
+ * the reference's loops; the library numbers the accepted fragments in that order on the device and
+ * then calls rand() itself, three times per fragment, so the pixels AND the process's rand() stream
+ * end up as after the reference's Draw (seed with srand as the reference's process would be).  Only
+ * screenBuffer is written (:653, :661), the texture fields are ignored, and indirectLightPowerPerArea is
+ * not reset (`indirect` applies to every fragment).  Whole frames only (no row bands; a multi-GPU
+ * context draws such frames on its first device). */
+#define B200_OPT_RAST_COLOUR_MODE 9
 int b200_set_option(b200_ctx *ctx, int option, int value);
 
 /* Counters of the last render on this context (b200_get_stats synchronises). */
@@ -291,9 +301,8 @@ typedef struct rast_textures_t {
  * findU / findV use cam->pos and glm::inverse(cam->R) (the reference's `yaw != 0` branch is taken
  * when cam->R is not the identity).  Where the reference reads outside an image (negative
  * findU / findV, normalMap_marble on screens taller than the marble) the coordinate wraps /
- * the index is clamped.  NULL switches textures off again.
- * Colour modes 1 and 2 (randColourSelect, :647-662) draw three rand() values per accepted
- * fragment in serial fragment order and are not provided. */
+ * the index is clamped.  NULL switches textures off again.  (Colour modes 1 and 2: see
+ * B200_OPT_RAST_COLOUR_MODE.) */
 int rast_set_textures(b200_ctx *ctx, const rast_textures_t *textures);
 
 /* screen->buffer of the whole rasteriser Draw. */

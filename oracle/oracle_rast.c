@@ -131,6 +131,7 @@ static o_image g_img[8];
 static const float *g_noise;      /* normalMap_marble, vec4 per entry (:157-168) */
 static long long g_noise_len;
 static int g_tex_on;              /* 0: every triangle is drawn as texture == 0 (no images) */
+static int g_colour_mode;         /* randColourSelect :81 */
 static float g_cam[4], g_Rinv[16];
 static int g_yaw_nonzero;
 
@@ -140,6 +141,9 @@ void oracle_rast_set_image(int which, const uint8_t *data, int rows, int cols, i
 }
 void oracle_rast_set_marble_noise(const float *noise4, long long n) { g_noise = noise4; g_noise_len = n; }
 void oracle_rast_enable_textures(int on) { g_tex_on = on; }
+/* 0, 1 (random colours) or 2 (night vision), :647-662; modes 1 / 2 call the C library's rand() exactly
+ * where PixelShader does (glibc's, like the reference's own build: seed with srand) */
+void oracle_rast_set_colour_mode(int mode) { g_colour_mode = mode; }
 
 /* glm::inverse(mat4), glm 0.9.7.2 detail/type_mat4x4.inl:37-92; m and out column-major, m[4 * c + r] */
 static void mat4_inverse(const float *m_, float *out) {
@@ -246,14 +250,29 @@ static void normal_from_map(const uint8_t *t, float *n) {
   for (int k = 0; k < 3; ++k) n[k] = v[k] * inv;
 }
 
-/* PixelShader :559-672, colour mode 0: texture == 0 (:578-586), marble (:588-599), metal grill (:601-621),
- * woven wood (:623-645).  Colour modes 1 and 2 (:647-662) draw from rand() and are not restated. */
+/* PixelShader :559-672.  Colour mode 0: texture == 0 (:578-586), marble (:588-599), metal grill (:601-621),
+ * woven wood (:623-645); colour modes 1 and 2 (:647-662). */
 static void pixel_shader(o_frame *f, const o_pixel *p, const o_rtri *t, int tri_index) {
   int x = p->x, y = p->y;
   if (x >= 0 && x < f->W && y >= 0 && y < f->H) {
     size_t q = (size_t)y * f->W + x;
     f->fragments++;
-    if (p->zinv >= f->depth[q] && t->color[0] >= 0) {
+    if (p->zinv >= f->depth[q] && t->color[0] >= 0 && g_colour_mode != 0) {
+      /* :647-662: three rand() per accepted fragment; only screenBuffer is written; the texture fields are
+       * not looked at and the global indirect light is not reset */
+      float LO = 0.2f;
+      float HI = 0.5f;
+      float r0 = LO + (float)rand() / ((float)(RAND_MAX / HI - LO));
+      float r1 = LO + (float)rand() / ((float)(RAND_MAX / HI - LO));
+      float r2 = LO + (float)rand() / ((float)(RAND_MAX / HI - LO));
+      float c[3] = {r0, r1, r2};
+      if (g_colour_mode == 2) { c[0] = r0 - 0.2f; c[1] = 1.0f; c[2] = r2 - 0.2f; }
+      float D[3];
+      illumination_D(f, p->pos, t->normal, D);
+      for (int k = 0; k < 3; ++k) f->screen[3 * q + k] = c[k] * (D[k] + f->indirect[k]);
+      if (f->index) f->index[q] = tri_index;
+      f->depth[q] = p->zinv;   /* :665 */
+    } else if (p->zinv >= f->depth[q] && t->color[0] >= 0) {
       const int tex = g_tex_on ? t->texture : 0;
       float zinv = p->zinv;
       float colour[3] = {t->color[0], t->color[1], t->color[2]};

@@ -329,6 +329,23 @@ def oracle_rast_set_textures(tex, cam=None, R=None, yaw=0.0):
     lib.oracle_rast_set_view(ptr(np.asarray(cam, np.float32)), ptr(np.asarray(R, np.float32)), c_i(1 if yaw != 0 else 0))
 
 
+_libc = None
+
+
+def srand(seed):
+    """Seeds the C library's rand() of this process -- shared by the compiled reference, the oracle and the
+    product library (colour modes 1 / 2, rasteriser/Source/skeleton.cpp:647-662)."""
+    global _libc
+    if _libc is None:
+        _libc = ctypes.CDLL(None)
+    _libc.srand(ctypes.c_uint(seed))
+
+
+def rand():
+    srand.__doc__  # (same libc handle)
+    return _libc.rand()
+
+
 def ref_rast_testmodel_tex(setting, setting_boxes, W=64, H=48):
     lib = ref_lib(ref_rast_name(W, H))
     room, boxes = np.zeros(16, RAST_TRI), np.zeros(32, RAST_TRI)
@@ -484,7 +501,7 @@ def scene_soup_rast(n, seed=0x5EED, edge=0.01):
 
 # ---- the reference PROGRAMS (oracle/refbuild/prog_harness.cpp) ---------------------------
 SDLK = {"UP": 0x40000052, "DOWN": 0x40000051, "LEFT": 0x40000050, "RIGHT": 0x4000004F,
-        **{c: ord(c) for c in "wsadqenmiozxfg12"}}
+        **{c: ord(c) for c in "wsadqenmiozxfg12 "}}
 
 
 def prog_run(name, frames, model=None):

@@ -218,3 +218,35 @@ def test_oracle_inverse_is_glm_inverse_on_rotations():
         lib.oracle_rast_inverse(h.ptr(R), h.ptr(inv))
         prod = R.reshape(4, 4).T.astype(np.float64) @ inv.reshape(4, 4).T.astype(np.float64)
         assert np.allclose(prod, np.eye(4), atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("cam,yaw,indirect", [(h.DEFAULT_RAST_CAM, 0.0, 0.2), ((0.1, -0.05, -2.6, 1.0), 0.174533, 0.15)])
+def test_oracle_colour_modes_vs_compiled_reference(mode, cam, yaw, indirect):
+    """randColourSelect = 1 / 2 (:647-662): three rand() per accepted fragment in the order of the reference's
+    loops, screenBuffer only, the entry value of the indirect light on every fragment.  Same seed, same
+    pixels, and the C library's stream ends at the same place."""
+    W, H, f = 320, 240, 120.0
+    if not h.have_ref(h.ref_rast_name(W, H)):
+        pytest.skip("oracle/_ref not built")
+    R = h.yaw_R(yaw) if yaw else h.identity_R()
+    room, boxes = h.ref_rast_testmodel(W, H)
+    light = dict(h.DEFAULT_RAST_LIGHT, indirect=(indirect,) * 3)
+    lib = h.ref_lib(h.ref_rast_name(W, H))
+    try:
+        lib.ref_rast_set_colour_mode(mode)
+        h.srand(99)
+        ref = h.ref_rast_draw(W, H, f, cam, R, light, room, boxes)
+        next_ref = h.rand()
+        h.oracle().oracle_rast_set_colour_mode(mode)
+        h.srand(99)
+        o = h.oracle_rast_draw(W, H, f, cam, R, light, room, boxes)
+        next_o = h.rand()
+    finally:
+        lib.ref_rast_set_colour_mode(0)
+        h.oracle().oracle_rast_set_colour_mode(0)
+    for key in ("depth", "low", "high", "rgb", "screen_post"):
+        assert np.array_equal(bits(ref[key]), bits(o[key])), key
+    assert np.array_equal(ref["shadow"], o["shadow"]) and np.array_equal(ref["argb"], o["argb"])
+    assert next_ref == next_o
+    assert not np.any(o["low"]) and not np.any(o["high"])

@@ -181,3 +181,81 @@ def test_rasteriser_program_with_the_reference_default_textures(size, script):
     assert np.array_equal(got, want), np.count_nonzero(got != want)
     plain = h.prog_run(f"libprog_rast_ref_{size}.so", script)
     assert not np.array_equal(plain, want)     # the textures do show
+
+
+# ---- colour modes 1 / 2 (randColourSelect, :647-662; B200_OPT_RAST_COLOUR_MODE) ----
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("W,H,f,cam_pos,yaw,indirect", [(320, 240, 120.0, h.DEFAULT_RAST_CAM, 0.0, 0.2),
+                                                        (256, 192, 90.0, (0.1, -0.05, -2.6, 1.0), 0.174533, 0.15),
+                                                        (900, 720, 512.0, h.DEFAULT_RAST_CAM, 0.0, 0.2)])
+def test_colour_modes(b200, renderer, mode, W, H, f, cam_pos, yaw, indirect):
+    """Every accepted fragment draws three rand() values in the reference's serial fragment order: the
+    library numbers the accepted fragments on the device and draws from the process's rand() itself.
+    Same seed: same pixels as the oracle (pinned on the unmodified reference), and the C library's stream
+    ends at the same place."""
+    R = h.yaw_R(yaw) if yaw else h.identity_R()
+    room, boxes = cornell(0, 0)
+    light = dict(h.DEFAULT_RAST_LIGHT, indirect=(indirect,) * 3)
+    cam = b200.make_camera(cam_pos, f, R, W, H)
+    L = b200.make_rast_light(light["pos"], light["power"], light["indirect"])
+    try:
+        h.oracle().oracle_rast_set_colour_mode(mode)
+        h.srand(4242)
+        want = h.oracle_rast_draw(W, H, f, cam_pos, R, light, room, boxes)
+        next_want = h.rand()
+        renderer.set_option(b200.OPT_RAST_COLOUR_MODE, mode)
+        h.srand(4242)
+        got = renderer.render_raster(room, boxes, cam, L)
+        next_got = h.rand()
+        with pytest.raises(b200.B200Error):      # the ordinals are those of the whole frame
+            renderer.render_raster(room, boxes, cam, L, row_begin=8, row_end=H)
+    finally:
+        h.oracle().oracle_rast_set_colour_mode(0)
+        renderer.set_option(b200.OPT_RAST_COLOUR_MODE, 0)
+    assert np.array_equal(got["index"], want["index"])
+    assert np.array_equal(bits(got["depth"]), bits(want["depth"]))
+    assert np.array_equal(bits(got["rgb"]), bits(want["rgb"])), np.count_nonzero(bits(got["rgb"]) != bits(want["rgb"]))
+    assert next_got == next_want
+    # and the default mode is back
+    got0 = renderer.render_raster(room, boxes, cam, L)
+    want0 = h.oracle_rast_draw(W, H, f, cam_pos, R, light, room, boxes)
+    assert np.array_equal(bits(got0["rgb"]), bits(want0["rgb"]))
+
+
+def test_colour_modes_ignore_textures_and_clipped_lists(b200, textured, tex):
+    """Tier 1, a random list with shadow triangles; texture fields set and textures loaded: :575 switches on
+    randColourSelect before anything looks at them."""
+    W, H, f = 256, 192, 150.0
+    clipped = h.random_clipped_list(300, 9, W, H, f, shadow_frac=0.2, size=0.6)
+    clipped["texture"] = np.where(clipped["color"][:, 0] < 0, 0, 2)
+    light_cam = h.f32(0.1, -0.4, 1.2, 1.0)
+    cam = b200.make_camera((0, 0, 0, 1), f, h.identity_R(), W, H)
+    L = b200.make_rast_light(light_cam, h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
+    try:
+        h.oracle_rast_set_textures(tex, (0, 0, 0, 1), h.identity_R(), 0.0)
+        h.oracle().oracle_rast_set_colour_mode(1)
+        h.srand(7)
+        want = h.oracle_rast_draw_clipped(W, H, f, light_cam, h.DEFAULT_RAST_LIGHT, clipped)
+        textured.set_option(b200.OPT_RAST_COLOUR_MODE, 1)
+        h.srand(7)
+        got = textured.render_raster_clipped(clipped, cam, L)
+    finally:
+        h.oracle().oracle_rast_set_colour_mode(0)
+        textured.set_option(b200.OPT_RAST_COLOUR_MODE, 0)
+    assert np.array_equal(got["index"], want["index"])
+    assert np.array_equal(bits(got["depth"]), bits(want["depth"]))
+    assert np.array_equal(bits(got["rgb"]), bits(want["rgb"]))
+
+
+def test_rasteriser_program_space_key_cycles_the_colour_modes():
+    """SPACE (:405-408) cycles randColourSelect; frames in modes 1 / 2 draw from rand(), whose stream also fed
+    normalMap_marble at start-up (:157-168, srand(1) in the harness): the drop-in program stays in step with
+    the unmodified one frame after frame."""
+    size = "64x48"
+    for n in (f"libprog_rast_dropin_{size}.so", f"libprog_rast_ref_{size}.so"):
+        if not h.have_ref(n):
+            pytest.skip(f"oracle/_ref/{n} not built")
+    for script in ([["g"] * 95 + [" "]], [["g"] * 95, [" "], ["m"], [" ", "UP"]], [["g"] * 95, [" ", " "], [" "], ["1"]]):
+        got = h.prog_run(f"libprog_rast_dropin_{size}.so", script)
+        want = h.prog_run(f"libprog_rast_ref_{size}.so", script)
+        assert np.array_equal(got, want), (script, np.count_nonzero(got != want))
