@@ -85,3 +85,38 @@ def test_library_multi_context_rasteriser(b200, renderer):
         assert m.stats()["fragments"] >= renderer.stats()["fragments"]      # bands overlap by their 2-row halos
     finally:
         m.close()
+
+
+def test_library_multi_context_textures_and_colour_modes(b200, renderer):
+    """rast_set_textures on a multi-GPU context copies the images to every device; textured frames are
+    shared by row bands like any other, colour-mode frames (whole-frame fragment ordinals) are drawn by
+    the first device.  Equal to the single-device frames bit for bit."""
+    import numpy as np
+    m = _multi(b200)
+    tex = h.synthetic_textures(3)
+    try:
+        room, boxes = h.golden_cornell_rast()
+        room["texture"] = 2
+        boxes["texture"] = 3
+        L = b200.make_rast_light(h.DEFAULT_RAST_LIGHT["pos"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
+        cam = b200.make_camera((0.1, -0.05, -2.6, 1.0), 170.0, h.yaw_R(0.174533), 320, 240)
+        renderer.set_textures(tex)
+        m.set_textures(tex)
+        want = renderer.render_raster(room, boxes, cam, L)
+        for frame in range(3):
+            got = m.render_raster(room, boxes, cam, L)
+            for k in ("rgb", "depth", "index"):
+                assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)), (frame, k)
+        for mode in (1, 2):
+            renderer.set_option(b200.OPT_RAST_COLOUR_MODE, mode)
+            m.set_option(b200.OPT_RAST_COLOUR_MODE, mode)
+            h.srand(5)
+            want = renderer.render_raster(room, boxes, cam, L)
+            h.srand(5)
+            got = m.render_raster(room, boxes, cam, L)
+            for k in ("rgb", "depth", "index"):
+                assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)), (mode, k)
+    finally:
+        renderer.set_option(b200.OPT_RAST_COLOUR_MODE, 0)
+        renderer.set_textures(None)
+        m.close()
