@@ -54,6 +54,8 @@ struct GeomParams {
 // offsets a scan of the counts gave (exact sizes: two passes and a host read-back in between);
 // MODE 2: one pass -- count, block scan, decoupled look-back over the preceding blocks'
 // published sums, write -- into a list whose capacity was guessed (pipelined frames).
+constexpr int GEOM_WARP_MAX_PRE = 8192;   // pre-clip triangles up to which a pipelined frame gives every triangle a warp
+
 template <int MODE>
 __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ GeomParams p) {
   constexpr bool WRITE = MODE != 0;
@@ -222,6 +224,118 @@ __global__ void __launch_bounds__(128) rast_geom_kernel(const __grid_constant__ 
   }
 }
 
+// Short lists -- the reference's own scene is 10 room + 20 box triangles = 150 pre-clip triangles, 120 of them
+// shadow-volume sides that nearly every plane cuts: with one thread per triangle the frame waited 32 us for the
+// longest chain of six planes x up to 32 descendants walked by a single lane out of local memory.  Here one WARP
+// takes a pre-clip triangle and lane i holds descendant i in registers: per plane every lane clips its own
+// triangle (clip_one, the same code), an exclusive prefix of the 0 / 1 / 2 results gives the places in the
+// reference's list order (:236-241: the list is rebuilt plane by plane, each triangle followed by its extra
+// triangle), and the descendants change lanes through shared memory.  Blocks chain their counts through the same
+// decoupled look-back as rast_geom_kernel<2>.  Pipelined frames without band culling / key clearing / chunks.
+constexpr int GW_WARPS = 4;
+__global__ void __launch_bounds__(32 * GW_WARPS) rast_geom_warp_kernel(const __grid_constant__ GeomParams p) {
+  __shared__ float xch[GW_WARPS][12][32];
+  __shared__ unsigned s_bid, s_cnt[GW_WARPS], s_prefix;
+  if (threadIdx.x == 0) s_bid = atomicAdd(p.ticket, 1u);
+  __syncthreads();
+  const int bid = (int)s_bid, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_pre = p.n_room + 7 * p.n_boxes;
+  const int j = bid * GW_WARPS + warp;
+  const int jj = j < n_pre ? j : n_pre - 1;   // tail warps repeat the last triangle, their output is dropped
+  const rast_triangle *srcp;
+  int s = 0;
+  if (jj < p.n_room) srcp = p.room + jj;
+  else { srcp = p.boxes + (jj - p.n_room) / 7; s = (jj - p.n_room) % 7; }
+  GTri mine;
+  float attr[9];   // normal[4], color[3], texture, index (bit-cast)
+  geom_preclip(p.x, srcp, s, mine, attr);      // every lane the same triangle
+  int n_cur = 1;
+  if (!geom_all_in(p.x, mine)) {
+    const float wfar = xdiv(5.0f, p.x.focal);
+    float (*xw)[32] = xch[warp];
+    for (int plane = 1; plane <= 6 && n_cur > 0; ++plane) {
+      ClipCtx c;
+      c.plane = plane; c.W = p.x.W; c.H = p.x.H; c.focal = p.x.focal; c.wfar = wfar;
+      GTri o0, o1;
+      int m = 0;
+      if (lane < n_cur) m = clip_one(c, mine, o0, o1);
+      int incl = m;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31), at = incl - m;
+      __syncwarp();                                   // the previous plane's reads are done
+      auto put = [&](const GTri &g, int k) {
+        xw[0][k] = g.v[0].x; xw[1][k] = g.v[0].y; xw[2][k] = g.v[0].z; xw[3][k] = g.v[0].w;
+        xw[4][k] = g.v[1].x; xw[5][k] = g.v[1].y; xw[6][k] = g.v[1].z; xw[7][k] = g.v[1].w;
+        xw[8][k] = g.v[2].x; xw[9][k] = g.v[2].y; xw[10][k] = g.v[2].z; xw[11][k] = g.v[2].w;
+      };
+      if (m >= 1 && at < 32) put(o0, at);
+      if (m == 2 && at + 1 < 32) put(o1, at + 1);
+      __syncwarp();
+      n_cur = min(total, 32);                         // (five doubling planes: 32 is the reference's own maximum)
+      if (lane < n_cur) {
+        mine.v[0].x = xw[0][lane]; mine.v[0].y = xw[1][lane]; mine.v[0].z = xw[2][lane]; mine.v[0].w = xw[3][lane];
+        mine.v[1].x = xw[4][lane]; mine.v[1].y = xw[5][lane]; mine.v[1].z = xw[6][lane]; mine.v[1].w = xw[7][lane];
+        mine.v[2].x = xw[8][lane]; mine.v[2].y = xw[9][lane]; mine.v[2].z = xw[10][lane]; mine.v[2].w = xw[11][lane];
+      }
+    }
+  }
+  if (lane == 0 && j < n_pre) {
+    const int texture = __float_as_int(attr[7]);
+    if (texture != 0 && (!p.tex_on || texture < 0 || texture > 3)) atomicOr(p.flags, 1ull);
+    if (s == 0 && !(attr[4] >= 0.0f)) atomicOr(p.flags, 2ull);
+  }
+  const unsigned cnt = j < n_pre ? (unsigned)n_cur : 0u;
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  unsigned before = 0, block_sum = 0;
+#pragma unroll
+  for (int w = 0; w < GW_WARPS; ++w) { before += w < warp ? s_cnt[w] : 0u; block_sum += s_cnt[w]; }
+  if (warp == 0) {
+    // decoupled look-back by the whole warp, as in rast_geom_kernel<2> (one sum: nothing is culled here)
+    const unsigned long long VAL = (1ull << 62) - 1, block_val = block_sum;
+    if (lane == 0 && bid > 0) atomicExch(p.desc + bid, (1ull << 62) | block_val);
+    unsigned long long prefix = 0;
+    for (int base = bid - 1;;) {
+      const int k = base - lane;
+      const unsigned long long v = k >= 0 ? atomicAdd(p.desc + k, 0ull) : (2ull << 62);   // "block -1": prefix 0
+      const unsigned state = (unsigned)(v >> 62);
+      const unsigned ready = __ballot_sync(0xffffffffu, state != 0), done = __ballot_sync(0xffffffffu, state == 2);
+      const int first = done ? __ffs(done) - 1 : 31;
+      const unsigned need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+      if ((ready & need) != need) continue;
+      unsigned long long part = lane <= first ? (v & VAL) : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      prefix += part;
+      if (done) break;
+      base -= 32;
+    }
+    if (lane == 0) {
+      atomicExch(p.desc + bid, (2ull << 62) | (prefix + block_val));
+      if (bid == p.n_blocks_total - 1) *p.total = prefix + block_val;   // length of the list
+      s_prefix = (unsigned)prefix;
+    }
+  }
+  __syncthreads();
+  const unsigned off = s_prefix + before + (unsigned)lane;
+  if (j < n_pre && lane < n_cur && off < p.out_cap) {
+    rast_triangle *o = p.out + off;
+    o->v0[0] = mine.v[0].x; o->v0[1] = mine.v[0].y; o->v0[2] = mine.v[0].z; o->v0[3] = mine.v[0].w;
+    o->v1[0] = mine.v[1].x; o->v1[1] = mine.v[1].y; o->v1[2] = mine.v[1].z; o->v1[3] = mine.v[1].w;
+    o->v2[0] = mine.v[2].x; o->v2[1] = mine.v[2].y; o->v2[2] = mine.v[2].z; o->v2[3] = mine.v[2].w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o->normal[k] = attr[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o->color[k] = attr[4 + k];
+    o->texture = __float_as_int(attr[7]);
+    o->index = __float_as_int(attr[8]);
+  }
+}
+
 // Exclusive scan of counts[0..n) into offs[0..n], total at offs[n]: per-block
 // sums, a one-block scan of those, then per-block scans with their offsets.
 constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 4, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
@@ -349,9 +463,12 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
   p.n_boxes = n_boxes;
   const int n_scan_blocks = (n_pre + SCAN_BLOCK - 1) / SCAN_BLOCK;
   const int n_blocks = (n_pre + 127) / 128;
+  const bool short_list = n_pre <= GEOM_WARP_MAX_PRE;   // pipelined frames: a warp per pre-clip triangle (rast_geom_warp_kernel)
+  const int n_blocks_warp = (n_pre + GW_WARPS - 1) / GW_WARPS;
+  const int n_desc = short_list && n_blocks_warp > n_blocks ? n_blocks_warp : n_blocks;
   const size_t tmp_words = 2 * (size_t)(n_pre + 1) + n_scan_blocks + 2;          // counts, offsets, scan scratch
   const size_t chain_off = (tmp_words * sizeof(unsigned) + 15) / 16 * 16;        // then: ticket (16 B), block descriptors
-  if (int rc = ensure(ctx, ctx->rast_geom_tmp, chain_off + 16 + sizeof(unsigned long long) * (size_t)(n_blocks + 1))) return rc;
+  if (int rc = ensure(ctx, ctx->rast_geom_tmp, chain_off + 16 + sizeof(unsigned long long) * (size_t)(n_desc + 1))) return rc;
   p.flags = (unsigned long long *)ctx->counters.p + 7;
   p.tex_on = ctx->rast_tex_on;
   p.counts = (unsigned *)ctx->rast_geom_tmp.p;
@@ -367,7 +484,7 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
     if (int rc = ensure(ctx, ctx->rast_src, sizeof(rast_triangle) * (size_t)cap)) return rc;
     p.out = (rast_triangle *)ctx->rast_src.p;
     p.out_cap = (unsigned)cap;
-    CU_CHECK(ctx, cudaMemsetAsync(p.ticket, 0, 16 + sizeof(unsigned long long) * (size_t)n_blocks, ctx->stream));
+    CU_CHECK(ctx, cudaMemsetAsync(p.ticket, 0, 16 + sizeof(unsigned long long) * (size_t)n_desc, ctx->stream));
     ctx->rast_culled = 0;
     if (ctx->rast_cull_on) {
       if (int rc = ensure(ctx, ctx->rast_orig, sizeof(int) * (size_t)cap)) return rc;
@@ -381,6 +498,15 @@ int rast_geometry(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light,
     // launch per chunk, each behind its chunk's copy; rast_launch scatters chunk k on the second
     // stream while chunk k + 1 is on the link.
     const int chunks = ctx->rast_geom_chunks;
+    if (short_list && !ctx->rast_cull_on && !clear && chunks == 1) {
+      p.n_blocks_total = n_blocks_warp;
+      rast_geom_warp_kernel<<<n_blocks_warp, 32 * GW_WARPS, 0, ctx->stream>>>(p);
+      ctx->stats.kernel_launches++;
+      tl_mark(ctx, "rast_geom_warp_kernel");
+      CU_CHECK(ctx, cudaGetLastError());
+      ctx->rast_n_tris = (int)cap;
+      return B200_OK;
+    }
     p.n_blocks_total = n_blocks;
     for (int c = 0; c < chunks; ++c) {
       const int b0 = chunks > 1 ? ctx->rast_up_edge[c] / 128 : 0;

@@ -460,6 +460,73 @@ __global__ void rast_rows_kernel(const __grid_constant__ RastParams p) {
   p.rowsB[s.row_off + r] = B;
 }
 
+// ---- short lists: everything between the clipped list and the fold in one launch ----------------
+// A list of at most RAST_BITS_MAX_TRIS triangles (the reference's own scene: ~300 clipped triangles, most of them
+// shadow-volume sides that span the screen) went through four dependent launches of a few microseconds of work
+// each -- rast_setup_kernel, two rast_spread_kernel, rast_rows_kernel: 38 of the 114 us of a 900 x 720 frame.
+// Here one block takes a triangle: every thread derives the setup record (VertexShader, the per-edge steps: the
+// same values in every thread), then the threads share out the row records (rast_row_record) and the bits of the
+// screen tiles the bounding box touches.  Row-table space is not claimed but fixed -- triangle t owns rows
+// [t * band, (t + 1) * band) of the table (at most 2048 x band rows) -- so nothing in the block waits.
+// (One block per (triangle, 128 rows) instead of a loop over the rows: measured slower, 22 700 mostly empty
+// blocks at 4K.)
+constexpr int SHORT_THREADS = 256;
+__global__ void __launch_bounds__(SHORT_THREADS) rast_short_kernel(const __grid_constant__ RastParams p) {
+  const int t = (int)blockIdx.x;
+  if (t >= rast_count_tris(p)) return;   // pipelined launches are sized by a bound on the list length
+  float trl[19];                         // v0[4] v1[4] v2[4] normal[4] color[3]
+  {
+    const float *tr = reinterpret_cast<const float *>(p.src + t);
+#pragma unroll
+    for (int k = 0; k < 19; ++k) trl[k] = __ldg(tr + k);
+  }
+  RastSetup s;
+  const bool ok = rast_tri_setup(trl, p.focal, p.W, p.H, s);
+  int nrows = 0, xmin = 0, xmax = -1, row0 = 0, ymin = 0;
+  if (ok) {
+    ymin = min(s.v[0].y, min(s.v[1].y, s.v[2].y));
+    const int ymax = max(s.v[0].y, max(s.v[1].y, s.v[2].y));
+    xmin = min(s.v[0].x, min(s.v[1].x, s.v[2].x)) - 1;   // a minor-axis sample can undershoot by one
+    xmax = max(s.v[0].x, max(s.v[1].x, s.v[2].x));
+    row0 = max(ymin, p.fb0);
+    const int rlast = min(ymax, p.fb1 - 1);
+    nrows = max(0, rlast - row0 + 1);
+    if (xmax <= 0 || xmin >= p.W || xmax <= xmin) nrows = 0;   // no pixel of [xmin, xmax) on screen
+  }
+  s.ymin = ymin; s.row0 = row0; s.nrows = nrows;
+  s.row_off = (unsigned)t * (unsigned)(p.fb1 - p.fb0) + (unsigned)(row0 - p.fb0);
+  s.chunk_off = 0; s.tri = t;
+  s.pad[0] = s.pad[1] = s.pad[2] = 0.f;
+  for (int r = threadIdx.x; r < nrows; r += SHORT_THREADS) {
+    float4 A, B;
+    rast_row_record(s, row0 + r, A, B);
+    p.rowsA[s.row_off + r] = A;
+    p.rowsB[s.row_off + r] = B;
+  }
+  if (threadIdx.x < 32) {   // the 160-byte record leaves as one coalesced word stream (lane k: words k and k + 32)
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(&s);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(p.setup + t);
+#pragma unroll
+    for (int k = 0; k < SETUP_WORDS; ++k)
+      if ((k & 31) == (int)threadIdx.x) dst[k] = w[k];
+  }
+  if (threadIdx.x == 0 && nrows > 0) {   // statistics, and what a later frame of another shape sizes its launches from
+    atomicAdd(p.counters + 4, (unsigned long long)nrows);
+    atomicAdd(p.counters + 6, (unsigned long long)nrows);
+  }
+  if (nrows > 0) {
+    const int ts = p.ts_log2;
+    const int a = max(0, xmin) >> ts;                               // first tile column
+    const int w = (min(p.W - 1, xmax - 1) >> ts) - a + 1;           // tile columns
+    const int c = row0 >> ts;                                       // first tile row
+    const int n = w * (((row0 + nrows - 1) >> ts) - c + 1);
+    for (int k = threadIdx.x; k < n; k += SHORT_THREADS) {
+      const size_t tile = (size_t)(c + k / w - p.ty0) * p.tiles_x + a + k % w;
+      atomicOr(p.tile_bits + tile * p.bits_words + (t >> 5), 1u << (t & 31));
+    }
+  }
+}
+
 // ---- tile lists ---------------------------------------------------------------------------
 __global__ void rast_scan_kernel(const __grid_constant__ RastParams p, int n_tiles) {
   __shared__ unsigned warp_excl[32];
@@ -1193,6 +1260,8 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   if (int rc = ensure(ctx, ctx->rast_chunks, sizeof(int) * chunk_cap)) return rc;
   p.chunk_owner = (int *)ctx->rast_chunks.p;
   p.chunk_cap = (unsigned)(chunk_cap > 0xffffffffull ? 0xffffffffull : chunk_cap);
+  // a short list (bit-per-triangle tile lists, rast_short_kernel): every triangle owns a band's worth of rows
+  if (n <= RAST_BITS_MAX_TRIS) row_cap = (size_t)(n ? n : 1) * (size_t)(p.fb1 - p.fb0);
   if (row_cap > row_budget) row_cap = row_budget;
   if (int rc = ensure(ctx, ctx->rast_rowsA, sizeof(float4) * row_cap)) return rc;
   if (int rc = ensure(ctx, ctx->rast_rowsB, sizeof(float4) * row_cap)) return rc;
@@ -1238,12 +1307,17 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   } else {
     CU_CHECK(ctx, cudaMemsetAsync(p.tile_count, 0, sizeof(unsigned) * (size_t)(n_tiles + 1), ctx->stream));
   }
-  if (n > 0) {
+  if (n > 0 && bits) {
+    // setup, row records and tile bits of a short list
+    rast_short_kernel<<<n, SHORT_THREADS, 0, ctx->stream>>>(p);
+    ctx->stats.kernel_launches++;
+    tl_mark(ctx, "rast_short_kernel");
+  } else if (n > 0) {
     rast_setup_kernel<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     tl_mark(ctx, "rast_setup_kernel");
     if (!p.spread_in_setup) rast_spread_launch(ctx, p, 0);
-    rast_spread_launch(ctx, p, bits ? 3 : 1);
+    rast_spread_launch(ctx, p, 1);
   }
   if (!bits) {
     rast_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p, n_tiles);
@@ -1264,7 +1338,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
   p.bins = (int *)ctx->rast_bins.p;
   p.bins_tmp = (int *)ctx->rast_tmp.p;
   p.bin_cap = (unsigned)(bin_cap > 0xffffffffull ? 0xffffffffull : bin_cap);
-  if (p.n_chunks > 0 && n > 0) {
+  if (p.n_chunks > 0 && n > 0 && !bits) {
     rast_rows_kernel<<<(int)(((size_t)p.n_chunks * RAST_CHUNK + 255) / 256), 256, 0, ctx->stream>>>(p);
     ctx->stats.kernel_launches++;
     tl_mark(ctx, "rast_rows_kernel");
