@@ -649,6 +649,7 @@ __device__ __forceinline__ void rast_shade(const RastParams &p, int t, int gx, i
       const unsigned long long mid = (lo_i + hi_i) >> 1;
       if (__ldg(p.colour_sorted + mid) < key) lo_i = mid + 1; else hi_i = mid;
     }
+    if (lo_i >= p.colour_n) lo_i = p.colour_n - 1;   // (every winner was accepted, so its key is there)
     rast_illum_D(p, px, py, pz, __ldg(tr + 12), __ldg(tr + 13), __ldg(tr + 14), D);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
