@@ -123,6 +123,9 @@ struct b200_ctx {
   int rt_bounds_on_device = 0;
   DevBuf rt_cells;    // direction grids: per-cell counts, cursors, padded counts, offsets, scan scratch
   DevBuf rt_cell_rec, rt_cell_idx;   // the cells' lists: plane records and triangle indices
+  DevBuf rt_cell_pairs;              // (cell, record) pairs written down by the counting pass
+  unsigned long long rt_grid_pairs_seen = 0;   // pairs (or list entries) of the last gridded frame, of a scene of ...
+  int rt_grid_pairs_n = 0;                     // ... this many triangles
   size_t rt_n_cells = 0, rt_n_cam_cells = 0;   // of the last gridded frame (diagnostics)
   int rt_grid_smem_set = 0;                    // the grid kernels' dynamic shared-memory limit has been raised
   int opt_rt_il_n = 1, opt_rt_il_r = 0;        // row-block interleave of rt_render_device (see the header)

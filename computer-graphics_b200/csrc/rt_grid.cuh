@@ -36,6 +36,11 @@ struct RtGridParams {
   float4 *cell_rec;           // [entries][3] plane records
   int *cell_idx;              // [entries] triangle indices
   unsigned long long cap;     // entries allocated
+  // counting pass, optional: every (cell, record) pair it finds is also written down, so that the lists can be
+  // filled by rt_grid_place_kernel from the pairs instead of by a second descent of every triangle
+  uint2 *pairs;               // (cell, origin * n_tris + triangle)
+  unsigned long long pair_cap;
+  unsigned long long *pair_cursor;   // pairs found (may exceed pair_cap: then the lists are filled the old way)
 };
 
 __device__ __forceinline__ float rt_grid_dir0(const RtGridParams &p, int u, int v) {
@@ -104,6 +109,32 @@ __global__ void __launch_bounds__(256) rt_grid_bin_kernel(const __grid_constant_
   if (tri >= p.n_tris) return;
   const float4 *rec = p.planes + (size_t)o * p.origin_stride_f4 + (size_t)tri * RT_REC_F4;
   const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+  // counting pass: the warp's pairs are collected in shared memory and leave with one atomic per warp
+  constexpr int PAIR_BUF = 96;
+  __shared__ unsigned s_pair[FILL ? 1 : 8][FILL ? 1 : PAIR_BUF];
+  unsigned *my_pairs = s_pair[FILL ? 0 : (threadIdx.x >> 5)];
+  int n_pair = 0;                                   // warp-uniform
+  const bool keep_pairs = !FILL && p.pairs != nullptr;
+  auto flush = [&]() {                              // called by the whole warp
+    if (n_pair == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(p.pair_cursor, (unsigned long long)n_pair);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (int i = lane; i < n_pair; i += 32)
+      if (base + i < p.pair_cap) p.pairs[base + i] = make_uint2(my_pairs[i], (unsigned)o * (unsigned)p.n_tris + (unsigned)tri);
+    __syncwarp();
+    n_pair = 0;
+  };
+  // whole warp: `hit` lanes name a cell each
+  auto note = [&](bool hit, unsigned cell) {
+    if (!keep_pairs) return;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (!m) return;
+    if (n_pair + __popc(m) > PAIR_BUF) flush();
+    if (hit) my_pairs[n_pair + __popc(m & ((1u << lane) - 1))] = cell;
+    n_pair += __popc(m);
+  };
 
   auto emit = [&](unsigned cell) {
     if (!FILL) {
@@ -142,8 +173,9 @@ __global__ void __launch_bounds__(256) rt_grid_bin_kernel(const __grid_constant_
 #pragma unroll 1
             for (int r0 = 0; r0 < 2; ++r0) {
               const int bx = X1 + (lane & 7), by = Y1 + r0 * 4 + (lane >> 3);
-              if (bx < p.gx && by < p.gy && rt_grid_test_cam(p, q0, q1, q2, bx, by, bx + 1, by + 1))
-                emit((unsigned)(by * p.gx + bx));
+              const bool hit = bx < p.gx && by < p.gy && rt_grid_test_cam(p, q0, q1, q2, bx, by, bx + 1, by + 1);
+              if (hit) emit((unsigned)(by * p.gx + bx));
+              note(hit, (unsigned)(by * p.gx + bx));
             }
           }
         }
@@ -169,12 +201,30 @@ __global__ void __launch_bounds__(256) rt_grid_bin_kernel(const __grid_constant_
 #pragma unroll 1
           for (int r0 = 0; r0 < 2; ++r0) {
             const int i = X1 + (lane & 7), j = Y1 + r0 * 4 + (lane >> 3);
-            if (rt_grid_test_light(q0, q1, q2, face, i, j, i + 1, j + 1))
-              emit(base + (unsigned)(face * RT_GRID_FACE + j * RT_GRID_G + i));
+            const bool hit = rt_grid_test_light(q0, q1, q2, face, i, j, i + 1, j + 1);
+            if (hit) emit(base + (unsigned)(face * RT_GRID_FACE + j * RT_GRID_G + i));
+            note(hit, base + (unsigned)(face * RT_GRID_FACE + j * RT_GRID_G + i));
           }
         }
       }
     }
+  }
+  if (keep_pairs) flush();
+}
+
+// Fills the cells' lists from the pairs the counting pass wrote down: one thread per pair claims a place in its
+// cell (atomic cursor: the lists are unordered anyway) and copies the 48-byte record and the triangle index.
+__global__ void __launch_bounds__(256) rt_grid_place_kernel(const __grid_constant__ RtGridParams p, unsigned long long n_pairs) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const uint2 pr = __ldg(p.pairs + i);
+  const unsigned o = pr.y / (unsigned)p.n_tris, tri = pr.y - o * (unsigned)p.n_tris;
+  const float4 *rec = p.planes + (size_t)o * p.origin_stride_f4 + (size_t)tri * RT_REC_F4;
+  const unsigned long long e = (unsigned long long)p.cell_off[pr.x] + atomicAdd(p.cell_cursor + pr.x, 1u);
+  if (e < p.cap) {
+    float4 *dst = p.cell_rec + e * RT_REC_F4;
+    dst[0] = __ldg(rec); dst[1] = __ldg(rec + 1); dst[2] = __ldg(rec + 2);
+    p.cell_idx[e] = (int)tri;
   }
 }
 

@@ -266,19 +266,29 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
     g.n_lights = f.n_lights;
     g.cell_cnt = cnt; g.cell_cursor = cursor; g.cell_off = off;
     g.cell_rec = nullptr; g.cell_idx = nullptr; g.cap = 0;
+    // The counting pass also writes its (cell, record) pairs down when the last gridded frame of this context tells
+    // how many to expect (+5 %); the lists are then filled from the pairs instead of by a second descent.
+    unsigned long long *dc = (unsigned long long *)ctx->counters.p;
+    g.pairs = nullptr; g.pair_cap = 0; g.pair_cursor = dc + 15;
+    if (ctx->rt_grid_pairs_seen > 0 && ctx->rt_grid_pairs_n == n) {
+      const unsigned long long want = ctx->rt_grid_pairs_seen + ctx->rt_grid_pairs_seen / 20 + 4096;
+      if (int rc = ensure(ctx, ctx->rt_cell_pairs, sizeof(uint2) * (size_t)want)) return rc;
+      g.pairs = (uint2 *)ctx->rt_cell_pairs.p;
+      g.pair_cap = want;
+      CU_CHECK(ctx, cudaMemsetAsync(g.pair_cursor, 0, sizeof(unsigned long long), ctx->stream));
+    }
     CU_CHECK(ctx, cudaMemsetAsync(cnt, 0, sizeof(unsigned) * 2 * cells, ctx->stream));   // counts and cursors
     const dim3 bgrid((n + 7) / 8, 1 + f.n_lights);
     rt_grid_bin_kernel<false><<<bgrid, 256, 0, ctx->stream>>>(g);
     rt_grid_pad_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(cnt, padded, (int)cells);
     ctx->stats.kernel_launches += 2;
     CU_CHECK(ctx, cudaGetLastError());
-    unsigned long long *dc = (unsigned long long *)ctx->counters.p;
     if (int rc = scan_exclusive(ctx, padded, off, (int)cells, tmp, dc + 9)) return rc;
-    // the lists are sized from the scanned total: one small read-back
+    // the lists are sized from the scanned total: one small read-back ([9] total, [15] pairs written down)
     unsigned long long *hc = (unsigned long long *)ctx->pinned;
-    CU_CHECK(ctx, cudaMemcpyAsync(hc, dc + 9, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(hc, dc + 9, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    const unsigned long long total = hc[0];
+    const unsigned long long total = hc[0], n_pairs = g.pairs ? hc[6] : 0;
     if (total > RT_GRID_MAX_ENTRIES) {
       use_grid = false;   // lists larger than the budget (huge triangles everywhere): stream the scene instead
     } else {
@@ -287,7 +297,13 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
       g.cell_rec = (float4 *)ctx->rt_cell_rec.p;
       g.cell_idx = (int *)ctx->rt_cell_idx.p;
       g.cap = total;
-      rt_grid_bin_kernel<true><<<bgrid, 256, 0, ctx->stream>>>(g);
+      if (g.pairs && n_pairs > 0 && n_pairs <= g.pair_cap)
+        rt_grid_place_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, ctx->stream>>>(g, n_pairs);
+      else
+        rt_grid_bin_kernel<true><<<bgrid, 256, 0, ctx->stream>>>(g);
+      // what the next frame's pair buffer is sized from: the entries of this one (padding included: an upper bound)
+      ctx->rt_grid_pairs_seen = g.pairs && n_pairs > 0 ? n_pairs : total;
+      ctx->rt_grid_pairs_n = n;
       ctx->stats.kernel_launches++;
       CU_CHECK(ctx, cudaGetLastError());
       p.cell_off = off; p.cell_cnt = cnt;
