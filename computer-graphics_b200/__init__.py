@@ -30,6 +30,7 @@ OPT_RT_INTERLEAVE_N = 6
 OPT_RT_INTERLEAVE_R = 7
 OPT_RAST_BAND_CULL = 8
 OPT_RAST_COLOUR_MODE = 9
+OPT_RT_PLAN = 10
 
 RT_TRI = np.dtype([("v0", "<f4", 4), ("v1", "<f4", 4), ("v2", "<f4", 4),
                    ("normal", "<f4", 4), ("color", "<f4", 3)])

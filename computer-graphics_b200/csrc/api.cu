@@ -168,6 +168,10 @@ int b200_set_option(b200_ctx *ctx, int option, int value) {
       ctx->opt_rast_pipelined = value != 0;
       ctx->rast_spec.valid = 0;
       return B200_OK;
+    case B200_OPT_RT_PLAN:
+      ctx->opt_rt_plan = value != 0;
+      ctx->rt_plan_valid = 0;
+      return B200_OK;
     case B200_OPT_RAST_COLOUR_MODE:
       if (value < 0 || value > 2) return ctx_fail(ctx, B200_EINVAL, "colour mode must be 0, 1 or 2");
       ctx->opt_rast_colour = value;

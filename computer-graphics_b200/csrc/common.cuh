@@ -123,6 +123,11 @@ struct b200_ctx {
   int rt_bounds_on_device = 0;
   DevBuf rt_cells;    // direction grids: per-cell counts, cursors, padded counts, offsets, scan scratch
   DevBuf rt_cell_rec, rt_cell_idx;   // the cells' lists: plane records and triangle indices
+  DevBuf rt_plan;                    // gridded frames: two per-block cost arrays, the block plan, its length (rt_plan_kernel)
+  unsigned long long rt_plan_shape = 0;
+  int rt_plan_valid = 0, rt_plan_flip = 0;
+  int opt_rt_plan = 1;               // B200_OPT_RT_PLAN
+  int rt_plan_heavy = 0;             // b200_debug_rt_plan_heavy (0: RT_PLAN_HEAVY)
   DevBuf rt_cell_pairs;              // (cell, record) pairs written down by the counting pass
   unsigned long long rt_grid_pairs_seen = 0;   // pairs (or list entries) of the last gridded frame, of a scene of ...
   int rt_grid_pairs_n = 0;                     // ... this many triangles

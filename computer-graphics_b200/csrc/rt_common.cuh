@@ -24,6 +24,12 @@ struct RtKParams {
   const unsigned *cell_cnt;  // entries in it
   const float4 *cell_rec;    // plane records, list by list
   const int *cell_idx;       // triangle index of each entry
+  // GRID kernels, frames that follow a frame of the same shape: blocks run in the order of `plan` (1-D launch) and
+  // the blocks that were expensive last time are split into eight launches of four pixels per warp (see rt_plan_kernel)
+  const unsigned *plan;      // entry: block x | block row of this launch << 12 | column of the 8 x 4 patches << 24 | split << 27
+  const unsigned *plan_n;    // entries (blocks beyond it leave at once)
+  unsigned *block_cost;      // this frame's cost per block (cycles >> 8 of its slowest warp; x 8 when split), for the next frame's plan
+  int gx;                    // 16-pixel blocks per row of blocks
   // outputs: full-frame addressing (pixel (x, y) at y*W + x); any may be null
   float *rgb;
   float *depth;

@@ -260,11 +260,28 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
   __shared__ int s_seen_all[GRID ? NRING * RT_SEEN : 1];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // which 16 x 16 pixel block: the launch's own coordinates, or (GRID, planned frames) what the plan says
+  int bx = (int)blockIdx.x, by = (int)blockIdx.y, sub = -1;
+  if (GRID && p.plan) {
+    if (blockIdx.x >= *p.plan_n) return;
+    const unsigned e = __ldg(p.plan + blockIdx.x);
+    bx = (int)(e & 0xfffu); by = (int)((e >> 12) & 0xfffu);
+    if ((e >> 27) & 1u) sub = (int)((e >> 24) & 7u);   // a split block: this launch takes one pixel column of every patch
+  }
+  // (kept in shared memory: two registers held over the whole kernel made it spill)
+  __shared__ unsigned s_cost_t0[GRID ? NRING : 1];
+  __shared__ int s_cost_at[GRID ? NRING : 1];
+  __shared__ int s_split;
+  if (GRID && lane == 0) {
+    s_cost_t0[warp] = (unsigned)clock();     // 32 bits wrap after two seconds; a warp runs milliseconds
+    s_cost_at[warp] = by * p.gx + bx;
+    if (warp == 0) s_split = sub >= 0;       // (read after the block barrier below)
+  }
   // warp = 8x4 pixel patch; 8 warps tile a 16x16 block as 2 columns x 4 rows
-  const int u = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-  const int block_y = blockIdx.y * p.il_n + p.il_r;     // 16-row block of the range (interleaved launches)
+  const int u = bx * 16 + (warp & 1) * 8 + (lane & 7);
+  const int block_y = by * p.il_n + p.il_r;     // 16-row block of the range (interleaved launches)
   const int v = p.row0 + block_y * 16 + (warp >> 1) * 4 + (lane >> 3);
-  const bool live = (u < p.W) && (v < p.row1);
+  const bool live = (u < p.W) && (v < p.row1) && (sub < 0 || (lane & 7) == sub);
   const size_t pid = (size_t)v * p.W + u;
   const size_t origin_stride = (size_t)((p.n_tris + RT_TILE - 1) / RT_TILE) * RT_TILE * RT_REC_F4;
 
@@ -333,7 +350,7 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
 
     RtCursor cursor = rt_cursor_scene(p.planes, p.n_tris);   // origin 0
     if (GRID) {
-      if (issuer) s_cells[0] = block_y * gridDim.x + blockIdx.x;   // this block's own cell
+      if (issuer) s_cells[0] = block_y * (GRID ? p.gx : (int)gridDim.x) + bx;   // this block's own cell
       ring_sync();
       cursor = rt_cursor_cells(s_cells, warp_live ? 1 : 0);
     }
@@ -558,7 +575,7 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
       for (int i = lane; i < RT_SEEN; i += 32) s_seen[i] = -1;
       if (lane == 0) s_ncells = 0;
       __syncwarp();
-      const int cell_base = (int)gridDim.x * p.blocks_y + l * 6 * RT_GRID_FACE;
+      const int cell_base = (GRID ? p.gx : (int)gridDim.x) * p.blocks_y + l * 6 * RT_GRID_FACE;
       int last = -2;
       float lb0 = 0.f, lb1 = 0.f, lc0 = 0.f, lc1 = 0.f;   // the last cell's bounds on its face plane
 #pragma unroll(GRID ? 1 : 9)   // grid kernels: smaller code (their warps run out of step and miss in the instruction cache)
@@ -763,6 +780,8 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
   }
   rt_count(p.counters + 0, (unsigned long long)__popc(active) * p.n_lights);
   rt_count(p.counters + 1, (unsigned long long)n_exact);
+  if (GRID && p.block_cost && lane == 0)   // what the next frame's plan is made from
+    atomicMax(p.block_cost + s_cost_at[warp], (((unsigned)clock() - s_cost_t0[warp]) >> 8) * (s_split ? 8u : 1u));
 #ifdef RT_PROFILE_COUNTERS
   if (live) for (int i = 0; i < 6; ++i) atomicAdd(p.counters + 2 + i, (unsigned long long)prof_cnt[i + (i >= 2 ? 1 : 0)]);
   // diagnostic build only: the depth plane carries this pixel's shadow L1 test count, the index plane its exact evaluations

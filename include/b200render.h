@@ -176,6 +176,11 @@ int b200_set_stream(b200_ctx *ctx, void *cuda_stream);
  * not reset (`indirect` applies to every fragment).  Whole frames only (no row bands; a multi-GPU
  * context draws such frames on its first device). */
 #define B200_OPT_RAST_COLOUR_MODE 9
+/* Raytracer, gridded (large-scene) frames: 1 (default) = a frame that follows a gridded frame of the same shape
+ * runs its 16x16 pixel blocks in an order planned from that frame's measured block costs -- the few blocks that
+ * cost several times the mean first, and split into eight launches of four pixels per warp; 0 = launch order.
+ * Results are identical. */
+#define B200_OPT_RT_PLAN 10
 int b200_set_option(b200_ctx *ctx, int option, int value);
 
 /* Counters of the last render on this context (b200_get_stats synchronises). */

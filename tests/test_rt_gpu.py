@@ -293,3 +293,38 @@ def test_tessellated_frame_matches_the_plain_cornell_frame(b200, renderer, corne
     diff = np.abs(a["rgb"] - b["rgb"]).max(axis=-1)
     assert np.count_nonzero(diff > 1e-4) <= 0.01 * diff.size                    # shadow / tessellation edges only
     assert np.median(diff) <= 1e-6
+
+
+def test_planned_frames_split_blocks(b200, renderer):
+    """Gridded frames that follow a frame of the same shape run from a plan made of that frame's block costs:
+    expensive blocks first, split into eight launches of one pixel column per 8x4 patch.  With the split
+    threshold at the mean (b200_debug_rt_plan_heavy) about half the blocks of a small frame are split; every
+    frame must still be the oracle's, and the ray counts must not change."""
+    tris, sph = b200.scene_cornell_rt_tessellated(8)
+    W, H, f = 150, 110, 75.0
+    cam, R = h.f32(0.1, 0.0, -2.2, 1), h.yaw_R(0.3)
+    lights = [((0.3, -0.6, -0.2, 1), (9, 9, 9)), ((-0.4, 0.5, -0.9, 1), (4, 5, 6))]
+    want = h.oracle_rt_render(W, H, f, cam, R, h.lights_array(lights), tris, sph)
+    c = b200.make_camera(cam, f, R, W, H)
+    lib = b200.load_library()
+    renderer.set_option(b200.OPT_RT_GRID, 1)
+    try:
+        for n_l in (1, 2):
+            want_l = want if n_l == 2 else h.oracle_rt_render(W, H, f, cam, R, h.lights_array(lights[:1]), tris, sph)
+            for heavy in (1, 2, 0):
+                assert lib.b200_debug_rt_plan_heavy(renderer.ctx, heavy) == 0
+                launches = []
+                for frame in range(3):
+                    got = renderer.render_raytrace(tris, sph, c, lights[:n_l])
+                    st = renderer.stats()
+                    check_equal(got, want_l, f"{n_l} light(s), split above {heavy} x mean, frame {frame}")
+                    assert st["primary_rays"] == want_l["primary"] and st["shadow_rays"] == want_l["shadow"]
+                    launches.append(st["kernel_launches"])
+            renderer.set_option(b200.OPT_RT_PLAN, 0)
+            got = renderer.render_raytrace(tris, sph, c, lights[:n_l])
+            check_equal(got, want_l, "unplanned")
+            renderer.set_option(b200.OPT_RT_PLAN, 1)
+    finally:
+        lib.b200_debug_rt_plan_heavy(renderer.ctx, 0)
+        renderer.set_option(b200.OPT_RT_PLAN, 1)
+        renderer.set_option(b200.OPT_RT_GRID, 0)
