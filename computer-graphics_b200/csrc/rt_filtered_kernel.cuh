@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(RT_THREADS, GRID ? 2 : RT_MIN_BLOCKS) rt_filte
   __shared__ int s_split;
   if (GRID && lane == 0) {
     s_cost_t0[warp] = (unsigned)clock();     // 32 bits wrap after two seconds; a warp runs milliseconds
-    s_cost_at[warp] = by * p.gx + bx;
+    s_cost_at[warp] = ((p.row0 >> 4) + by * p.il_n + p.il_r) * p.gx + bx;   // by the block's place in the whole frame
     if (warp == 0) s_split = sub >= 0;       // (read after the block barrier below)
   }
   // warp = 8x4 pixel patch; 8 warps tile a 16x16 block as 2 columns x 4 rows

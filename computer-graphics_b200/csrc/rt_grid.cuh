@@ -248,15 +248,21 @@ __global__ void rt_grid_pad_kernel(const unsigned *__restrict__ cnt, unsigned *_
 // order or the split; a frame without a predecessor runs unplanned.
 constexpr int RT_PLAN_MAX_SPLIT = 2048;      // blocks that may be split
 constexpr unsigned RT_PLAN_HEAVY = 10;       // x the mean cost (measured on the 100 800-triangle frame: 4 .. 32 tried, N = 1 and 8)
-__global__ void __launch_bounds__(1024) rt_plan_kernel(const unsigned *__restrict__ cost, int gx, int n_blocks,
-                                                       unsigned *__restrict__ plan, unsigned *__restrict__ plan_n, unsigned heavy) {
+// cost[] is indexed by a block's place in the WHOLE frame (16-row block of the frame x block column), so that a
+// launch that renders another row range or another interleave class than the last one (the adaptive bands of a
+// multi-GPU context move from frame to frame) still finds what is known about its blocks; `first_row`, `il_n`,
+// `il_r` locate this launch's block rows in the frame.  A block without history counts as cheap.
+__global__ void __launch_bounds__(1024) rt_plan_kernel(const unsigned *__restrict__ cost_frame, int gx, int n_blocks, int first_row,
+                                                       int il_n, int il_r, unsigned *__restrict__ plan, unsigned *__restrict__ plan_n,
+                                                       unsigned heavy) {
+  auto cost_of = [&](int b) -> unsigned { return cost_frame[(size_t)(first_row + (b / gx) * il_n + il_r) * gx + b % gx]; };
   __shared__ unsigned long long s_sum;
   __shared__ unsigned s_heavy, s_base, s_warp[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { s_sum = 0; s_heavy = 0; }
   __syncthreads();
   unsigned long long sum = 0;
-  for (int b = threadIdx.x; b < n_blocks; b += 1024) sum += cost[b];
+  for (int b = threadIdx.x; b < n_blocks; b += 1024) sum += cost_of(b);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if (lane == 0) atomicAdd(&s_sum, sum);
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(1024) rt_plan_kernel(const unsigned *__restric
   unsigned long long limit = s_sum / (unsigned long long)n_blocks * heavy + 1ull;
   // how many are heavy?  More than the budget (not a frame with a few outliers): nothing is split
   unsigned mine = 0;
-  for (int b = threadIdx.x; b < n_blocks; b += 1024) mine += cost[b] > limit ? 1u : 0u;
+  for (int b = threadIdx.x; b < n_blocks; b += 1024) mine += cost_of(b) > limit ? 1u : 0u;
   if (mine) atomicAdd(&s_heavy, mine);
   __syncthreads();
   if (s_heavy > (unsigned)RT_PLAN_MAX_SPLIT) limit = ~0ull;
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(1024) rt_plan_kernel(const unsigned *__restric
   __syncthreads();
   // the heavy blocks, split, at the front
   for (int b = threadIdx.x; b < n_blocks; b += 1024) {
-    if (cost[b] <= limit) continue;
+    if (cost_of(b) <= limit) continue;
     const unsigned at = atomicAdd(&s_heavy, 1u);
     const unsigned e = (unsigned)(b % gx) | ((unsigned)(b / gx) << 12) | (1u << 27);
     for (unsigned c = 0; c < 8; ++c) plan[8 * at + c] = e | (c << 24);
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(1024) rt_plan_kernel(const unsigned *__restric
   // the others in their usual order
   for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
     const int b = b0 + threadIdx.x;
-    const bool other = b < n_blocks && cost[b] <= limit;
+    const bool other = b < n_blocks && cost_of(b) <= limit;
     const unsigned m = __ballot_sync(0xffffffffu, other);
     if (lane == 0) s_warp[warp] = __popc(m);
     __syncthreads();

@@ -322,28 +322,33 @@ int rt_launch_filtered(b200_ctx *ctx, const RtFrame &f, RtKParams &p) {
   if (use_grid) {
     // one private double-buffered ring per warp: records + triangle indices
     const size_t gsmem = (size_t)(RT_THREADS / 32) * 2 * RT_WTILE * (RT_REC_F4 * sizeof(float4) + sizeof(int)) + hit_smem;
-    // Block order and splits from the cost of the last gridded frame of the same shape (rt_plan_kernel); this frame
-    // leaves its own block costs for the next one.  Layout: cost[2][nb], plan[nb + 7 * RT_PLAN_MAX_SPLIT], plan_n.
+    // Block order and splits from the block costs of the last gridded frame (rt_plan_kernel); this frame leaves its
+    // own for the next one.  Costs are kept per block of the WHOLE frame (any row range / interleave class finds its
+    // blocks).  Layout: cost[2][frame blocks], plan[nb + 7 * RT_PLAN_MAX_SPLIT], plan_n.
     const unsigned nb = grid.x * grid.y;
     dim3 lgrid = grid;
     p.plan = nullptr; p.plan_n = nullptr; p.block_cost = nullptr; p.gx = (int)grid.x;
     if (grid.x <= 4096 && grid.y <= 4096 && ctx->opt_rt_plan) {
+      const size_t frame_blocks = (size_t)grid.x * (size_t)((f.H + 15) / 16 + 1);
       const size_t plan_cap = (size_t)nb + 7 * (size_t)RT_PLAN_MAX_SPLIT;
-      if (int rc = ensure(ctx, ctx->rt_plan, sizeof(unsigned) * (2 * (size_t)nb + plan_cap + 4))) return rc;
-      unsigned *cost = (unsigned *)ctx->rt_plan.p, *plan = cost + 2 * (size_t)nb, *plan_n = plan + plan_cap;
-      const unsigned long long shape = ((unsigned long long)nb << 32) ^ ((unsigned long long)grid.x << 16) ^ (unsigned long long)(f.row0 * 131 + p.il_n * 17 + p.il_r) ^
-                                       ((unsigned long long)n << 40) ^ ((unsigned long long)f.n_lights << 60);
+      // (sized for the whole frame whatever this launch's share: a buffer that grew would lose the cost history)
+      const size_t plan_room = frame_blocks + 7 * (size_t)RT_PLAN_MAX_SPLIT;
+      const void *before = ctx->rt_plan.p;
+      if (int rc = ensure(ctx, ctx->rt_plan, sizeof(unsigned) * (2 * frame_blocks + plan_room + 4))) return rc;
+      if (ctx->rt_plan.p != before) ctx->rt_plan_valid = 0;
+      unsigned *cost = (unsigned *)ctx->rt_plan.p, *plan = cost + 2 * frame_blocks, *plan_n = plan + plan_room;
+      const unsigned long long shape = ((unsigned long long)f.W << 44) ^ ((unsigned long long)f.H << 28) ^ ((unsigned long long)n << 4) ^ (unsigned long long)f.n_lights;
       const bool planned = ctx->rt_plan_shape == shape && ctx->rt_plan_valid;
       const int cur = planned ? ctx->rt_plan_flip ^ 1 : 0;
-      CU_CHECK(ctx, cudaMemsetAsync(cost + (size_t)cur * nb, 0, sizeof(unsigned) * nb, ctx->stream));
+      CU_CHECK(ctx, cudaMemsetAsync(cost + (size_t)cur * frame_blocks, 0, sizeof(unsigned) * frame_blocks, ctx->stream));
       if (planned) {
-        rt_plan_kernel<<<1, 1024, 0, ctx->stream>>>(cost + (size_t)(cur ^ 1) * nb, (int)grid.x, (int)nb, plan, plan_n,
-                                                    ctx->rt_plan_heavy ? (unsigned)ctx->rt_plan_heavy : RT_PLAN_HEAVY);
+        rt_plan_kernel<<<1, 1024, 0, ctx->stream>>>(cost + (size_t)(cur ^ 1) * frame_blocks, (int)grid.x, (int)nb, f.row0 >> 4, p.il_n, p.il_r,
+                                                    plan, plan_n, ctx->rt_plan_heavy ? (unsigned)ctx->rt_plan_heavy : RT_PLAN_HEAVY);
         ctx->stats.kernel_launches++;
         p.plan = plan; p.plan_n = plan_n;
         lgrid = dim3((unsigned)plan_cap);
       }
-      p.block_cost = cost + (size_t)cur * nb;
+      p.block_cost = cost + (size_t)cur * frame_blocks;
       ctx->rt_plan_shape = shape; ctx->rt_plan_valid = 1; ctx->rt_plan_flip = cur;
     }
     if (f.n_lights > 1)
