@@ -607,7 +607,7 @@ def run_b200_one(args, workload):
                 else:
                     m.draw_raster_band(room_h, boxes_h, cam, L, 0, H, whole.data_ptr())
 
-            for _ in range(max(6, args.warmup)):   # warm-up: buffers, pipelined sizes, adaptive bands, planned RT frames
+            for _ in range(max(12, args.warmup)):  # warm-up: buffers, pipelined sizes, adaptive bands (they move every other frame), planned RT frames
                 whole_frame()
             k = max(2, args.steps // 2)
             t0 = time.perf_counter()

@@ -440,7 +440,7 @@ int draw_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const
   // grids are built per launch).
   const int rows = row_end - row_begin;
   const bool gridded = ctx->opt_rt_grid == 1 || (ctx->opt_rt_grid == 0 && n_tris >= RT_GRID_AUTO_TRIS);
-  const int k = (!gridded && (size_t)rows * cam->width >= ((size_t)1 << 20)) ? B200_SLICES : 1;
+  const int k = (!gridded && (size_t)rows * cam->width >= B200_SLICE_MIN_PIXELS) ? B200_SLICES : 1;
   band_slices_begin(ctx, argb_out, (const uint32_t *)ctx->out_argb.p, row_begin, cam->width);
   int rc_loop = B200_OK;
   for (int i = 0; i < k && rc_loop == B200_OK; ++i) {

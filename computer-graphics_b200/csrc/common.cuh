@@ -67,6 +67,10 @@ __host__ __device__ __forceinline__ uint32_t put_pixel_argb(float r, float g, fl
 
 // ---- context -------------------------------------------------------------------
 #define B200_SLICES 4
+// Bands below this many pixels come back in one piece: four launches of a quarter of a ~1 Mpixel band (what one of
+// eight GPUs gets of a 4K frame) leave most of the GPU idle in each -- measured 0.15 -> 0.30 ms per band -- and
+// made the adaptive bands of a multi-GPU context oscillate around the threshold.
+#define B200_SLICE_MIN_PIXELS ((size_t)3 << 20)
 constexpr int RAST_UP_CHUNKS = 4;   // a large raster scene travels to the device in this many chunks (draw_raster_band)
 struct DevBuf {
   void *p = nullptr;

@@ -73,6 +73,7 @@ struct b200_multi {
   std::vector<int> edges[2];
   std::vector<float> cost[2];
   int edges_h[2] = {0, 0};
+  int rt_settled = 0;                   // the last raytraced frame ran on the same bands as the one before it
   int peer_ok = 0;                      // every pair of devices can address each other's memory
 };
 
@@ -281,7 +282,15 @@ int multi_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_
   if (row_begin < 0 || row_end > cam->height || row_begin > row_end) return ctx_fail(ctx, B200_EINVAL, "bad row band");
   const int rows = row_end - row_begin, n = mc->n;
   std::vector<int> edges;
-  multi_band_edges(mc->edges_h[0] == rows ? mc->edges[0] : std::vector<int>(), mc->cost[0], rows, n, 16, edges);
+  // Large scenes run their blocks from a plan made of the previous frame's block costs, which every device keeps
+  // for the rows IT rendered (rt_plan_kernel): the frame after a band moved is dearer on the rows it gained, and
+  // balancing on that cost sent the edges back and forth (8 GPUs, 100 800 triangles: costs +-50 % from frame to
+  // frame, never settled).  So the bands move only on the evidence of a frame that ran on the same bands as its
+  // predecessor -- every other frame while they are still converging.
+  const bool have = mc->edges_h[0] == rows && (int)mc->edges[0].size() == n + 1;
+  if (have && !mc->rt_settled) edges = mc->edges[0];
+  else multi_band_edges(have ? mc->edges[0] : std::vector<int>(), mc->cost[0], rows, n, 16, edges);
+  mc->rt_settled = have && edges == mc->edges[0];
   const size_t W = (size_t)cam->width;
   const int rc = multi_run(ctx, [&](int i) -> int {
     const int a = row_begin + edges[i], b = row_begin + edges[i + 1];

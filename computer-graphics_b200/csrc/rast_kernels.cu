@@ -1240,7 +1240,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     }
     // host-pointer entries: resolve in slices, each slice's packed rows leave for the host
     // while the next one is resolved (band_slice_done is a no-op otherwise)
-    const int k = (ctx->slice_host && (size_t)(row1 - row0) * W >= ((size_t)1 << 20)) ? B200_SLICES : 1;
+    const int k = (ctx->slice_host && (size_t)(row1 - row0) * W >= B200_SLICE_MIN_PIXELS) ? B200_SLICES : 1;
     for (int i = 0; i < k; ++i) {
       p.row0 = band_slice_edge(row0, row1 - row0, i, k, RS_H);
       p.row1 = band_slice_edge(row0, row1 - row0, i + 1, k, RS_H);
@@ -1404,7 +1404,7 @@ int rast_launch(b200_ctx *ctx, const camera_t *cam, const rast_light_t *light, i
     p.colour_n = n_acc;
     p.colour_rgb = (const float *)ctx->rast_colour_rgb.p;
   }
-  const int k = (ctx->slice_host && (size_t)(row1 - row0) * W >= ((size_t)1 << 20)) ? B200_SLICES : 1;
+  const int k = (ctx->slice_host && (size_t)(row1 - row0) * W >= B200_SLICE_MIN_PIXELS) ? B200_SLICES : 1;
   for (int i = 0; i < k; ++i) {
     p.row0 = band_slice_edge(row0, row1 - row0, i, k, fused ? RS_H : 8);
     p.row1 = band_slice_edge(row0, row1 - row0, i + 1, k, fused ? RS_H : 8);

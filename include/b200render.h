@@ -226,7 +226,7 @@ int draw_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_s
                   uint32_t *argb_out);
 
 /* Band variant: argb_out is band-sized, (row_end - row_begin) * W.  Frames of a
- * megapixel or more come back in slices copied on a second stream while the next
+ * three megapixels or more come back in slices copied on a second stream while the next
  * slice is rendered (pass pinned memory to benefit); the call returns when the
  * whole band is in argb_out. */
 int draw_raytrace_band(b200_ctx *ctx, const rt_triangle *tris, int n_tris,

@@ -373,10 +373,10 @@ def test_pipelined_clipped_lists_and_soup(b200, renderer):
 
 
 def test_sliced_framebuffer_return(b200, renderer):
-    """draw_raster(_band) returns megapixel frames in slices that overlap the resolve / post pass:
+    """draw_raster(_band) returns frames of three megapixels or more in slices that overlap the resolve / post pass:
     both strategies, against the quantised float frame of the plain path."""
     room, boxes = b200.scene_cornell_rast()
-    W, H, f = 1296, 1000, 700.0
+    W, H, f = 2064, 1840, 1250.0     # the band of H - 203 rows is still above the 3 Mi pixels from which frames are sliced
     cam = b200.make_camera(h.DEFAULT_RAST_CAM, f, h.identity_R(), W, H)
     L = b200.make_rast_light(h.DEFAULT_RAST_LIGHT["pos"], h.DEFAULT_RAST_LIGHT["power"], h.DEFAULT_RAST_LIGHT["indirect"])
     for scene in ((room, boxes), (room, np.zeros(0, h.RAST_TRI))):     # ordered tiles / scatter-resolve

@@ -210,11 +210,11 @@ def test_grid_full_size_matches_streaming_kernel(b200, renderer):
 
 
 def test_sliced_framebuffer_return(b200, renderer, cornell_rt):
-    """Frames of a megapixel or more come back from draw_raytrace(_band) in slices that overlap
+    """Frames of three megapixels or more come back from draw_raytrace(_band) in slices that overlap
     the rendering; the packed frame must equal the quantised float frame of the plain path."""
     tris, sph = cornell_rt
-    W, H = 1296, 1000       # not a multiple of the 16-row blocks
-    c = b200.make_camera(h.f32(0, 0, -3, 1), 640.0, h.identity_R(), W, H)
+    W, H = 2064, 1640       # 3.4 Mpixel (slices from 3 Mi pixels), not a multiple of the 16-row blocks
+    c = b200.make_camera(h.f32(0, 0, -3, 1), 1050.0, h.identity_R(), W, H)
     want = b200.quantise(renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS, want=("rgb",))["rgb"])
     got = renderer.draw_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
     assert np.array_equal(got, want)
