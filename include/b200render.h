@@ -225,7 +225,7 @@ int draw_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_s
                   int n_spheres, const camera_t *cam, const light_t *lights, int n_lights,
                   uint32_t *argb_out);
 
-/* Band variant: argb_out is band-sized, (row_end - row_begin) * W.  Frames of a
+/* Band variant: argb_out is band-sized, (row_end - row_begin) * W.  Frames of
  * three megapixels or more come back in slices copied on a second stream while the next
  * slice is rendered (pass pinned memory to benefit); the call returns when the
  * whole band is in argb_out. */

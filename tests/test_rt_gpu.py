@@ -213,7 +213,7 @@ def test_sliced_framebuffer_return(b200, renderer, cornell_rt):
     """Frames of three megapixels or more come back from draw_raytrace(_band) in slices that overlap
     the rendering; the packed frame must equal the quantised float frame of the plain path."""
     tris, sph = cornell_rt
-    W, H = 2064, 1640       # 3.4 Mpixel (slices from 3 Mi pixels), not a multiple of the 16-row blocks
+    W, H = 2064, 1700       # 3.5 Mpixel (slices from 3 Mi pixels; the band below: 3.02 Mi), not a multiple of the 16-row blocks
     c = b200.make_camera(h.f32(0, 0, -3, 1), 1050.0, h.identity_R(), W, H)
     want = b200.quantise(renderer.render_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS, want=("rgb",))["rgb"])
     got = renderer.draw_raytrace(tris, sph, c, h.DEFAULT_RT_LIGHTS)
