@@ -73,7 +73,7 @@ struct b200_multi {
   std::vector<int> edges[2];
   std::vector<float> cost[2];
   int edges_h[2] = {0, 0};
-  int rt_settled = 0;                   // the last raytraced frame ran on the same bands as the one before it
+  int settled[2] = {0, 0};              // the last frame of the kind ran on the same bands as the one before it
   int peer_ok = 0;                      // every pair of devices can address each other's memory
 };
 
@@ -129,7 +129,7 @@ static int multi_run(b200_ctx *ctx, const std::function<int(int)> &job) {
 // edges that would have equalised the previous frame's measured cost (piecewise-constant cost
 // per row inside each of its bands), on multiples of `align` rows.
 void multi_band_edges(const std::vector<int> &prev_edges, const std::vector<float> &prev_cost, int H, int n, int align,
-                      std::vector<int> &out) {
+                      std::vector<int> &out, double tolerance = 1.06) {
   out.assign(n + 1, 0);
   out[n] = H;
   bool usable = (int)prev_edges.size() == n + 1 && (int)prev_cost.size() == n && prev_edges[n] == H;
@@ -146,7 +146,7 @@ void multi_band_edges(const std::vector<int> &prev_edges, const std::vector<floa
     // changes cannot be pipelined from its predecessor, and timing noise must not move edges).
     float worst = 0.f;
     for (int i = 0; i < n; ++i) worst = prev_cost[i] > worst ? prev_cost[i] : worst;
-    if (worst * n <= 1.06 * total) { out = prev_edges; return; }
+    if (worst * n <= tolerance * total) { out = prev_edges; return; }
     int band = 0;
     double before = 0;   // cost of the bands in front of `band`
     for (int k = 1; k < n; ++k) {
@@ -288,9 +288,9 @@ int multi_raytrace(b200_ctx *ctx, const rt_triangle *tris, int n_tris, const rt_
   // frame, never settled).  So the bands move only on the evidence of a frame that ran on the same bands as its
   // predecessor -- every other frame while they are still converging.
   const bool have = mc->edges_h[0] == rows && (int)mc->edges[0].size() == n + 1;
-  if (have && !mc->rt_settled) edges = mc->edges[0];
+  if (have && !mc->settled[0]) edges = mc->edges[0];
   else multi_band_edges(have ? mc->edges[0] : std::vector<int>(), mc->cost[0], rows, n, 16, edges);
-  mc->rt_settled = have && edges == mc->edges[0];
+  mc->settled[0] = have && edges == mc->edges[0];
   const size_t W = (size_t)cam->width;
   const int rc = multi_run(ctx, [&](int i) -> int {
     const int a = row_begin + edges[i], b = row_begin + edges[i + 1];
@@ -329,7 +329,14 @@ int multi_raster(b200_ctx *ctx, const rast_triangle *room, int n_room, const ras
   if (row_begin < 0 || row_end > cam->height || row_begin > row_end) return ctx_fail(ctx, B200_EINVAL, "bad row band");
   const int rows = row_end - row_begin, n = mc->n;
   std::vector<int> edges;
-  multi_band_edges(mc->edges_h[1] == rows ? mc->edges[1] : std::vector<int>(), mc->cost[1], rows, n, 8, edges);
+  // As for the raytracer, the bands move only on the evidence of a frame that ran on the bands of its predecessor:
+  // the frame after a move cannot be pipelined (two host waits, sometimes reallocations -- a 75 ms frame was seen
+  // on 8 GPUs when all devices grew their buffers at once), and balancing on its cost kept the edges moving.  The
+  // tolerance is wider than the raytracer's: a band costs 0.10 - 0.12 ms, of which timing noise is a tenth.
+  const bool have = mc->edges_h[1] == rows && (int)mc->edges[1].size() == n + 1;
+  if (have && !mc->settled[1]) edges = mc->edges[1];
+  else multi_band_edges(have ? mc->edges[1] : std::vector<int>(), mc->cost[1], rows, n, 8, edges, 1.12);
+  mc->settled[1] = have && edges == mc->edges[1];
   const bool colour = mc->child[0]->opt_rast_colour != 0;
   if (colour) edges.assign(n + 1, rows), edges[0] = 0;   // colour modes number the fragments of the whole frame: one device draws it
   const size_t W = (size_t)cam->width;
