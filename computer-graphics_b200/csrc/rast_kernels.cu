@@ -747,9 +747,10 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
   __shared__ int list[RAST_LIST_CAP];
   __shared__ float4 recA[RAST_BATCH][TS];
   __shared__ int recFlags[RAST_BATCH];
-  // TEX: texture | index << 8 of the staged triangles, and where their row records are (row_off - row0):
-  // a metal-grill / woven-wood fragment that passes the depth test needs its position for the opacity map
-  __shared__ int recTex[TEX ? RAST_BATCH : 1];
+  // TEX: texture and index of the staged triangles (the index in full: the reference leaves one uninitialised,
+  // TestModelH.h:254-257), and where their row records are (row_off - row0): a metal-grill / woven-wood fragment
+  // that passes the depth test needs its position for the opacity map
+  __shared__ int recTex[TEX ? RAST_BATCH : 1], recIdx[TEX ? RAST_BATCH : 1];
   __shared__ unsigned recRowBase[TEX ? RAST_BATCH : 1];
   __shared__ unsigned triRows[RAST_BATCH];   // per staged triangle: the tile rows in which its span meets the tile's columns
   __shared__ unsigned rowTris[TS];           // the transpose: per tile row, the staged triangles a pixel of that row has to look at
@@ -834,7 +835,8 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
       const int row0 = s->row0, nrows = s->nrows;
       if (lane == 0) recFlags[b] = s->flags;
       if (TEX && lane == 0) {
-        recTex[b] = (p.src[t].texture & 0xff) | (p.src[t].index << 8);
+        recTex[b] = p.src[t].texture;
+        recIdx[b] = p.src[t].index;
         recRowBase[b] = s->row_off - (unsigned)row0;
       }
       bool meets = false;
@@ -875,14 +877,14 @@ __global__ void __launch_bounds__(1 << (2 * TS_LOG2)) rast_fill_kernel(const __g
           } else if (zinv >= depth) {                                // :574
             bool hole = false;
             if (TEX) {
-              const int texture = p.colour_mode ? 0 : recTex[b] & 0xff;   // the colour modes never look at it (:575)
+              const int texture = p.colour_mode ? 0 : recTex[b];   // the colour modes never look at it (:575)
               if (texture == 2 || texture == 3) {                    // :603, :625: the opacity map decides
                 const float4 B = __ldg(p.rowsB + (recRowBase[b] + (unsigned)y));
                 const float fi = (float)(x - lx);
                 const float pz = xdiv(1.0f, zinv);                              // :546
                 const float px = xdiv(xadd(B.x, xmul(B.y, fi)), zinv);          // :547
                 const float py = xdiv(xadd(B.z, xmul(B.w, fi)), zinv);          // :548
-                hole = rast_tex_hole(p.tex, texture, recTex[b] >> 8, px, py, pz);
+                hole = rast_tex_hole(p.tex, texture, recIdx[b], px, py, pz);
               }
             }
             if (hole) {

@@ -101,6 +101,8 @@ def test_textured_random_clipped_lists(b200, textured, tex, seed):
     clipped = h.random_clipped_list(400, seed, W, H, f, shadow_frac=0.15, size=0.6)
     clipped["texture"] = rng.integers(0, 4, len(clipped))
     clipped["index"] = rng.integers(0, 6, len(clipped))     # 5: no branch of findU / findV, texel (0, 0)
+    clipped["index"][::7] = 0x01000003                      # garbage (the reference leaves one index uninitialised,
+    clipped["index"][3::11] = -7                            # TestModelH.h:254-257): no branch either
     clipped["texture"][clipped["color"][:, 0] < 0] = 0
     cam_pos, yaw = (0.2, -0.1, -1.5, 1.0), (0.0 if seed == 1 else 0.3)
     R = h.yaw_R(yaw) if yaw != 0 else h.identity_R()
