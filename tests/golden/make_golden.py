@@ -108,10 +108,24 @@ def make_rast_textured():
     print("textured rast goldens written")
 
 
+def make_reference_textures():
+    """The decoded pixels of the texture files in the reference's repository (rasteriser/Textures: metal grill and
+    woven wood; cv2 = the decoder cv::imread uses; the two opacity maps grey + thresholded like main() :148-155), so
+    that the GPU box -- which has neither the files nor /root/reference -- can draw with the real images
+    (helpers.reference_textures).  4 MiB compressed."""
+    tex = h.reference_textures(from_files=True)
+    assert tex is not None, "the reference's texture files (or cv2) are not here"
+    np.savez_compressed(os.path.join(HERE, "rast_reference_textures.npz"), **{k: tex[k] for k in h.TEX_IMAGES if k != "marble"})
+    print("reference textures written")
+
+
 if __name__ == "__main__":
-    if "textured" in sys.argv[1:]:
+    if "textures" in sys.argv[1:]:
+        make_reference_textures()
+    elif "textured" in sys.argv[1:]:
         make_rast_textured()
     else:
         make_rt()
         make_rast()
         make_rast_textured()
+        make_reference_textures()

@@ -302,6 +302,39 @@ def synthetic_textures(seed=7, noise_amp=0.01):
     return t
 
 
+def reference_textures(seed=7, from_files=False):
+    """The texture state the reference's main() builds (rasteriser/Source/skeleton.cpp:133-169) from the image
+    files of ITS repository: metal grill and woven wood, decoded with OpenCV (cv2: the decoder cv::imread uses)
+    and post-processed like :148-155 (BGR2GRAY, threshold 100 -> 0 / 255 on the two opacity maps).
+    Textures/Marble2000x2000.jpg (:135) is not in the repository: marble and normalMap_marble stay synthetic.
+    from_files: decode rasteriser/Textures/*.jpg here (None when the files or cv2 are missing); otherwise the
+    committed decoded pixels, tests/golden/rast_reference_textures.npz (tests/golden/make_golden.py textures)."""
+    t = synthetic_textures(seed)
+    if not from_files:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "rast_reference_textures.npz"))
+        for k in z.files:
+            t[k] = np.ascontiguousarray(z[k])
+        return t
+    d = "/root/reference/rasteriser/Textures"
+    try:
+        import cv2
+    except ImportError:
+        return None
+    names = {"grill": "Metal_Grill_002_basecolor.jpg", "grill_opacity": "Metal_Grill_002_opacity.jpg",
+             "grill_normal": "Metal_Grill_002_normal.jpg", "woven": "woven1024x1024.jpg",
+             "woven_occlusion": "Wood_wicker_003_ambientOcclusion.jpg", "woven_opacity": "Wood_wicker_003_opacity.jpg",
+             "woven_normal": "Wood_wicker_003_normal.jpg"}
+    for key, f in names.items():
+        im = cv2.imread(os.path.join(d, f), cv2.IMREAD_UNCHANGED)
+        if im is None:
+            return None
+        if key.endswith("opacity"):
+            gray = cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)
+            im = cv2.threshold(gray, 100, 255, cv2.THRESH_BINARY)[1].reshape(gray.shape[0], gray.shape[1], 1)
+        t[key] = np.ascontiguousarray(im)
+    return t
+
+
 def ref_rast_set_textures(W, H, tex, cam, R, yaw):
     lib = ref_lib(ref_rast_name(W, H))
     for i, name in enumerate(TEX_IMAGES):

@@ -250,3 +250,34 @@ def test_oracle_colour_modes_vs_compiled_reference(mode, cam, yaw, indirect):
     assert np.array_equal(ref["shadow"], o["shadow"]) and np.array_equal(ref["argb"], o["argb"])
     assert next_ref == next_o
     assert not np.any(o["low"]) and not np.any(o["high"])
+
+
+@pytest.mark.parametrize("setting,setting_boxes,cam,yaw", [(2, 3, h.DEFAULT_RAST_CAM, 0.0), (3, 2, (0.1, -0.05, -2.6, 1.0), 0.174533),
+                                                           (2, 1, h.DEFAULT_RAST_CAM, -0.349066)])
+def test_oracle_textures_with_the_reference_repository_images(setting, setting_boxes, cam, yaw):
+    """The same comparison on the images of the reference's own repository (metal grill, woven wood: decoded with
+    cv2, grey + threshold like main() :148-155; committed as tests/golden/rast_reference_textures.npz): real hole
+    patterns, real normal maps."""
+    W, H, f = 320, 240, 120.0
+    if not h.have_ref(h.ref_rast_name(W, H)):
+        pytest.skip("oracle/_ref not built")
+    tex = h.reference_textures()          # the committed decoded pixels ...
+    assert set(np.unique(tex["grill_opacity"])) <= {0, 255} and tex["grill"].shape == (1024, 1024, 3)
+    files = h.reference_textures(from_files=True)
+    if files is not None:                 # ... are what decoding the reference's files here gives
+        for k in h.TEX_IMAGES:
+            assert np.array_equal(tex[k], files[k]), k
+    R = h.yaw_R(yaw) if yaw != 0 else h.identity_R()
+    room, boxes = h.ref_rast_testmodel_tex(setting, setting_boxes, W, H)
+    h.ref_rast_set_textures(W, H, tex, cam, R, yaw)
+    ref = h.ref_rast_draw(W, H, f, cam, R, h.DEFAULT_RAST_LIGHT, room, boxes)
+    try:
+        h.oracle_rast_set_textures(tex, cam, R, yaw)
+        o = h.oracle_rast_draw(W, H, f, cam, R, h.DEFAULT_RAST_LIGHT, room, boxes)
+    finally:
+        h.oracle_rast_set_textures(None)
+    for key in ("depth", "low", "high", "rgb", "screen_post"):
+        assert np.array_equal(bits(ref[key]), bits(o[key])), key
+    assert np.array_equal(ref["shadow"], o["shadow"]) and np.array_equal(ref["argb"], o["argb"])
+    holes = np.count_nonzero((o["depth"] == 0) & (o["index"] >= 0))
+    assert holes > 0 or setting_boxes == 1

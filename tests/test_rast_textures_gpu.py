@@ -261,3 +261,22 @@ def test_rasteriser_program_space_key_cycles_the_colour_modes():
         got = h.prog_run(f"libprog_rast_dropin_{size}.so", script)
         want = h.prog_run(f"libprog_rast_ref_{size}.so", script)
         assert np.array_equal(got, want), (script, np.count_nonzero(got != want))
+
+
+@pytest.mark.parametrize("setting,setting_boxes,W,H,f,cam_pos,yaw", [
+    (2, 3, 320, 240, 120.0, h.DEFAULT_RAST_CAM, 0.0), (3, 2, 320, 240, 120.0, (0.1, -0.05, -2.6, 1.0), 0.174533),
+    (2, 1, 900, 720, 512.0, h.DEFAULT_RAST_CAM, 0.0), (3, 3, 640, 480, 300.0, (0.0, 0.1, -1.6, 1.0), -0.349066)])
+def test_textures_of_the_reference_repository(b200, renderer, setting, setting_boxes, W, H, f, cam_pos, yaw):
+    """The metal-grill and woven-wood images of the reference's own repository (decoded pixels committed as
+    tests/golden/rast_reference_textures.npz; the oracle is pinned on the compiled reference with the same images by
+    tests/test_oracle_rast.py): real hole patterns and normal maps, incl. BASELINE config 2's resolution with the
+    settings the reference ships with (2, 1)."""
+    tex = h.reference_textures()
+    room, boxes = cornell(setting, setting_boxes)
+    renderer.set_textures(tex)
+    try:
+        check_draw(b200, renderer, tex, W, H, f, cam_pos, yaw, h.DEFAULT_RAST_LIGHT, room, boxes,
+                   f"reference images, textures {setting}/{setting_boxes}", buffers=W <= 320)
+    finally:
+        renderer.set_textures(None)
+        h.oracle_rast_set_textures(None)
