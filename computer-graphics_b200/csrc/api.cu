@@ -532,6 +532,7 @@ int rast_set_textures(b200_ctx *ctx, const rast_textures_t *tex) {
     total += ((size_t)im[k]->rows * (size_t)im[k]->step + 255) & ~(size_t)255;
   }
   if (!tex->marble_noise || tex->marble_noise_len < 1) return ctx_fail(ctx, B200_EINVAL, "marble_noise missing");
+  ctx->rast_tex_on = 0;   // until everything below has succeeded (the buffers may move: no stale pointers behind an error)
   if (int rc = ensure(ctx, ctx->rast_tex_images, total)) return rc;
   if (int rc = ensure(ctx, ctx->rast_tex_noise, (size_t)tex->marble_noise_len * sizeof(float4))) return rc;
   RastTex &t = ctx->rast_tex;
