@@ -104,7 +104,8 @@ void b200_destroy(b200_ctx *ctx) {
                     &ctx->rast_setup, &ctx->rast_rowsA, &ctx->rast_rowsB, &ctx->rast_bins, &ctx->rast_tile_count, &ctx->rast_tile_bits,
                     &ctx->rast_tmp, &ctx->rast_keys, &ctx->rast_trimeta, &ctx->rast_big, &ctx->rast_orig, &ctx->rast_shadow8, &ctx->rast_srowsB, &ctx->rast_srowsL, &ctx->rast_chunks, &ctx->rast_world, &ctx->rast_geom_tmp, &ctx->rast_screen, &ctx->rast_low, &ctx->rast_high, &ctx->rast_shadow,
                     &ctx->rast_depth, &ctx->rast_index, &ctx->out_rgb, &ctx->out_depth, &ctx->out_index,
-                    &ctx->out_argb, &ctx->counters};
+                    &ctx->out_argb, &ctx->counters, &ctx->rt_plan, &ctx->rt_cell_pairs, &ctx->rast_tex_images, &ctx->rast_tex_noise,
+                    &ctx->rast_colour_keys, &ctx->rast_colour_rgb, &ctx->rast_colour_tmp};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaEventDestroy(ctx->ev0);
