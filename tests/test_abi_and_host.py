@@ -280,3 +280,12 @@ def test_host_inverse_of_R_is_the_oracle_restatement_of_glm_inverse(b200):
 def test_texture_structs_match_the_header(b200):
     assert ctypes.sizeof(b200.RastImage) == 24            # pointer, three int32, padded to 8
     assert ctypes.sizeof(b200.RastTextures) == 8 * 24 + 16
+
+
+def test_option_constants_match_the_header(b200):
+    """Every B200_OPT_* of include/b200render.h has its twin in the ctypes plumbing, same value."""
+    header = open(os.path.join(ROOT, "include", "b200render.h")).read()
+    opts = dict(re.findall(r"^#define B200_(OPT_\w+)\s+(\d+)\s*(?:/\*.*)?$", header, re.M))
+    assert len(opts) >= 10
+    for name, value in opts.items():
+        assert getattr(b200, name) == int(value), name
